@@ -1,0 +1,712 @@
+// C-ABI of libmdacp_b200.so (include/mdacp_b200.h) and the per-step orchestration that
+// MDManager does in the reference (mdmanager.cc:116-349).  Host code only; kernels live in
+// cells.cu / exchange.cu / integrate.cu / force.cu / observe.cu.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+#include <algorithm>
+#include <set>
+#include <vector>
+#include "comm.h"
+#include "unit.h"
+
+namespace mdb {
+
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int check_device_error(Unit *u) {
+  const int e = u->ctrl_host->err;
+  if (e == 0) return MDB200_OK;
+  if (e & DE_TOOFAST) {
+    set_error("Too fast particles exists. Try smaller time step (unit %d)", u->prm.unit_id);
+    return MDB200_ETOOFAST;
+  }
+  if (e & DE_POSITION) {
+    set_error("Invalid position (unit %d)", u->prm.unit_id);
+    return MDB200_EPOSITION;
+  }
+  if (e & DE_CELL) {
+    set_error("Invalid index (unit %d)", u->prm.unit_id);
+    return MDB200_ECELL;
+  }
+  set_error("capacity exceeded (unit %d)", u->prm.unit_id);
+  return MDB200_ECAPACITY;
+}
+
+static int pull_error_word(Unit *u) {
+  MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->err, &u->ctrl->err, sizeof(int), cudaMemcpyDeviceToHost, u->stream));
+  MDB_CUDA(cudaStreamSynchronize(u->stream));
+  return check_device_error(u);
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// phase timing (mirrors the StopWatch objects of mdmanager.cc:117-147)
+// ---------------------------------------------------------------------------------------------
+enum Phase { PH_ALL = 0, PH_FORCE, PH_COMM, PH_PAIR, PH_INTEG, PH_CHECK };
+struct PhaseTimer {
+  Unit *u;
+  int ph;
+  cudaEvent_t a, b;
+  bool on;
+  PhaseTimer(Unit *u_, int ph_) : u(u_), ph(ph_), on(u_->profiling) {
+    if (!on) return;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, u->stream);
+  }
+  ~PhaseTimer() {
+    if (!on) return;
+    cudaEventRecord(b, u->stream);
+    cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    u->t_ms[ph] += ms;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+  }
+};
+
+// make every stream of the group wait for everything queued so far on the others
+static int stage_barrier(Unit **us, int n) {
+  std::vector<cudaStream_t> streams;
+  std::vector<int> devs;
+  for (int i = 0; i < n; i++) {
+    if (std::find(streams.begin(), streams.end(), us[i]->stream) == streams.end()) {
+      streams.push_back(us[i]->stream);
+      devs.push_back(us[i]->device);
+    }
+  }
+  if (streams.size() <= 1) return MDB200_OK;
+  std::vector<cudaEvent_t> evs(streams.size());
+  for (size_t k = 0; k < streams.size(); k++) {
+    DeviceGuard g(devs[k]);
+    MDB_CUDA(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming));
+    MDB_CUDA(cudaEventRecord(evs[k], streams[k]));
+  }
+  for (size_t k = 0; k < streams.size(); k++)
+    for (size_t j = 0; j < streams.size(); j++)
+      if (j != k) {
+        DeviceGuard g(devs[k]);
+        MDB_CUDA(cudaStreamWaitEvent(streams[k], evs[j], 0));
+      }
+  for (size_t k = 0; k < streams.size(); k++) cudaEventDestroy(evs[k]);
+  return MDB200_OK;
+}
+
+static void setup_consts(Unit *u) {
+  const mdb200_params &p = u->prm;
+  Consts &c = u->c;
+  for (int d = 0; d < 3; d++) {
+    c.L[d] = p.L[d];
+    // mdunit.cc:19-24
+    const double ul = p.L[d] / static_cast<double>(p.grid_size[d]);
+    c.s[d] = ul * static_cast<double>(p.grid_pos[d]);
+    c.e[d] = c.s[d] + ul;
+  }
+  c.dt = p.time_step;
+  c.dt2 = p.time_step * 0.5;
+  c.BL = p.buffer_length;
+  c.SL = p.cutoff + p.buffer_length;  // simulationinfo.cc:7
+  c.SL2 = c.SL * c.SL;
+  c.CL2 = p.cutoff * p.cutoff;
+  {
+    // variables.cc:21-27
+    const double s2 = 1.0 / (p.cutoff * p.cutoff);
+    const double s6 = s2 * s2 * s2;
+    const double s8 = s6 * s2;
+    const double s12 = s6 * s6;
+    const double s14 = s12 * s2;
+    c.C2 = 6.0 * s14 - 3.0 * s8;
+    c.C0 = -s12 + s6 - c.C2 / s2;
+  }
+  c.ncell = 1;
+  for (int d = 0; d < 3; d++) {
+    // meshlist.cc:31-55: ms = int(w / SL) interior cells of edge w/ms >= SL, one halo layer
+    const double w = c.e[d] - c.s[d];
+    int ms = static_cast<int>(w / c.SL);
+    if (ms < 1) ms = 1;
+    c.ms[d] = ms;
+    c.m[d] = ms + 2;
+    c.inv_edge[d] = 1.0 / (w / static_cast<double>(ms));
+    c.ncell *= c.m[d];
+  }
+  // periodic shifts applied when a ghost crosses the global box (mdunit.cc:141-163)
+  for (int dir = 0; dir < 6; dir++) {
+    for (int d = 0; d < 3; d++) u->shift[dir][d] = 0.0;
+    const int axis = dir / 2;
+    const bool low = (dir % 2 == 0);
+    const bool over = low ? (p.grid_pos[axis] == 0) : (p.grid_pos[axis] == p.grid_size[axis] - 1);
+    if (over) u->shift[dir][axis] = low ? p.L[axis] : -p.L[axis];  // ParaInfo::IsOverBoundary, parainfo.cc:256-275
+  }
+}
+
+static int reset_ctrl(Unit *u, bool keep_zeta) {
+  Ctrl h;
+  memset(&h, 0, sizeof(h));
+  h.buffer_length = u->c.BL;
+  (void)keep_zeta;
+  MDB_CUDA(cudaMemcpyAsync(u->ctrl, &h, sizeof(Ctrl), cudaMemcpyHostToDevice, u->stream));
+  MDB_CUDA(cudaStreamSynchronize(u->stream));
+  memset(u->ctrl_host, 0, sizeof(Ctrl));
+  return MDB200_OK;
+}
+
+__global__ void k_iota(int *a, int *b, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { a[i] = i; b[i] = i; }
+}
+__global__ void k_pack_host_rows(const double *__restrict__ src4, double4 *__restrict__ dst, int n, int zero_w) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 v = reinterpret_cast<const double4 *>(src4)[i];
+  if (zero_w) v.w = 0.0;
+  dst[i] = v;
+}
+__global__ void k_gather_ref_order(const double4 *__restrict__ src, const int *__restrict__ slot_of_ref,
+                                   double4 *__restrict__ dst, int pn, int tn) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= tn) return;
+  dst[r] = src[(r < pn) ? slot_of_ref[r] : r];
+}
+__global__ void k_gather_ref_order_i(const int *__restrict__ src, const int *__restrict__ slot_of_ref,
+                                     int *__restrict__ dst, int pn) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= pn) return;
+  dst[r] = src[slot_of_ref[r]];
+}
+
+// ---------------------------------------------------------------------------------------------
+// rebuild = MDManager::MakePairList (mdmanager.cc:262-280)
+// ---------------------------------------------------------------------------------------------
+static int make_pairlist(Unit **us, int n) {
+  std::vector<long long> cnt(n);
+  std::vector<PhaseTimer *> timers;
+  struct TimerScope {
+    std::vector<PhaseTimer *> &t;
+    ~TimerScope() { for (auto *x : t) delete x; }
+  } scope{timers};
+  for (int i = 0; i < n; i++) timers.push_back(new PhaseTimer(us[i], PH_PAIR));
+
+  // --- SendParticles (mdmanager.cc:251-259): six one-hop migrations, then the periodic wrap
+  for (int i = 0; i < n; i++) {
+    DeviceGuard g(us[i]->device);
+    us[i]->scratch_tail = std::max(us[i]->pn, us[i]->tn);
+    MDB_TRY(rebuild_begin_order(us[i]));
+  }
+  for (int dir = 0; dir < 6; dir++) {
+    for (int i = 0; i < n; i++) {
+      DeviceGuard g(us[i]->device);
+      MDB_TRY(migrate_flag_and_count(us[i], dir, &cnt[i]));
+    }
+    for (int i = 0; i < n; i++) {
+      DeviceGuard g(us[i]->device);
+      MDB_TRY(migrate_compact_pack(us[i], dir, cnt[i]));
+    }
+    MDB_TRY(stage_barrier(us, n));
+    MDB_TRY(comm_migrate(us, n, dir, cnt.data()));
+    MDB_TRY(stage_barrier(us, n));
+  }
+  for (int i = 0; i < n; i++) {
+    DeviceGuard g(us[i]->device);
+    MDB_TRY(wrap_periodic(us[i]));
+    // --- MeshList cell sort: locals become cell-ordered; tn := pn (mdmanager.cc:264-268)
+    MDB_TRY(cell_sort_locals(us[i]));
+  }
+  // --- border lists + first ghost exchange (mdmanager.cc:269-275)
+  for (int dir = 0; dir < 6; dir++) {
+    for (int i = 0; i < n; i++) {
+      DeviceGuard g(us[i]->device);
+      MDB_TRY(find_border(us[i], dir, &cnt[i]));
+    }
+    MDB_TRY(stage_barrier(us, n));
+    MDB_TRY(comm_border_setup(us, n, dir));
+    MDB_TRY(stage_barrier(us, n));
+  }
+  // --- per unit MDUnit::MakePairList (mdunit.cc:194-198)
+  for (int i = 0; i < n; i++) {
+    Unit *u = us[i];
+    DeviceGuard g(u->device);
+    MDB_TRY(bin_ghosts(u));
+    MDB_TRY(snapshot_positions(u));  // PairList::Init
+    MDB_TRY(build_pair_list(u));     // MeshList::MakeList
+    // PairList::Init: buffer_length = BufferLength, lifetime = 0
+    const double bl = u->c.BL;
+    MDB_CUDA(cudaMemcpyAsync(&u->ctrl->buffer_length, &bl, sizeof(double), cudaMemcpyHostToDevice, u->stream));
+    u->lifetime = 0;
+    u->list_initialized = true;
+    u->nbuilds++;
+    MDB_TRY(pull_error_word(u));
+  }
+  return MDB200_OK;
+}
+
+// MDManager::SendBorderParticles (mdmanager.cc:283-292)
+static int send_border_particles(Unit **us, int n) {
+  for (int dir = 0; dir < 6; dir++) {
+    MDB_TRY(comm_border_refresh(us, n, dir));
+    if (dir % 2 == 1) MDB_TRY(stage_barrier(us, n));
+  }
+  return MDB200_OK;
+}
+
+static int any_expired(Unit **us, int n, int *expired) {
+  int ex = 0;
+  bool uninit = false;
+  for (int i = 0; i < n; i++)
+    if (!us[i]->list_initialized) uninit = true;
+  if (uninit) {
+    ex = 1;  // pairlist.cc:27-29
+  } else {
+    for (int i = 0; i < n; i++) {
+      DeviceGuard g(us[i]->device);
+      PhaseTimer t(us[i], PH_CHECK);
+      MDB_TRY(expiry_check_launch(us[i]));
+    }
+    for (int i = 0; i < n; i++) {
+      DeviceGuard g(us[i]->device);
+      MDB_CUDA(cudaStreamSynchronize(us[i]->stream));
+      MDB_TRY(check_device_error(us[i]));
+      ex |= us[i]->ctrl_host->expired;
+    }
+  }
+  MDB_TRY(comm_allreduce_or(us, n, &ex));  // Communicator::AllReduceBoolean, mdmanager.cc:375
+  *expired = ex;
+  return MDB200_OK;
+}
+
+static int kinetic_temperature(Unit **us, int n, double *T) {
+  double tot[4] = {0, 0, 0, 0};
+  for (int i = 0; i < n; i++) {
+    DeviceGuard g(us[i]->device);
+    double o[4];
+    MDB_TRY(observe_kinetic(us[i], o));
+    tot[0] += o[0];
+    tot[3] += o[3];
+  }
+  MDB_TRY(comm_allreduce_sum(us, n, tot, 4));
+  *T = tot[0] / tot[3] / 1.5;  // mdmanager.cc:390-392, 403-407
+  return MDB200_OK;
+}
+
+// MDManager::Calculate (mdmanager.cc:116-148)
+static int calculate(Unit **us, int n) {
+  int expired = 0;
+  MDB_TRY(any_expired(us, n, &expired));
+  if (expired) MDB_TRY(make_pairlist(us, n));
+  for (int i = 0; i < n; i++) {
+    DeviceGuard g(us[i]->device);
+    PhaseTimer t(us[i], PH_INTEG);
+    MDB_TRY(drift_half(us[i]));
+  }
+  {
+    std::vector<PhaseTimer *> tm;
+    for (int i = 0; i < n; i++) tm.push_back(new PhaseTimer(us[i], PH_COMM));
+    int r = send_border_particles(us, n);
+    for (auto *x : tm) delete x;
+    MDB_TRY(r);
+  }
+  const bool ct = us[0]->prm.control_temperature != 0;
+  if (ct && us[0]->prm.heatbath_type == MDB200_HT_NOSEHOOVER) {
+    // MDManager::CalculateNoseHoover (mdmanager.cc:160-175)
+    double t = 0.0;
+    MDB_TRY(kinetic_temperature(us, n, &t));
+    for (int i = 0; i < n; i++) {
+      Unit *u = us[i];
+      DeviceGuard g(u->device);
+      const double tau = u->prm.heatbath_tau;
+      u->zeta += ((t - u->prm.aimed_temperature) / (tau * tau)) * u->c.dt2;  // fcalculator.cc:744-750
+      MDB_TRY(heatbath_momenta(u));
+      MDB_TRY(force_kick(u));
+      MDB_TRY(heatbath_momenta(u));
+    }
+    MDB_TRY(kinetic_temperature(us, n, &t));
+    for (int i = 0; i < n; i++) {
+      Unit *u = us[i];
+      DeviceGuard g(u->device);
+      const double tau = u->prm.heatbath_tau;
+      u->zeta += ((t - u->prm.aimed_temperature) / (tau * tau)) * u->c.dt2;
+      MDB_TRY(drift_half(u));
+    }
+  } else if (ct) {
+    // MDManager::CalculateLangevin (mdmanager.cc:186-192): no second half drift (finding 5)
+    for (int i = 0; i < n; i++) {
+      DeviceGuard g(us[i]->device);
+      { PhaseTimer t(us[i], PH_FORCE); MDB_TRY(force_kick(us[i])); }
+      MDB_TRY(langevin_kick(us[i]));
+    }
+  } else {
+    // MDManager::CalculateForce (mdmanager.cc:151-157)
+    for (int i = 0; i < n; i++) {
+      DeviceGuard g(us[i]->device);
+      { PhaseTimer t(us[i], PH_FORCE); MDB_TRY(force_kick(us[i])); }
+      { PhaseTimer t(us[i], PH_INTEG); MDB_TRY(drift_half(us[i])); }
+    }
+  }
+  for (int i = 0; i < n; i++) us[i]->step_count++;
+  return MDB200_OK;
+}
+
+}  // namespace mdb
+
+using namespace mdb;
+
+// =============================================================================================
+// C-ABI
+// =============================================================================================
+extern "C" {
+
+int mdb200_abi_version(void) { return MDB200_ABI_VERSION; }
+const char *mdb200_last_error(void) { return g_err; }
+
+int mdb200_device_count(int *count) {
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) {
+    *count = 0;
+    set_error("no CUDA device: %s", cudaGetErrorString(e));
+    return MDB200_ECUDA;
+  }
+  *count = c;
+  return MDB200_OK;
+}
+
+int mdb200_create(const mdb200_params *params, int device, mdb200_unit **out) {
+  if (!params || !out) { set_error("null argument"); return MDB200_EINVAL; }
+  if (params->cutoff <= 0 || params->buffer_length <= 0 || params->time_step <= 0) {
+    set_error("cutoff, buffer_length and time_step must be positive");
+    return MDB200_EINVAL;
+  }
+  for (int d = 0; d < 3; d++)
+    if (params->grid_size[d] < 1 || params->grid_pos[d] < 0 || params->grid_pos[d] >= params->grid_size[d] ||
+        !(params->L[d] > 0)) {
+      set_error("bad grid or box along axis %d", d);
+      return MDB200_EINVAL;
+    }
+  int ndev = 0;
+  MDB_TRY(mdb200_device_count(&ndev));
+  if (device < 0 || device >= ndev) { set_error("device %d out of range (%d devices)", device, ndev); return MDB200_ECUDA; }
+  mdb200_unit *h = new mdb200_unit();
+  Unit *u = &h->u;
+  u->prm = *params;
+  u->device = device;
+  setup_consts(u);
+  for (int d = 0; d < 3; d++) {
+    const double w = u->c.e[d] - u->c.s[d];
+    if (static_cast<int>(w / u->c.SL) < 1) {
+      delete h;
+      set_error("sub-box narrower than the search length along axis %d", d);
+      return MDB200_EINVAL;
+    }
+  }
+  DeviceGuard g(device);
+  MDB_CUDA(cudaStreamCreateWithFlags(&u->stream, cudaStreamNonBlocking));
+  u->own_stream = true;
+  MDB_CUDA(cudaMalloc(&u->ctrl, sizeof(Ctrl)));
+  MDB_CUDA(cudaMallocHost(&u->ctrl_host, sizeof(Ctrl)));
+  MDB_TRY(reset_ctrl(u, false));
+  for (int d = 0; d < 6; d++) { u->nbr[d] = nullptr; u->src[d] = nullptr; }
+  *out = h;
+  return MDB200_OK;
+}
+
+int mdb200_destroy(mdb200_unit *h) {
+  if (!h) return MDB200_OK;
+  Unit *u = &h->u;
+  DeviceGuard g(u->device);
+  cudaStreamSynchronize(u->stream);
+  comm_release(u);
+  u->q.release(); u->q_alt.release(); u->p.release(); u->p_alt.release();
+  u->type.release(); u->type_alt.release(); u->q0.release();
+  u->ref_of_slot.release(); u->slot_of_ref.release(); u->ord.release(); u->ord_alt.release();
+  u->flags.release(); u->scan.release(); u->scan_ws.release(); u->scan_ws64.release();
+  u->cell_of.release(); u->cell_count.release(); u->cell_start.release(); u->cell_cursor.release();
+  u->cell_items.release(); u->gcell_count.release(); u->gcell_start.release(); u->gcell_cursor.release();
+  u->gcell_items.release();
+  for (int d = 0; d < 6; d++) u->border[d].release();
+  u->send_buf.release(); u->mig_send_q.release(); u->mig_send_p.release(); u->mig_recv_q.release();
+  u->mig_recv_p.release(); u->mig_send_t.release(); u->mig_recv_t.release();
+  u->row_count.release(); u->warp_len.release(); u->warp_off.release(); u->list.release();
+  u->disp.release(); u->cand.release(); u->partial.release();
+  if (u->ctrl) cudaFree(u->ctrl);
+  if (u->ctrl_host) cudaFreeHost(u->ctrl_host);
+  if (u->own_stream) cudaStreamDestroy(u->stream);
+  delete h;
+  return MDB200_OK;
+}
+
+int mdb200_get_rect(mdb200_unit *h, double s[3], double e[3]) {
+  if (!h) return MDB200_EINVAL;
+  for (int d = 0; d < 3; d++) { s[d] = h->u.c.s[d]; e[d] = h->u.c.e[d]; }
+  return MDB200_OK;
+}
+
+int mdb200_upload(mdb200_unit *h, const double (*q)[4], const double (*p)[4], const int *type, long long pn) {
+  if (!h || pn < 0 || (pn > 0 && (!q || !p))) { set_error("bad upload arguments"); return MDB200_EINVAL; }
+  if (pn > 2000000000LL) { set_error("pn exceeds 32-bit index range"); return MDB200_ECAPACITY; }
+  Unit *u = &h->u;
+  DeviceGuard g(u->device);
+  // capacity: locals with head-room for migration, ghosts from the halo-shell volume ratio
+  long long need_p = std::max<long long>(u->prm.pn_capacity, pn);
+  double ratio = 1.0;
+  for (int d = 0; d < 3; d++) {
+    const double w = u->c.e[d] - u->c.s[d];
+    ratio *= (w + 2.0 * u->c.SL) / w;
+  }
+  long long need_t = std::max<long long>(u->prm.tn_capacity, (long long)(need_p * std::min(ratio, 27.0) * 1.05) + 1024);
+  MDB_TRY(ensure_capacity(u, need_p, need_t));
+  if (pn > 0) {
+    // stage through the alt buffers (device-side repack keeps lane 3 == 0)
+    MDB_CUDA(cudaMemcpyAsync(u->q_alt.ptr, q, sizeof(double) * 4 * (size_t)pn, cudaMemcpyHostToDevice, u->stream));
+    MDB_CUDA(cudaMemcpyAsync(u->p_alt.ptr, p, sizeof(double) * 4 * (size_t)pn, cudaMemcpyHostToDevice, u->stream));
+    const unsigned nb = (unsigned)((pn + 255) / 256);
+    k_pack_host_rows<<<nb, 256, 0, u->stream>>>((const double *)u->q_alt.ptr, u->q.ptr, (int)pn, 1);
+    k_pack_host_rows<<<nb, 256, 0, u->stream>>>((const double *)u->p_alt.ptr, u->p.ptr, (int)pn, 0);
+    if (type)
+      MDB_CUDA(cudaMemcpyAsync(u->type.ptr, type, sizeof(int) * (size_t)pn, cudaMemcpyHostToDevice, u->stream));
+    else
+      MDB_CUDA(cudaMemsetAsync(u->type.ptr, 0, sizeof(int) * (size_t)pn, u->stream));
+    k_iota<<<nb, 256, 0, u->stream>>>(u->ref_of_slot.ptr, u->slot_of_ref.ptr, (int)pn);
+    u->launches += 3;
+    MDB_CUDA(cudaGetLastError());
+  }
+  u->pn = pn;
+  u->tn = pn;
+  u->scratch_tail = pn;
+  u->list_initialized = false;
+  u->npairs = 0;
+  u->list_entries = 0;
+  for (int d = 0; d < 6; d++) { u->n_border[d] = 0; u->recv_cnt[d] = 0; u->recv_off[d] = pn; }
+  MDB_TRY(reset_ctrl(u, true));
+  MDB_CUDA(cudaStreamSynchronize(u->stream));
+  return MDB200_OK;
+}
+
+int mdb200_download(mdb200_unit *h, double (*q)[4], double (*p)[4], int *type, long long cap_rows, long long *pn,
+                    long long *tn) {
+  if (!h) return MDB200_EINVAL;
+  Unit *u = &h->u;
+  DeviceGuard g(u->device);
+  if (pn) *pn = u->pn;
+  if (tn) *tn = u->tn;
+  if (!q && !p && !type) return MDB200_OK;
+  if ((q && cap_rows < u->tn) || cap_rows < u->pn) {
+    set_error("download buffers too small: %lld rows, need pn %lld / tn %lld", cap_rows, u->pn, u->tn);
+    return MDB200_ECAPACITY;
+  }
+  if (u->tn == 0) return MDB200_OK;
+  const unsigned nbt = (unsigned)((u->tn + 255) / 256), nbp = (unsigned)((u->pn + 255) / 256);
+  if (q) {
+    k_gather_ref_order<<<nbt, 256, 0, u->stream>>>(u->q.ptr, u->slot_of_ref.ptr, u->q_alt.ptr, (int)u->pn, (int)u->tn);
+    u->launches++;
+    MDB_CUDA(cudaMemcpyAsync(q, u->q_alt.ptr, sizeof(double) * 4 * (size_t)u->tn, cudaMemcpyDeviceToHost, u->stream));
+  }
+  if (p && u->pn) {
+    k_gather_ref_order<<<nbp, 256, 0, u->stream>>>(u->p.ptr, u->slot_of_ref.ptr, u->p_alt.ptr, (int)u->pn, (int)u->pn);
+    u->launches++;
+    MDB_CUDA(cudaMemcpyAsync(p, u->p_alt.ptr, sizeof(double) * 4 * (size_t)u->pn, cudaMemcpyDeviceToHost, u->stream));
+  }
+  if (type && u->pn) {
+    k_gather_ref_order_i<<<nbp, 256, 0, u->stream>>>(u->type.ptr, u->slot_of_ref.ptr, u->type_alt.ptr, (int)u->pn);
+    u->launches++;
+    MDB_CUDA(cudaMemcpyAsync(type, u->type_alt.ptr, sizeof(int) * (size_t)u->pn, cudaMemcpyDeviceToHost, u->stream));
+  }
+  MDB_CUDA(cudaGetLastError());
+  MDB_CUDA(cudaStreamSynchronize(u->stream));
+  return MDB200_OK;
+}
+
+int mdb200_get_counts(mdb200_unit *h, long long *pn, long long *tn, long long *npairs, long long *nbuilds) {
+  if (!h) return MDB200_EINVAL;
+  if (pn) *pn = h->u.pn;
+  if (tn) *tn = h->u.tn;
+  if (npairs) *npairs = h->u.npairs;
+  if (nbuilds) *nbuilds = h->u.nbuilds;
+  return MDB200_OK;
+}
+
+int mdb200_comm_unique_id(void *out128) { return comm_unique_id(out128); }
+
+int mdb200_comm_init(mdb200_unit **units, int n, int nranks, int rank, const void *nccl_unique_id) {
+  if (!units || n < 1) { set_error("no units"); return MDB200_EINVAL; }
+  std::vector<Unit *> us(n);
+  for (int i = 0; i < n; i++) us[i] = &units[i]->u;
+  return comm_init(us.data(), n, nranks, rank, nccl_unique_id);
+}
+
+static int unpack_units(mdb200_unit **units, int n, std::vector<Unit *> &us) {
+  if (!units || n < 1) { set_error("no units"); return MDB200_EINVAL; }
+  us.resize(n);
+  for (int i = 0; i < n; i++) {
+    if (!units[i]) { set_error("null unit"); return MDB200_EINVAL; }
+    us[i] = &units[i]->u;
+  }
+  if (!us[0]->comm_ready) {
+    // a lone unit that was never wired: periodic self-neighbour in every direction
+    if (n == 1 && us[0]->prm.grid_size[0] * us[0]->prm.grid_size[1] * us[0]->prm.grid_size[2] == 1) {
+      MDB_TRY(comm_init(us.data(), 1, 1, 0, nullptr));
+    } else {
+      set_error("mdb200_comm_init has not been called for these units");
+      return MDB200_ECOMM;
+    }
+  }
+  return MDB200_OK;
+}
+
+int mdb200_make_pairlist(mdb200_unit **units, int n) {
+  std::vector<Unit *> us;
+  MDB_TRY(unpack_units(units, n, us));
+  return make_pairlist(us.data(), n);
+}
+
+int mdb200_step(mdb200_unit **units, int n, int nsteps) {
+  std::vector<Unit *> us;
+  MDB_TRY(unpack_units(units, n, us));
+  for (int s = 0; s < nsteps; s++) MDB_TRY(calculate(us.data(), n));
+  return MDB200_OK;
+}
+
+int mdb200_is_pairlist_expired(mdb200_unit **units, int n, int *expired) {
+  std::vector<Unit *> us;
+  MDB_TRY(unpack_units(units, n, us));
+  return any_expired(us.data(), n, expired);
+}
+
+int mdb200_update_position_half(mdb200_unit *h) {
+  if (!h) return MDB200_EINVAL;
+  DeviceGuard g(h->u.device);
+  return drift_half(&h->u);
+}
+
+int mdb200_send_border_particles(mdb200_unit **units, int n) {
+  std::vector<Unit *> us;
+  MDB_TRY(unpack_units(units, n, us));
+  return send_border_particles(us.data(), n);
+}
+
+int mdb200_calculate_force(mdb200_unit *h) {
+  if (!h) return MDB200_EINVAL;
+  if (!h->u.list_initialized) { set_error("pair list not built"); return MDB200_EINVAL; }
+  DeviceGuard g(h->u.device);
+  return force_kick(&h->u);
+}
+
+int mdb200_heatbath_zeta(mdb200_unit *h, double t) {
+  if (!h) return MDB200_EINVAL;
+  Unit *u = &h->u;
+  const double tau = u->prm.heatbath_tau;
+  u->zeta += ((t - u->prm.aimed_temperature) / (tau * tau)) * u->c.dt2;
+  return MDB200_OK;
+}
+int mdb200_heatbath_momenta(mdb200_unit *h) {
+  if (!h) return MDB200_EINVAL;
+  DeviceGuard g(h->u.device);
+  return heatbath_momenta(&h->u);
+}
+int mdb200_langevin(mdb200_unit *h) {
+  if (!h) return MDB200_EINVAL;
+  DeviceGuard g(h->u.device);
+  return langevin_kick(&h->u);
+}
+int mdb200_set_seed(mdb200_unit *h, int seed) {
+  if (!h) return MDB200_EINVAL;
+  h->u.seed = seed;
+  return MDB200_OK;
+}
+int mdb200_get_zeta(mdb200_unit *h, double *z) {
+  if (!h || !z) return MDB200_EINVAL;
+  *z = h->u.zeta;
+  return MDB200_OK;
+}
+int mdb200_set_zeta(mdb200_unit *h, double z) {
+  if (!h) return MDB200_EINVAL;
+  h->u.zeta = z;
+  return MDB200_OK;
+}
+int mdb200_set_control_temperature(mdb200_unit *h, int on) {
+  if (!h) return MDB200_EINVAL;
+  h->u.prm.control_temperature = on ? 1 : 0;
+  return MDB200_OK;
+}
+int mdb200_set_aimed_temperature(mdb200_unit *h, double t) {
+  if (!h) return MDB200_EINVAL;
+  h->u.prm.aimed_temperature = t;
+  return MDB200_OK;
+}
+
+int mdb200_observe_unit(mdb200_unit *h, double out[4]) {
+  if (!h || !out) return MDB200_EINVAL;
+  DeviceGuard g(h->u.device);
+  return observe_unit(&h->u, out);
+}
+
+int mdb200_observe(mdb200_unit **units, int n, double out[4]) {
+  std::vector<Unit *> us;
+  MDB_TRY(unpack_units(units, n, us));
+  double tot[4] = {0, 0, 0, 0};
+  for (int i = 0; i < n; i++) {
+    DeviceGuard g(us[i]->device);
+    double o[4];
+    MDB_TRY(observe_unit(us[i], o));
+    for (int k = 0; k < 4; k++) tot[k] += o[k];
+  }
+  MDB_TRY(comm_allreduce_sum(us.data(), n, tot, 4));
+  for (int k = 0; k < 4; k++) out[k] = tot[k];
+  return MDB200_OK;
+}
+
+int mdb200_get_pairs(mdb200_unit *h, int *key, int *partner, long long cap, long long *npairs) {
+  if (!h || !npairs) return MDB200_EINVAL;
+  DeviceGuard g(h->u.device);
+  return extract_pairs(&h->u, key, partner, cap, npairs);
+}
+
+int mdb200_get_impulse(mdb200_unit *h, double *f3, long long cap_rows) {
+  if (!h || !f3) return MDB200_EINVAL;
+  if (!h->u.list_initialized) { set_error("pair list not built"); return MDB200_EINVAL; }
+  DeviceGuard g(h->u.device);
+  return force_impulse(&h->u, f3, cap_rows);
+}
+
+int mdb200_timers(mdb200_unit *h, double out_ms[6], long long *out_launches, int reset) {
+  if (!h) return MDB200_EINVAL;
+  Unit *u = &h->u;
+  if (out_ms) for (int k = 0; k < 6; k++) out_ms[k] = u->t_ms[k];
+  if (out_launches) *out_launches = u->launches;
+  if (reset) {
+    for (int k = 0; k < 6; k++) u->t_ms[k] = 0.0;
+    u->launches = 0;
+  }
+  return MDB200_OK;
+}
+int mdb200_set_profiling(mdb200_unit *h, int on) {
+  if (!h) return MDB200_EINVAL;
+  h->u.profiling = on != 0;
+  return MDB200_OK;
+}
+int mdb200_synchronize(mdb200_unit *h) {
+  if (!h) return MDB200_EINVAL;
+  DeviceGuard g(h->u.device);
+  MDB_CUDA(cudaStreamSynchronize(h->u.stream));
+  return MDB200_OK;
+}
+
+}  // extern "C"

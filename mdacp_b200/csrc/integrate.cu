@@ -1,0 +1,305 @@
+// Elementwise integrators, thermostats and the Verlet-margin expiry test.
+//
+//   drift               ForceCalculator::UpdatePositionHalf   fcalculator.cc:22-32
+//   Nose-Hoover scaling ForceCalculator::HeatbathMomenta      fcalculator.cc:752-762
+//   Langevin            ForceCalculator::Langevin             fcalculator.cc:765-778
+//   expiry test         PairList::IsPairListExpired / UpdatePairListValidity /
+//                       CheckByDisplacement                   pairlist.cc:26-121
+//
+// Arithmetic that feeds decisions or is cheap to keep identical (drift, velocity budget,
+// displacement test) is written with explicit round-to-nearest mul/add intrinsics so no FMA
+// contraction happens: it then matches the scalar x86-64 reference bit for bit on equal inputs.
+// All kernels are HBM-bound streams: 64 B read + 32 B written per particle for the drift.
+#include <math.h>
+#include "unit.h"
+
+namespace mdb {
+
+static const int TPB = 256;
+static inline unsigned nblk(long long n, int tpb = TPB) {
+  long long b = (n + tpb - 1) / tpb;
+  return (unsigned)(b < 1 ? 1 : b);
+}
+
+__device__ __forceinline__ unsigned long long dbits(double v) { return (unsigned long long)__double_as_longlong(v); }
+__device__ __forceinline__ double bits_d(unsigned long long b) { return __longlong_as_double((long long)b); }
+
+__device__ __forceinline__ double block_max(double v, double *sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = sh[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); w++) r = fmax(r, sh[w]);
+  __syncthreads();
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// drift
+// ---------------------------------------------------------------------------------------------
+__global__ void k_drift_half(double4 *__restrict__ q, const double4 *__restrict__ p, int pn, double dt2) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pn) return;
+  double4 qq = q[i];
+  const double4 pp = p[i];
+  qq.x = __dadd_rn(qq.x, __dmul_rn(pp.x, dt2));
+  qq.y = __dadd_rn(qq.y, __dmul_rn(pp.y, dt2));
+  qq.z = __dadd_rn(qq.z, __dmul_rn(pp.z, dt2));
+  q[i] = qq;
+}
+
+int drift_half(Unit *u) {
+  if (u->pn == 0) return MDB200_OK;
+  k_drift_half<<<nblk(u->pn), TPB, 0, u->stream>>>(u->q.ptr, u->p.ptr, (int)u->pn, u->c.dt2);
+  u->launches++;
+  MDB_CUDA(cudaGetLastError());
+  return MDB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// thermostats
+// ---------------------------------------------------------------------------------------------
+__global__ void k_scale_p(double4 *__restrict__ p, int pn, double f) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pn) return;
+  double4 v = p[i];
+  v.x *= f; v.y *= f; v.z *= f; v.w *= f;  // all D = 4 lanes (fcalculator.cc:757-761)
+  p[i] = v;
+}
+
+int heatbath_momenta(Unit *u) {
+  if (u->pn == 0) return MDB200_OK;
+  // exp() evaluated on the host exactly where the reference evaluates it (fcalculator.cc:756)
+  const double exp1 = exp(-u->c.dt2 * u->zeta);
+  k_scale_p<<<nblk(u->pn), TPB, 0, u->stream>>>(u->p.ptr, (int)u->pn, exp1);
+  u->launches++;
+  MDB_CUDA(cudaGetLastError());
+  return MDB200_OK;
+}
+
+// Counter-based per-particle RNG (Philox4x32-10): the reference draws 3 normals per particle in
+// index order from one sequential std::mt19937 per unit (fcalculator.cc:772-777), which a
+// data-parallel kernel cannot reproduce bit-wise (SURVEY.md finding 5 / row a10).  Parity is
+// exact for AimedTemperature = 0 (noise amplitude 0) and statistical otherwise.
+__device__ __forceinline__ void philox_round(unsigned &c0, unsigned &c1, unsigned &c2, unsigned &c3, unsigned k0,
+                                             unsigned k1) {
+  const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  unsigned hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+  unsigned hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+  unsigned n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+  c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+}
+__device__ __forceinline__ void philox4x32(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0,
+                                           unsigned k1, unsigned out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    philox_round(c0, c1, c2, c3, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ double u01(unsigned hi, unsigned lo) {
+  // (0,1]: 53 random bits, never 0 so that log() is finite
+  unsigned long long b = (((unsigned long long)hi << 32) | lo) >> 11;
+  return ((double)b + 1.0) * (1.0 / 9007199254740992.0);
+}
+
+__global__ void k_langevin(double4 *__restrict__ p, const int *__restrict__ ref_of_slot, int pn, double gamma,
+                           double amp, double dt, unsigned key0, unsigned key1, unsigned step_lo,
+                           unsigned step_hi) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pn) return;
+  double n0 = 0.0, n1 = 0.0, n2 = 0.0;
+  if (amp != 0.0) {
+    unsigned r[4], s[4];
+    unsigned id = (unsigned)ref_of_slot[i];
+    philox4x32(id, step_lo, step_hi, 0u, key0, key1, r);
+    philox4x32(id, step_lo, step_hi, 1u, key0, key1, s);
+    double ua = u01(r[0], r[1]), ub = u01(r[2], r[3]);
+    double uc = u01(s[0], s[1]), ud = u01(s[2], s[3]);
+    double ra = sqrt(-2.0 * log(ua)), rc = sqrt(-2.0 * log(uc));
+    double sa, ca, sc, cc;
+    sincospi(2.0 * ub, &sa, &ca);
+    sincospi(2.0 * ud, &sc, &cc);
+    n0 = ra * ca; n1 = ra * sa; n2 = rc * cc;
+    (void)sc;
+  }
+  double4 v = p[i];
+  // p += (-gamma * p + xi) * dt, evaluated in the reference's operation order without FMA
+  v.x = __dadd_rn(v.x, __dmul_rn(__dadd_rn(__dmul_rn(-gamma, v.x), __dmul_rn(amp, n0)), dt));
+  v.y = __dadd_rn(v.y, __dmul_rn(__dadd_rn(__dmul_rn(-gamma, v.y), __dmul_rn(amp, n1)), dt));
+  v.z = __dadd_rn(v.z, __dmul_rn(__dadd_rn(__dmul_rn(-gamma, v.z), __dmul_rn(amp, n2)), dt));
+  p[i] = v;
+}
+
+int langevin_kick(Unit *u) {
+  if (u->pn == 0) return MDB200_OK;
+  const double dt = u->c.dt;
+  const double g = u->prm.heatbath_gamma;
+  const double T = u->prm.aimed_temperature;
+  const double amp = sqrt(2.0 * g * T / dt);  // hb_D, fcalculator.cc:771
+  unsigned long long sc = (unsigned long long)u->step_count;
+  unsigned key0 = (unsigned)(u->seed + u->prm.unit_id);  // MDUnit::SetSeed: seed + id (mdunit.h:58)
+  unsigned key1 = 0x6d646163u;                            // "mdac"
+  k_langevin<<<nblk(u->pn), TPB, 0, u->stream>>>(u->p.ptr, u->ref_of_slot.ptr, (int)u->pn, g, amp, dt, key0, key1,
+                                                  (unsigned)(sc & 0xffffffffu), (unsigned)(sc >> 32));
+  u->launches++;
+  MDB_CUDA(cudaGetLastError());
+  return MDB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// expiry test
+// ---------------------------------------------------------------------------------------------
+// Stage 1: velocity budget (pairlist.cc:34-36, 48-65).  max |p|^2 over locals; non-negative
+// doubles order like their bit patterns, so one 64-bit atomicMax per block suffices.  The last
+// block to finish does the scalar bookkeeping.
+__global__ void k_expiry_vmax(const double4 *__restrict__ p, int pn, Ctrl *ctrl, double dt, double BL) {
+  __shared__ double sh[TPB / 32];
+  __shared__ bool last;
+  double v = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pn; i += (long long)gridDim.x * blockDim.x) {
+    const double4 pp = p[i];
+    double s = __dadd_rn(__dadd_rn(__dmul_rn(pp.x, pp.x), __dmul_rn(pp.y, pp.y)), __dmul_rn(pp.z, pp.z));
+    v = fmax(v, s);
+  }
+  v = block_max(v, sh);
+  if (threadIdx.x == 0) {
+    atomicMax(&ctrl->vmax2_bits, dbits(v));
+    __threadfence();
+    unsigned t = atomicAdd(&ctrl->ticket[0], 1u);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double bl = ctrl->buffer_length;
+    if (bl > 0.0) {
+      double vmax = sqrt(bits_d(atomicAdd(&ctrl->vmax2_bits, 0ull)));
+      double dec = __dmul_rn(__dmul_rn(vmax, 2.0), dt);
+      if (dec > BL) atomicOr(&ctrl->err, (int)DE_TOOFAST);
+      bl = __dadd_rn(bl, -dec);
+      ctrl->buffer_length = bl;
+    }
+    ctrl->phase = (bl < 0.0) ? 1 : 0;
+    ctrl->expired = 0;
+    ctrl->vmax2_bits = 0ull;
+    ctrl->dr2max_bits = 0ull;
+    ctrl->cand_count = 0;
+    ctrl->ticket[0] = 0u;
+    ctrl->ticket[1] = 0u;
+    ctrl->ticket[2] = 0u;
+  }
+}
+
+// Stage 2: displacement since the snapshot over locals AND ghosts (pairlist.cc:69-83).
+__global__ void k_expiry_disp(const double4 *__restrict__ q, const double4 *__restrict__ q0,
+                              double *__restrict__ disp, int tn, Ctrl *ctrl, double BL) {
+  if (ctrl->phase == 0) return;
+  __shared__ double sh[TPB / 32];
+  __shared__ bool last;
+  double v = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tn; i += (long long)gridDim.x * blockDim.x) {
+    const double4 a = q0[i], b = q[i];
+    double dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+    double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    disp[i] = d2;
+    v = fmax(v, d2);
+  }
+  v = block_max(v, sh);
+  if (threadIdx.x == 0) {
+    atomicMax(&ctrl->dr2max_bits, dbits(v));
+    __threadfence();
+    unsigned t = atomicAdd(&ctrl->ticket[1], 1u);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double dmax = sqrt(bits_d(atomicAdd(&ctrl->dr2max_bits, 0ull)));
+    double cd = __dadd_rn(BL, -dmax);  // pairlist.cc:88
+    ctrl->c_d2 = __dmul_rn(cd, cd);
+  }
+}
+
+// Stage 3: candidates (pairlist.cc:90-97) and, by the last block, the candidate-pair test
+// (pairlist.cc:104-119).  Both outcomes depend only on the candidate SET, not on its order.
+__global__ void k_expiry_cand(const double4 *__restrict__ q, const double4 *__restrict__ q0,
+                              const double *__restrict__ disp, int *__restrict__ cand, int tn, int Nl, Ctrl *ctrl,
+                              double SL2, double CL2) {
+  if (ctrl->phase == 0) return;
+  __shared__ bool last;
+  __shared__ int hit;
+  const double c_d2 = ctrl->c_d2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tn; i += (long long)gridDim.x * blockDim.x) {
+    if (disp[i] > c_d2) {
+      int k = atomicAdd(&ctrl->cand_count, 1);
+      if (k < Nl) cand[k] = (int)i;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned t = atomicAdd(&ctrl->ticket[2], 1u);
+    last = (t == gridDim.x - 1);
+    hit = 0;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  const int cnt = atomicAdd(&ctrl->cand_count, 0);
+  if (cnt >= Nl) {
+    // pairlist.cc:93-95 returns true from inside the loop, which needs at least one candidate
+    if (threadIdx.x == 0) ctrl->expired = (cnt > 0) ? 1 : 0;
+    return;
+  }
+  const long long npair = (long long)cnt * (cnt - 1) / 2;
+  for (long long t = threadIdx.x; t < npair && !hit; t += blockDim.x) {
+    // unrank t -> (a,b), a < b
+    long long a = (long long)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while (a * (a + 1) / 2 > t) a--;
+    while ((a + 1) * (a + 2) / 2 <= t) a++;
+    long long b2 = t - a * (a + 1) / 2;  // b2 <= a ; pair (b2, a+1)
+    int i1 = cand[b2], i2 = cand[a + 1];
+    const double4 o1 = q0[i1], o2 = q0[i2];
+    double dx = o1.x - o2.x, dy = o1.y - o2.y, dz = o1.z - o2.z;
+    double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    if (d2 < SL2) continue;
+    const double4 n1 = q[i1], n2 = q[i2];
+    dx = n1.x - n2.x; dy = n1.y - n2.y; dz = n1.z - n2.z;
+    d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    if (d2 < CL2) hit = 1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) ctrl->expired = hit ? 1 : 0;
+}
+
+int expiry_check_launch(Unit *u) {
+  const int grid_p = (int)((u->pn + TPB - 1) / TPB) < 1 ? 1 : (int)(((u->pn + TPB - 1) / TPB) > 1184 ? 1184 : ((u->pn + TPB - 1) / TPB));
+  const int grid_t = (int)((u->tn + TPB - 1) / TPB) < 1 ? 1 : (int)(((u->tn + TPB - 1) / TPB) > 1184 ? 1184 : ((u->tn + TPB - 1) / TPB));
+  const int cll = u->prm.check_list_length;
+  const int Nl = (u->tn > cll) ? cll : (int)u->tn;  // pairlist.cc:85
+  MDB_TRY(u->cand.ensure((size_t)(cll > 0 ? cll : 1) + 1));
+  MDB_TRY(u->disp.ensure((size_t)u->cap_t + 1));
+  u->lifetime++;
+  k_expiry_vmax<<<grid_p, TPB, 0, u->stream>>>(u->p.ptr, (int)u->pn, u->ctrl, u->c.dt, u->c.BL);
+  k_expiry_disp<<<grid_t, TPB, 0, u->stream>>>(u->q.ptr, u->q0.ptr, u->disp.ptr, (int)u->tn, u->ctrl, u->c.BL);
+  k_expiry_cand<<<grid_t, TPB, 0, u->stream>>>(u->q.ptr, u->q0.ptr, u->disp.ptr, u->cand.ptr, (int)u->tn, Nl,
+                                               u->ctrl, u->c.SL2, u->c.CL2);
+  u->launches += 3;
+  MDB_CUDA(cudaGetLastError());
+  MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->expired, &u->ctrl->expired, 2 * sizeof(int), cudaMemcpyDeviceToHost,
+                           u->stream));  // expired + err (adjacent)
+  return MDB200_OK;
+}
+
+int expiry_check_local(Unit *u, int *expired) {
+  MDB_TRY(expiry_check_launch(u));
+  MDB_CUDA(cudaStreamSynchronize(u->stream));
+  *expired = u->ctrl_host->expired;
+  return MDB200_OK;
+}
+
+}  // namespace mdb

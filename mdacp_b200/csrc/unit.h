@@ -1,0 +1,219 @@
+// Internal state of one spatial unit (one reference MDUnit) on one B200.
+// Not part of the C-ABI (include/mdacp_b200.h is).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/mdacp_b200.h"
+
+namespace mdb {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+#define MDB_CUDA(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      mdb::set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e__), __FILE__,      \
+                     __LINE__, #call);                                                      \
+      return MDB200_ECUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+#define MDB_TRY(call)                  \
+  do {                                 \
+    int r__ = (call);                  \
+    if (r__ != MDB200_OK) return r__;  \
+  } while (0)
+
+// device-side error word (bit set by kernels, read back at sync points)
+enum DevErr : int { DE_TOOFAST = 1, DE_POSITION = 2, DE_CELL = 4, DE_CAPACITY = 8 };
+
+// ---------------------------------------------------------------------------------------------
+// growable device buffer
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+  T *ptr = nullptr;
+  size_t cap = 0;
+  int ensure(size_t n, bool keep = false, cudaStream_t st = 0) {
+    if (n <= cap) return MDB200_OK;
+    size_t ncap = n + n / 8 + 64;
+    T *np = nullptr;
+    MDB_CUDA(cudaMalloc(&np, ncap * sizeof(T)));
+    if (keep && ptr && cap) {
+      MDB_CUDA(cudaMemcpyAsync(np, ptr, cap * sizeof(T), cudaMemcpyDeviceToDevice, st));
+      MDB_CUDA(cudaStreamSynchronize(st));
+    }
+    if (ptr) cudaFree(ptr);
+    ptr = np;
+    cap = ncap;
+    return MDB200_OK;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+  }
+};
+
+// constants every kernel needs, passed by value
+struct Consts {
+  double L[3];
+  double s[3], e[3];     // sub-box (mdunit.cc:19-24)
+  double dt, dt2;        // TimeStep, TimeStep*0.5 (fcalculator.cc:23)
+  double CL2, SL2, SL;   // cutoff^2, search^2, search length
+  double C2, C0;         // variables.cc:21-27
+  double BL;             // BufferLength
+  // cell grid: interior ms[d] cells of edge w/ms >= SL plus one halo layer (meshlist.cc:31-55)
+  int ms[3];
+  int m[3];              // ms + 2
+  double inv_edge[3];
+  int ncell;
+};
+
+// scalar device-resident control block (one per unit)
+struct Ctrl {
+  double buffer_length;          // PairList::buffer_length (pairlist.h:15)
+  double c_d2;                   // (BufferLength - sqrt(dr2_max))^2, pairlist.cc:88-89
+  unsigned long long vmax2_bits; // max |p|^2 as ordered bits
+  unsigned long long dr2max_bits;
+  int phase;                     // 1 = displacement check active in this call
+  int cand_count;
+  int expired;
+  int err;                       // DevErr bits
+  unsigned int ticket[4];        // last-block tickets
+  int too_fast_index;
+  unsigned long long npairs;     // reference-style pair count of the current list
+  int max_row;
+  double obs[4];                 // K,U,W scratch
+  double zeta;                   // Variables::Zeta (variables.h:19)
+  int scratch[8];
+};
+
+struct Unit {
+  mdb200_params prm;
+  Consts c;
+  int device = 0;
+  cudaStream_t stream = 0;
+  bool own_stream = false;
+
+  long long pn = 0, tn = 0;       // Variables::particle_number / total_particle_number
+  long long cap_p = 0, cap_t = 0; // capacities (rows); sentinel particle lives at q[cap_t]
+  bool list_initialized = false;  // PairList::initialized (pairlist.h:25)
+  long long nbuilds = 0;          // MeshList::number_of_constructions
+  long long lifetime = 0;         // PairList::lifetime
+  long long step_count = 0;       // number of completed Calculate() calls
+  int seed = 0;                   // MDUnit::SetSeed
+  double zeta = 0.0;              // Variables::Zeta (variables.h:19)
+
+  // particle store, SLOT order: locals [0,pn) cell-sorted, ghosts [pn,tn) in arrival order
+  DevBuf<double4> q, q_alt;       // positions (x,y,z,0)
+  DevBuf<double4> p, p_alt;       // momenta of locals (px,py,pz,0)
+  DevBuf<int> type, type_alt;     // Variables::type of locals
+  DevBuf<double4> q0;             // PairList::qb_old snapshot (slot order)
+  DevBuf<int> ref_of_slot;        // reference index of the local in slot s
+  DevBuf<int> slot_of_ref;        // inverse
+  DevBuf<int> ord, ord_alt;       // rebuild scratch: handles (slots) in reference order
+  DevBuf<int> flags, scan;        // rebuild scratch
+  DevBuf<int> scan_ws;            // scan workspace
+  DevBuf<long long> scan_ws64;    // scan workspace (64-bit offsets)
+  long long scratch_tail = 0;     // first free slot while arrivals are appended during a rebuild
+
+  // cells
+  DevBuf<int> cell_of;            // per item
+  DevBuf<int> cell_count, cell_start, cell_cursor, cell_items;     // locals (items = ref idx)
+  DevBuf<int> gcell_count, gcell_start, gcell_cursor, gcell_items; // ghosts (items = slot)
+
+  // ghosts: per direction send list (slots) and receive window
+  DevBuf<int> border[6];
+  long long n_border[6] = {0, 0, 0, 0, 0, 0};
+  long long recv_off[6] = {0, 0, 0, 0, 0, 0}, recv_cnt[6] = {0, 0, 0, 0, 0, 0};
+  double shift[6][3];             // mdunit.cc:141-163
+  DevBuf<double4> send_buf;       // pack buffer for off-device neighbours
+  DevBuf<double4> mig_send_q, mig_send_p, mig_recv_q, mig_recv_p;
+  DevBuf<int> mig_send_t, mig_recv_t;
+
+  // full neighbour list, warp-interleaved: entry t of lane l of warp w at
+  // list[warp_off[w] + t*32 + l]; rows padded to the warp maximum with the sentinel index
+  DevBuf<int> row_count;          // listed partners per local slot
+  DevBuf<int> warp_len;
+  DevBuf<long long> warp_off;
+  DevBuf<int> list;
+  long long list_entries = 0;
+  long long npairs = 0;
+  int max_row = 0;
+
+  // expiry check
+  DevBuf<double> disp;            // PairList::disp
+  DevBuf<int> cand;               // candidate list (pairlist.cc:86-97)
+
+  // reductions
+  DevBuf<double> partial;         // per-block partial sums
+
+  Ctrl *ctrl = nullptr;           // device
+  Ctrl *ctrl_host = nullptr;      // pinned mirror
+
+  // neighbours resolved by mdb200_comm_init: pointer if the unit lives in this process
+  Unit *nbr[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // destination when sending in dir
+  Unit *src[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // source when receiving in dir (neighbour in opposite dir)
+  bool comm_ready = false;
+
+  // profiling
+  bool profiling = false;
+  double t_ms[6] = {0, 0, 0, 0, 0, 0};
+  long long launches = 0;
+  cudaEvent_t ev[8];
+  bool ev_ready = false;
+};
+
+inline int sentinel_index(const Unit *u) { return (int)u->cap_t; }
+
+// ---------------------------------------------------------------------------------------------
+// kernels / phases (host launchers; all asynchronous on u->stream unless stated)
+// ---------------------------------------------------------------------------------------------
+// scan.cu
+size_t scan_workspace_ints(long long n);
+int exclusive_scan_i32(const int *in, int *out, long long n, int *ws, cudaStream_t st, long long *launches);
+int exclusive_scan_i32_to_i64(const int *in, long long *out, long long n, long long *ws, cudaStream_t st,
+                              long long *launches, int scale);
+
+// cells.cu
+int ensure_capacity(Unit *u, long long need_p, long long need_t);
+int rebuild_begin_order(Unit *u);                                        // ord[r] = slot_of_ref[r]
+int migrate_flag_and_count(Unit *u, int dir, long long *n_leave);        // sync
+int migrate_compact_pack(Unit *u, int dir, long long n_leave);           // keepers compacted, leavers packed
+int migrate_unpack(Unit *dst, const double4 *rq, const double4 *rp, const int *rt, long long n);
+int wrap_periodic(Unit *u);
+int cell_sort_locals(Unit *u);
+int find_border(Unit *u, int dir, long long *n_border);                  // sync
+int bin_ghosts(Unit *u);
+int build_pair_list(Unit *u);                                            // sync (list size)
+int snapshot_positions(Unit *u);
+int extract_pairs(Unit *u, int *key, int *partner, long long cap, long long *npairs); // sync
+
+// exchange.cu
+int ghost_put(Unit *srcu, int dir, Unit *dstu, long long dst_off);       // dst.q[off+i] = src.q[border[i]] + shift
+int ghost_pack(Unit *srcu, int dir);                                     // into send_buf
+
+// integrate.cu
+int drift_half(Unit *u);
+int heatbath_momenta(Unit *u);
+int langevin_kick(Unit *u);
+int expiry_check_local(Unit *u, int *expired);                           // sync
+
+// force.cu
+int force_kick(Unit *u);
+int force_impulse(Unit *u, double *f3_host, long long cap_rows);         // sync
+
+// observe.cu
+int observe_unit(Unit *u, double out[4]);                                // sync
+
+}  // namespace mdb
+
+struct mdb200_unit {
+  mdb::Unit u;
+};
