@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include <algorithm>
+#include <map>
 #include <set>
 #include <vector>
 #include "comm.h"
@@ -418,8 +419,19 @@ int mdb200_create(const mdb200_params *params, int device, mdb200_unit **out) {
     }
   }
   DeviceGuard g(device);
-  MDB_CUDA(cudaStreamCreateWithFlags(&u->stream, cudaStreamNonBlocking));
-  u->own_stream = true;
+  // one stream per device for the whole process: units that share a device are then ordered
+  // by the stream itself when they hand particles to each other
+  {
+    static std::map<int, cudaStream_t> dev_stream;
+    auto it = dev_stream.find(device);
+    if (it == dev_stream.end()) {
+      cudaStream_t st;
+      MDB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      it = dev_stream.emplace(device, st).first;
+    }
+    u->stream = it->second;
+    u->own_stream = false;
+  }
   MDB_CUDA(cudaMalloc(&u->ctrl, sizeof(Ctrl)));
   MDB_CUDA(cudaMallocHost(&u->ctrl_host, sizeof(Ctrl)));
   MDB_TRY(reset_ctrl(u, false));

@@ -114,18 +114,8 @@ int comm_init(Unit **us, int n, int nranks, int rank, const void *unique_id) {
     set_error("multi-process runs take exactly one unit per process (got %d)", n);
     return MDB200_EINVAL;
   }
-  // units of one process that share a device share one stream: every hand-off is then ordered
-  // by the stream itself; units on different devices get peer access to each other
-  for (int i = 0; i < n; i++)
-    for (int j = 0; j < i; j++)
-      if (us[j]->device == us[i]->device && us[i]->stream != us[j]->stream) {
-        if (us[i]->own_stream) {
-          cudaSetDevice(us[i]->device);
-          cudaStreamDestroy(us[i]->stream);
-          us[i]->own_stream = false;
-        }
-        us[i]->stream = us[j]->stream;
-      }
+  // units of one process that share a device already share that device's stream (mdb200_create);
+  // units on different devices get peer access to each other
   for (int i = 0; i < n; i++)
     for (int j = 0; j < n; j++)
       if (us[i]->device != us[j]->device) {

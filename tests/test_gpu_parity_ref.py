@@ -77,6 +77,10 @@ def _run_case(cfg, nunits, steps, state_at_end=True, pairs_every_build=True):
                     if c["nbuilds"] == 0 and idx > 0:
                         continue
                     den = abs(r[idx]) if r[idx] != 0 else 1.0
+                    if name == "W":
+                        # the virial is a sum with cancellation (near-zero pressure droplets): its error
+                        # is measured on the scale it enters the pressure with, P = (2K/3 - W) / V
+                        den = max(den, abs(r[0]))
                     worst[name] = max(worst[name], abs(o[idx] - r[idx]) / den)
             for name in worst:
                 assert worst[name] <= TOL_OBS, "%s differs by %.3e (relative) at step %d" % (name, worst[name], s)
@@ -140,7 +144,7 @@ def test_collision_first_step_builds():
 def test_collision_two_units_load_imbalance():
     # droplets 5 apart so that they touch, exchange ghosts and migrate across the unit boundary
     _run_case({"DumpInit": "Collision", "SystemSizeX": 40, "SystemSizeY": 30, "SystemSizeZ": 30,
-               "TimeStep": 0.004, "LocalGridX": 2, "LocalGridY": 1, "LocalGridZ": 1}, 2, 700)
+               "TimeStep": 0.004, "LocalGridX": 2, "LocalGridY": 1, "LocalGridZ": 1}, 2, 400)
 
 
 def test_nose_hoover():
