@@ -59,6 +59,13 @@ __device__ __forceinline__ double pair_df(double r2, const ForceConsts &fc) {
   }
 }
 
+// one 256-bit load per gathered partner (LDG.E.256, sm_100+): a single L1 request per pair
+// instead of a 128-bit + 64-bit pair of requests that each walk the same 32 sectors
+__device__ __forceinline__ void ld_q256(const double4 *p, double &x, double &y, double &z) {
+  double w;
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(p));
+}
+
 template <int VARIANT, bool KICK>
 __global__ void __launch_bounds__(128)
 k_force(const double4 *__restrict__ q, double4 *__restrict__ p, double *__restrict__ fout,
@@ -81,10 +88,16 @@ k_force(const double4 *__restrict__ q, double4 *__restrict__ p, double *__restri
   for (int t = 0; t < len; t++) {
     const int j = jn;
     if (t + 1 < len) jn = __ldg(lp + (long long)(t + 1) * 32);
-    const double2 jxy = __ldg(reinterpret_cast<const double2 *>(q + j));
-    const double jz = __ldg(reinterpret_cast<const double *>(q + j) + 2);
-    const double dx = jxy.x - qxy.x;
-    const double dy = jxy.y - qxy.y;
+    double jx, jy, jz;
+    if (VARIANT >= 2) {
+      ld_q256(q + j, jx, jy, jz);
+    } else {
+      const double2 jxy = __ldg(reinterpret_cast<const double2 *>(q + j));
+      jx = jxy.x; jy = jxy.y;
+      jz = __ldg(reinterpret_cast<const double *>(q + j) + 2);
+    }
+    const double dx = jx - qxy.x;
+    const double dy = jy - qxy.y;
     const double dz = jz - qz;
     const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
     double df = pair_df<VARIANT>(r2, fc);
@@ -112,8 +125,8 @@ static int force_variant() {
   static int v = -1;
   if (v < 0) {
     const char *e = getenv("MDB200_FORCE_VARIANT");
-    v = e ? atoi(e) : 1;
-    if (v < 0 || v > 1) v = 1;
+    v = e ? atoi(e) : 2;
+    if (v < 0 || v > 2) v = 2;
   }
   return v;
 }
@@ -137,6 +150,9 @@ int force_kick(Unit *u) {
   if (force_variant() == 0)
     k_force<0, true><<<grid, tpb, 0, u->stream>>>(u->q.ptr, u->p.ptr, nullptr, u->list.ptr, u->warp_off.ptr,
                                                    u->warp_len.ptr, u->ref_of_slot.ptr, (int)u->pn, fc);
+  else if (force_variant() == 2)
+    k_force<2, true><<<grid, tpb, 0, u->stream>>>(u->q.ptr, u->p.ptr, nullptr, u->list.ptr, u->warp_off.ptr,
+                                                   u->warp_len.ptr, u->ref_of_slot.ptr, (int)u->pn, fc);
   else
     k_force<1, true><<<grid, tpb, 0, u->stream>>>(u->q.ptr, u->p.ptr, nullptr, u->list.ptr, u->warp_off.ptr,
                                                    u->warp_len.ptr, u->ref_of_slot.ptr, (int)u->pn, fc);
@@ -158,6 +174,9 @@ int force_impulse(Unit *u, double *f3_host, long long cap_rows) {
   ForceConsts fc = make_fc(u);
   if (force_variant() == 0)
     k_force<0, false><<<grid, tpb, 0, u->stream>>>(u->q.ptr, u->p.ptr, f.ptr, u->list.ptr, u->warp_off.ptr,
+                                                    u->warp_len.ptr, u->ref_of_slot.ptr, (int)u->pn, fc);
+  else if (force_variant() == 2)
+    k_force<2, false><<<grid, tpb, 0, u->stream>>>(u->q.ptr, u->p.ptr, f.ptr, u->list.ptr, u->warp_off.ptr,
                                                     u->warp_len.ptr, u->ref_of_slot.ptr, (int)u->pn, fc);
   else
     k_force<1, false><<<grid, tpb, 0, u->stream>>>(u->q.ptr, u->p.ptr, f.ptr, u->list.ptr, u->warp_off.ptr,
