@@ -4,11 +4,9 @@ Runs where oracle/_ref/mdacp_scalar exists (built by oracle/Makefile from /root/
 same comparisons against the committed fixtures live in tests/test_oracle_golden.py, so the pin
 also holds where the reference is absent.
 """
-import numpy as np
 import pytest
 
-from common import refdump, states_from_dump
-from oracle import pyoracle
+from common import check_oracle_against_records, refdump
 
 CASES = {
     "bench1": ({"DumpInit": "Benchmark", "SystemSize": 20, "TimeStep": 0.004, "InitialVelocity": 2.5}, 1, 120),
@@ -27,52 +25,6 @@ CASES = {
                     "ControlTemperature": "yes", "HeatbathType": "NoseHoover", "AimedTemperature": 1.0,
                     "HeatbathTau": 0.1}, 1, 60),
 }
-
-
-def check_oracle_against_records(rec, steps, init_build, seed=None):
-    """Replays a reference dump on the C oracle and asserts bit-equality everywhere."""
-    meta = refdump.meta_of(rec)
-    nu = meta["nunits"]
-    osys = pyoracle.System.from_meta(meta, capacity=60000)
-    try:
-        for u, st in enumerate(states_from_dump(rec, 0, nu)):
-            osys.set_unit(u, st["q"], st["p"], st["type"])
-        if seed is not None:
-            osys.set_seed(seed)
-        if init_build:
-            osys.make_pair_list()
-        last = [0] * nu
-        for s in range(steps + 1):
-            if s > 0:
-                osys.calculate(1)
-            for u in range(nu):
-                c = osys.counts(u)
-                assert c["nbuilds"] == rec["builds"][s, u]
-                assert c["pn"] == rec["pn"][s, u] and c["tn"] == rec["tn"][s, u]
-                o = osys.observe(u)
-                assert np.array_equal(o[:3], rec["obs_KUW"][s, u]), (s, u, o[:3], rec["obs_KUW"][s, u])
-                if c["nbuilds"] != last[u]:
-                    last[u] = c["nbuilds"]
-                    kname = "pair_key.s%d.u%d" % (s, u)
-                    if kname in rec:
-                        k, p = osys.pairs(u)
-                        assert np.array_equal(k, rec[kname])  # same ORDER, not only the same set
-                        assert np.array_equal(p, rec["pair_partner.s%d.u%d" % (s, u)])
-                if ("csr_list.s%d.u%d" % (s, u)) in rec:
-                    ptr, cnt, lst = osys.csr(u)
-                    assert np.array_equal(ptr, rec["csr_pointer.s%d.u%d" % (s, u)])
-                    assert np.array_equal(cnt, rec["csr_count.s%d.u%d" % (s, u)])
-                    assert np.array_equal(lst, rec["csr_list.s%d.u%d" % (s, u)])
-                if ("impulse.s%d.u%d" % (s, u)) in rec:
-                    assert np.array_equal(osys.impulse(u), rec["impulse.s%d.u%d" % (s, u)])
-                if ("q.s%d.u%d" % (s, u)) in rec and s > 0:
-                    st = osys.state(u)
-                    assert np.array_equal(st["q"], rec["q.s%d.u%d" % (s, u)])
-                    assert np.array_equal(st["p"], rec["p.s%d.u%d" % (s, u)])
-                    assert np.array_equal(st["type"], rec["type.s%d.u%d" % (s, u)])
-                    assert osys.zeta(u) == rec["zeta.s%d.u%d" % (s, u)][0]
-    finally:
-        osys.close()
 
 
 def dump_cfg(cfg, steps):
