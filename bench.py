@@ -1,0 +1,461 @@
+#!/usr/bin/env python
+"""bench.py -- LJ particle-updates/sec of the hot path (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps K --warmup W              # our arm (libmdacp_b200.so)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's own CPU path
+
+A "step" is one MDManager::Calculate() (mdmanager.cc:116-148) on the benchmark.cfg-shaped workload:
+FCC LJ, density 0.7, cutoff 3.0 (as shipped), dt 0.001, v0 1.0, one cubic unit of edge UNIT_LENGTH per
+GPU (284 -> 16,034,412 particles/GPU; BASELINE.json configs[1]/[2]); the timed window contains the
+margin-based pair-list rebuilds, the ghost refresh and an observation every 100 steps, exactly like
+the reference's Benchmark::Run window (benchmark.cc:28-45).  value = N_total * K / seconds.
+
+Rank 0 prints ONE JSON line (contract in the task statement): value (state resident in HBM), e2e
+(same metric through the C-ABI from/to pinned HOST buffers: upload + first list build + K steps +
+observation + download inside the timed region), roofline of the force kernel, cpu_baseline.
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "LJ particle-updates/sec"
+UNIT = "particle-updates/s"
+OBSERVE_LOOP = 100
+DENSITY = 0.7
+V0 = 1.0
+DT = 0.001
+CUTOFF = 3.0
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                d = json.load(f)
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 8:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                   f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.remove(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update({"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                        "samples": len(sm)})
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+# reference / CPU baseline
+# ------------------------------------------------------------------------------------------
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def cubic_units(cores):
+    """largest n^3 <= cores: Benchmark mode asserts cubic sub-boxes (confmaker.cc:181-182)"""
+    n = 1
+    while (n + 1) ** 3 <= cores:
+        n += 1
+    return n ** 3
+
+
+def run_reference_cpu(unit_length, n_gpus_equiv, therm, loop, timeout=1500):
+    """Times the reference's own CPU implementation (oracle/_ref, unmodified sources) on the host
+    cores: Mode=Benchmark on the SAME system as the GPU arm (global box = the GPU run's box), with
+    as many OpenMP units as fit a cubic grid.  Returns dict(value, cores, kind, sample, ...)."""
+    from oracle import refdump
+    from mdacp_b200 import driver
+    cores = host_cores()
+    units = cubic_units(cores)
+    # bounded sample: the CPU cannot hold the N-GPU weak-scaled system (N x 16 M particles), and its
+    # throughput does not grow with the box, so every N is compared with the one-GPU-sized box
+    g = [1, 1, 1]
+    L = [unit_length * g[0], unit_length * g[1], unit_length * g[2]]
+    cubic_box = (L[0] == L[1] == L[2])
+    if not cubic_box:
+        # the reference can only make cubic units: take the largest grid whose units are cubes
+        lg = [int(round(x / min(L))) for x in L]
+        k = 1
+        while (k + 1) ** 3 * lg[0] * lg[1] * lg[2] <= cores:
+            k += 1
+        lgrid = [k * x for x in lg]
+        units = lgrid[0] * lgrid[1] * lgrid[2]
+    else:
+        k = round(units ** (1.0 / 3.0))
+        lgrid = [k, k, k]
+    n_total = int(L[0] * L[1] * L[2] * DENSITY)
+    per_unit = n_total / units * 1.35 + 50000  # locals + ghosts
+    exe = refdump.REF_AVX2 if per_unit < 950000 else refdump.REF_AVX2_BIG
+    kind = "reference"
+    if not refdump.have_ref(exe):
+        return run_oracle_port_cpu(therm, loop)
+    cfg = ("Mode=Benchmark\nThermalizeLoop=%d\nTotalLoop=%d\nObserveLoop=%d\nTimeStep=%r\nInitialVelocity=%r\n"
+           "SystemSizeX=%r\nSystemSizeY=%r\nSystemSizeZ=%r\nLocalGridX=%d\nLocalGridY=%d\nLocalGridZ=%d\n" % (
+               therm, loop, OBSERVE_LOOP, DT, V0, L[0], L[1], L[2], lgrid[0], lgrid[1], lgrid[2]))
+    tmp = tempfile.mkdtemp(prefix="refbench_")
+    with open(os.path.join(tmp, "bench.cfg"), "w") as f:
+        f.write(cfg)
+    env = dict(os.environ)
+    env["OMP_NUM_THREADS"] = str(units)
+    env["OMP_PROC_BIND"] = "true"
+    t0 = time.time()
+    res = subprocess.run([exe, "bench.cfg"], cwd=tmp, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                         text=True, timeout=timeout)
+    wall = time.time() - t0
+    m = re.search(r"# N = (\d+) ([0-9.eE+-]+) \[SEC\] ([0-9.eE+-]+) \[MUPS\]", res.stdout)
+    if not m:
+        log("reference run failed:\n" + res.stdout[-2000:])
+        return {"value": None, "unit": UNIT, "cores": units, "kind": kind, "sample": "failed: " + res.stdout[-200:]}
+    n, sec, mups = int(m.group(1)), float(m.group(2)), float(m.group(3))
+    return {"value": mups * 1e6, "unit": UNIT, "cores": units, "kind": kind,
+            "sample": "unmodified reference (%s, AVX2 kernel, %d OpenMP units %dx%dx%d) Mode=Benchmark box %gx%gx%g "
+                      "N=%d, %d thermalise + %d timed steps; %.1f s timed, %.0f s wall incl. set-up; host %s, %d cores" % (
+                          os.path.basename(exe), units, lgrid[0], lgrid[1], lgrid[2], L[0], L[1], L[2], n, therm, loop,
+                          sec, wall, cpu_model(), cores),
+            "n": n, "sec": sec, "steps": loop}
+
+
+def run_oracle_port_cpu(therm, loop):
+    """Fallback when oracle/_ref is absent: the C restatement (oracle/liboracle.so), 8 OpenMP units,
+    on a bounded 2M-particle sample of the same lattice."""
+    import numpy as np
+    from oracle import pyoracle
+    from mdacp_b200 import hostlib
+    Ls = 142.0
+    osys = pyoracle.System([Ls] * 3, DT, grid=(2, 2, 2), cutoff=CUTOFF, capacity=600000)
+    n = 0
+    for u in range(8):
+        lo, hi = osys.rect(u)
+        q = hostlib.benchmark_config(lo, hi, DENSITY, u)
+        p = hostlib.initial_velocity(len(q), V0, u)
+        osys.set_unit(u, q, p)
+        n += len(q)
+    osys.make_pair_list()
+    osys.calculate(therm)
+    t0 = time.time()
+    osys.calculate(loop)
+    sec = time.time() - t0
+    osys.close()
+    return {"value": n * loop / sec, "unit": UNIT, "cores": min(8, host_cores()), "kind": "port",
+            "sample": "C oracle port, 2x2x2 units, box %g^3 N=%d, %d+%d steps, %.1f s; host %s" % (
+                Ls, n, therm, loop, sec, cpu_model()), "n": n, "sec": sec, "steps": loop}
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from mdacp_b200 import capi, driver, hostlib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        log("warning: WORLD_SIZE %d != --gpus %d" % (world, args.gpus))
+    if capi.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    uid = None
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        uid = bytes(buf.cpu().numpy().tobytes())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    UL = float(args.unit_length)
+    cfg = {"Mode": "Benchmark", "UnitLength": repr(UL), "TimeStep": repr(DT), "InitialVelocity": repr(V0)}
+    mdm = driver.MDManager(cfg, num_procs=world, rank=rank, num_threads=1, devices=[local_rank], unique_id=uid,
+                           cutoff=CUTOFF)
+    unit = mdm.GetMDUnit(0)
+    s, e = mdm.GetRect(0)
+    grid = mdm.pinfo.GetGridSize()
+
+    # --- synthetic input: the reference's own benchmark generator semantics (host side, C++) ---
+    t0 = time.time()
+    cap = int((e[0] - s[0]) * (e[1] - s[1]) * (e[2] - s[2]) * DENSITY) + 64
+    q_pin = torch.zeros((cap, 4), dtype=torch.float64).pin_memory()
+    p_pin = torch.zeros((cap, 4), dtype=torch.float64).pin_memory()
+    qh, ph = q_pin.numpy(), p_pin.numpy()
+    q0 = hostlib.benchmark_config(s, e, DENSITY, rank, out=qh)
+    n_local = q0.shape[0]
+    hostlib.initial_velocity(n_local, V0, rank, out=ph)
+    t_gen = time.time() - t0
+    n_total = int(allsum(float(n_local)))
+    log("[rank %d] unit %s box %s..%s  N_local=%d N_total=%d  (generated in %.1f s)" % (
+        rank, grid, [round(x, 3) for x in s], [round(x, 3) for x in e], n_local, n_total, t_gen))
+
+    # --- state resident in HBM: upload, first build, warm-up (untimed) ---
+    unit.upload4(qh[:n_local], ph[:n_local])
+    mdm.MakePairList()
+    W, K = args.warmup, args.steps
+    obs = None
+    for i in range(W):
+        mdm.Calculate()
+    unit.synchronize()
+    c0 = unit.counts()
+    npairs = c0["npairs"]
+
+    # --- timed region 1: `value` (K steps, rebuilds + ghost refresh + observations inside) ---
+    sampler = ClockSampler(local_rank)
+    unit.set_profiling(1)  # force kernel timed with CUDA events on the unit's stream, no extra syncs
+    unit.timers(reset=True)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    unit.event_record(0)
+    tw0 = time.time()
+    for i in range(K):
+        mdm.Calculate()
+        if i % OBSERVE_LOOP == 0:
+            obs = mdm.observables()  # T, P, E of benchmark.cc:34-40 (4 doubles back to the host)
+    unit.event_record(1)
+    unit.synchronize()
+    barrier()
+    tw1 = time.time()
+    ms_dev = unit.event_elapsed_ms(0, 1)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = allmax(ms_dev)
+    tm = unit.timers()
+    c1 = unit.counts()
+    unit.set_profiling(0)
+    launches = int(allsum(float(tm["launches"])))
+    value = n_total * K / (ms_total * 1e-3)
+    rebuilds = c1["nbuilds"] - c0["nbuilds"]
+    n_obs = (K + OBSERVE_LOOP - 1) // OBSERVE_LOOP
+
+    # --- roofline of the dominant kernel (force kick), measured live in the timed region above ---
+    peak, peak_src = measured_peaks()
+    P = npairs / max(n_local, 1)  # listed unordered pairs per particle (reference count)
+    f_ms = tm["force"] / max(tm["force_launches"], 1)
+    alg_bytes = (4.0 * P + 96.0) * n_local   # half-list indices + q read + p read/write
+    alg_flops = 30.0 * P * n_local
+    achieved = alg_bytes / (f_ms * 1e-3) / 1e9 if f_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "force_traffic.json")
+    if os.path.exists(tp):
+        try:
+            tj = json.load(open(tp))
+            # measured dram bytes per particle of the force kernel (ncu --set full), scaled to this launch
+            traffic = tj["dram_bytes_per_particle"] * n_local
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_force (LJ force kick)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                "peak_source": peak_src, "ms_per_launch": f_ms, "launches_timed": tm["force_launches"],
+                "algorithmic_bytes_per_particle": 4.0 * P + 96.0, "pairs_per_particle": P,
+                "force_share_of_step": (tm["force"] / ms_total) if ms_total else None,
+                "fp64": {"achieved_tflops": alg_flops / (f_ms * 1e-3) / 1e12 if f_ms > 0 else 0.0,
+                         "peak_tflops": 37.0, "peak_source": "nominal B200 FP64 (not in MEASURED_PEAKS.json)",
+                         "flops_per_pair": 30}}
+
+    # --- timed region 2: `e2e` through the C-ABI with HOST buffers ---
+    unit.download(want_type=False, out=(qh, ph))  # current state -> pinned host (untimed)
+    unit.synchronize()
+    barrier()
+    te0 = time.time()
+    unit.upload4(qh[:n_local], ph[:n_local])       # H2D inside the timed region
+    for i in range(K):
+        mdm.Calculate()                            # first call rebuilds the list (pairlist.cc:27-29)
+        if i % OBSERVE_LOOP == 0:
+            obs2 = mdm.observables()               # D2H of the observation
+    unit.download(want_type=False, out=(qh, ph))   # D2H of the final state
+    unit.synchronize()
+    barrier()
+    te1 = time.time()
+    e2e_s = allmax(te1 - te0)
+    e2e_val = n_total * K / e2e_s
+    h2d = (2 * n_local * 32) / K
+    d2h = ((n_local + c1["tn"]) * 32 + n_obs * 32) / K
+
+    out = None
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "benchmark.cfg-shaped LJ FCC, UnitLength=%g per GPU (%d particles/GPU), density 0.7, "
+                                   "cutoff 3.0 (as shipped), skin 0.3, dt 0.001, v0 1.0; unit grid %dx%dx%d; "
+                                   "BASELINE.json configs[%d]" % (UL, n_local, grid[0], grid[1], grid[2],
+                                                                  1 if world == 1 else 2),
+                       "n_particles": n_total, "rebuilds_in_window": rebuilds, "observations_in_window": n_obs,
+                       "l2": "inputs (%.1f GB of positions, momenta and pair list per GPU) far exceed the 126 MB L2; "
+                             "no flush needed" % ((n_local * 64 + (2 * npairs * 4.4)) / 1e9),
+                       "parallelism": "domain decomposition, one unit per GPU, NCCL halo" if world > 1 else "single unit",
+                       "timing": "CUDA events on the unit's stream, max over ranks; host wall %.3f s" % (tw1 - tw0)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "seconds": e2e_s, "includes": "upload from pinned host, first pair-list build, K steps, "
+                                                  "observations, download of q and p"},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "observables_last": obs,
+        }
+    mdm.close()
+    return out, rank, world
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--unit-length", type=float, default=float(os.environ.get("MDB200_BENCH_UNIT_LENGTH", "284")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        if rank != 0:
+            return 0
+        therm = max(3, min(args.warmup, 5))
+        loop = max(5, min(args.steps, 20))
+        r = run_reference_cpu(args.unit_length, args.gpus, therm, loop)
+        n_units = r.get("cores", 1)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": (r["sec"] / r["steps"] * 1e3) if r.get("sec") else None, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "benchmark.cfg-shaped LJ FCC on the host CPU, same box as the %d-GPU run "
+                                   "(UnitLength=%g per GPU), cutoff 3.0; each run a bounded sample: %d thermalise + %d "
+                                   "timed steps" % (args.gpus, args.unit_length, therm, loop)},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": n_units, "kind": r["kind"],
+                             "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line), flush=True)
+        return 0
+
+    out, rank, world = run_ours(args)
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                r = run_reference_cpu(args.unit_length, 1, 3, 12)
+                out["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                                       "sample": r["sample"]}
+            except Exception as ex:  # the baseline is reported, never required for the GPU number
+                out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": host_cores(), "kind": "reference",
+                                       "sample": "failed: %r" % (ex,)}
+        else:
+            out["cpu_baseline"] = None
+        print(json.dumps(out), flush=True)
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

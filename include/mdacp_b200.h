@@ -91,9 +91,9 @@ int mdb200_get_rect(mdb200_unit *u, double s[3], double e[3]);
 int mdb200_upload(mdb200_unit *u, const double (*q)[4], const double (*p)[4], const int *type,
                   long long pn);
 /* Device -> host Variables, in REFERENCE INDEX ORDER: exactly the order the reference's arrays
- * would hold after the same history of migrations (mdunit.cc:78-122).  q receives tn rows
- * (locals then ghosts), p and type receive pn rows.  Any of q/p/type may be NULL.
- * Capacities are in rows; MDB200_ECAPACITY if too small. */
+ * would hold after the same history of migrations (mdunit.cc:78-122).  q receives min(tn, cap_rows)
+ * rows (locals, then as many ghosts as fit), p and type receive pn rows.  Any of q/p/type may be
+ * NULL.  cap_rows is the row capacity of every non-NULL buffer; MDB200_ECAPACITY if cap_rows < pn. */
 int mdb200_download(mdb200_unit *u, double (*q)[4], double (*p)[4], int *type, long long cap_rows,
                     long long *pn, long long *tn);
 int mdb200_get_counts(mdb200_unit *u, long long *pn, long long *tn, long long *npairs,
@@ -156,10 +156,17 @@ int mdb200_get_impulse(mdb200_unit *u, double *f3, long long cap_rows);
 
 /* Device-side timing of the phases MDManager::Calculate wraps in StopWatch objects
  * (mdmanager.cc:117-147): accumulated milliseconds since the last reset and launch counts.
- * out_ms = {all, force, comm, pair, integrate, check}; out_launches = kernels launched. */
-int mdb200_timers(mdb200_unit *u, double out_ms[6], long long *out_launches, int reset);
+ * out_ms = {all, force, comm, pair, integrate, check}; out_counts = {kernels launched, force
+ * kernels timed}.
+ * Profiling level 1 times only the force kernel, with events resolved at the step's existing
+ * host synchronisation (no extra syncs); level 2 times every phase (adds a sync per phase). */
+int mdb200_timers(mdb200_unit *u, double out_ms[6], long long out_counts[2], int reset);
 /* Enable per-phase CUDA-event timing (adds event records to the stream; default off). */
 int mdb200_set_profiling(mdb200_unit *u, int on);
+/* CUDA-event stopwatch on the unit's stream (the stream every kernel of the unit is launched on):
+ * record slot 0..7, then elapsed milliseconds between two recorded slots (synchronises on b). */
+int mdb200_event_record(mdb200_unit *u, int slot);
+int mdb200_event_elapsed_ms(mdb200_unit *u, int slot_a, int slot_b, double *ms);
 /* Block until all work queued for the unit has finished. */
 int mdb200_synchronize(mdb200_unit *u);
 

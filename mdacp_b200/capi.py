@@ -24,7 +24,7 @@ SYMBOLS = [
     "mdb200_heatbath_zeta", "mdb200_heatbath_momenta", "mdb200_langevin", "mdb200_set_seed", "mdb200_get_zeta",
     "mdb200_set_zeta", "mdb200_set_control_temperature", "mdb200_set_aimed_temperature", "mdb200_observe",
     "mdb200_observe_unit", "mdb200_get_pairs", "mdb200_get_impulse", "mdb200_timers", "mdb200_set_profiling",
-    "mdb200_synchronize",
+    "mdb200_synchronize", "mdb200_event_record", "mdb200_event_elapsed_ms",
 ]
 
 
@@ -86,6 +86,8 @@ def lib():
         L.mdb200_timers.argtypes = [vp, dp, llp, C.c_int]
         L.mdb200_set_profiling.argtypes = [vp, C.c_int]
         L.mdb200_synchronize.argtypes = [vp]
+        L.mdb200_event_record.argtypes = [vp, C.c_int]
+        L.mdb200_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, dp]
         _lib = L
     return _lib
 
@@ -160,7 +162,9 @@ class Unit:
             q = np.zeros((rows, 4)) if want_q else None
             p = np.zeros((rows, 4)) if want_p else None
         else:
-            q, p = out
+            q, p = out  # caller's (possibly pinned) (n,4) buffers; ghosts are returned as far as they fit
+            rows = min(x.shape[0] for x in (q, p) if x is not None)
+            tn = min(tn, rows)
         t = np.zeros(rows, dtype=np.int32) if want_type else None
         a, b = C.c_longlong(), C.c_longlong()
         check(lib().mdb200_download(self.handle, _ptr(q), _ptr(p), _ptr(t), rows, C.byref(a), C.byref(b)))
@@ -211,16 +215,27 @@ class Unit:
     def zeta(self, v):
         check(lib().mdb200_set_zeta(self.handle, float(v)))
 
-    def set_profiling(self, on):
-        check(lib().mdb200_set_profiling(self.handle, 1 if on else 0))
+    def set_profiling(self, level):
+        """0 off; 1 force kernel only (no extra syncs); 2 / True every phase"""
+        level = 2 if level is True else int(level)
+        check(lib().mdb200_set_profiling(self.handle, level))
+
+    def event_record(self, slot):
+        check(lib().mdb200_event_record(self.handle, slot))
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_double()
+        check(lib().mdb200_event_elapsed_ms(self.handle, a, b, C.byref(ms)))
+        return ms.value
 
     def timers(self, reset=False):
         ms = (C.c_double * 6)()
-        n = C.c_longlong()
-        check(lib().mdb200_timers(self.handle, ms, C.byref(n), 1 if reset else 0))
+        n = (C.c_longlong * 2)()
+        check(lib().mdb200_timers(self.handle, ms, n, 1 if reset else 0))
         names = ["all", "force", "comm", "pair", "integrate", "check"]
         d = dict(zip(names, ms[:]))
-        d["launches"] = n.value
+        d["launches"] = n[0]
+        d["force_launches"] = n[1]
         return d
 
     def synchronize(self):

@@ -68,7 +68,7 @@ struct PhaseTimer {
   int ph;
   cudaEvent_t a, b;
   bool on;
-  PhaseTimer(Unit *u_, int ph_) : u(u_), ph(ph_), on(u_->profiling) {
+  PhaseTimer(Unit *u_, int ph_) : u(u_), ph(ph_), on(u_->profiling >= 2) {
     if (!on) return;
     cudaEventCreate(&a);
     cudaEventCreate(&b);
@@ -85,6 +85,31 @@ struct PhaseTimer {
     cudaEventDestroy(b);
   }
 };
+
+// level-1 profiling: two events around the force kernel, resolved at the next host sync
+static void force_timer_begin(Unit *u) {
+  if (u->profiling != 1) return;
+  if (!u->fev_ready) {
+    cudaEventCreate(&u->fev[0]);
+    cudaEventCreate(&u->fev[1]);
+    u->fev_ready = true;
+  }
+  cudaEventRecord(u->fev[0], u->stream);
+}
+static void force_timer_end(Unit *u) {
+  if (u->profiling != 1) return;
+  cudaEventRecord(u->fev[1], u->stream);
+  u->fev_pending = true;
+}
+static void force_timer_resolve(Unit *u) {
+  if (!u->fev_pending) return;
+  float ms = 0.f;
+  if (cudaEventSynchronize(u->fev[1]) == cudaSuccess && cudaEventElapsedTime(&ms, u->fev[0], u->fev[1]) == cudaSuccess) {
+    u->t_ms[PH_FORCE] += ms;
+    u->force_launches++;
+  }
+  u->fev_pending = false;
+}
 
 // make every stream of the group wait for everything queued so far on the others
 static int stage_barrier(Unit **us, int n) {
@@ -285,6 +310,7 @@ static int any_expired(Unit **us, int n, int *expired) {
     for (int i = 0; i < n; i++) {
       DeviceGuard g(us[i]->device);
       MDB_CUDA(cudaStreamSynchronize(us[i]->stream));
+      force_timer_resolve(us[i]);
       MDB_TRY(check_device_error(us[i]));
       ex |= us[i]->ctrl_host->expired;
     }
@@ -358,7 +384,12 @@ static int calculate(Unit **us, int n) {
     // MDManager::CalculateForce (mdmanager.cc:151-157)
     for (int i = 0; i < n; i++) {
       DeviceGuard g(us[i]->device);
-      { PhaseTimer t(us[i], PH_FORCE); MDB_TRY(force_kick(us[i])); }
+      {
+        PhaseTimer t(us[i], PH_FORCE);
+        force_timer_begin(us[i]);
+        MDB_TRY(force_kick(us[i]));
+        force_timer_end(us[i]);
+      }
       { PhaseTimer t(us[i], PH_INTEG); MDB_TRY(drift_half(us[i])); }
     }
   }
@@ -520,16 +551,17 @@ int mdb200_download(mdb200_unit *h, double (*q)[4], double (*p)[4], int *type, l
   if (pn) *pn = u->pn;
   if (tn) *tn = u->tn;
   if (!q && !p && !type) return MDB200_OK;
-  if ((q && cap_rows < u->tn) || cap_rows < u->pn) {
-    set_error("download buffers too small: %lld rows, need pn %lld / tn %lld", cap_rows, u->pn, u->tn);
+  if (cap_rows < u->pn) {
+    set_error("download buffers too small: %lld rows, need pn %lld (tn %lld)", cap_rows, u->pn, u->tn);
     return MDB200_ECAPACITY;
   }
   if (u->tn == 0) return MDB200_OK;
-  const unsigned nbt = (unsigned)((u->tn + 255) / 256), nbp = (unsigned)((u->pn + 255) / 256);
+  const long long qrows = cap_rows < u->tn ? cap_rows : u->tn;  // locals always, ghosts as far as they fit
+  const unsigned nbt = (unsigned)((qrows + 255) / 256), nbp = (unsigned)((u->pn + 255) / 256);
   if (q) {
-    k_gather_ref_order<<<nbt, 256, 0, u->stream>>>(u->q.ptr, u->slot_of_ref.ptr, u->q_alt.ptr, (int)u->pn, (int)u->tn);
+    k_gather_ref_order<<<nbt, 256, 0, u->stream>>>(u->q.ptr, u->slot_of_ref.ptr, u->q_alt.ptr, (int)u->pn, (int)qrows);
     u->launches++;
-    MDB_CUDA(cudaMemcpyAsync(q, u->q_alt.ptr, sizeof(double) * 4 * (size_t)u->tn, cudaMemcpyDeviceToHost, u->stream));
+    MDB_CUDA(cudaMemcpyAsync(q, u->q_alt.ptr, sizeof(double) * 4 * (size_t)qrows, cudaMemcpyDeviceToHost, u->stream));
   }
   if (p && u->pn) {
     k_gather_ref_order<<<nbp, 256, 0, u->stream>>>(u->p.ptr, u->slot_of_ref.ptr, u->p_alt.ptr, (int)u->pn, (int)u->pn);
@@ -698,20 +730,46 @@ int mdb200_get_impulse(mdb200_unit *h, double *f3, long long cap_rows) {
   return force_impulse(&h->u, f3, cap_rows);
 }
 
-int mdb200_timers(mdb200_unit *h, double out_ms[6], long long *out_launches, int reset) {
+int mdb200_timers(mdb200_unit *h, double out_ms[6], long long out_counts[2], int reset) {
   if (!h) return MDB200_EINVAL;
   Unit *u = &h->u;
+  {
+    DeviceGuard g(u->device);
+    force_timer_resolve(u);
+  }
   if (out_ms) for (int k = 0; k < 6; k++) out_ms[k] = u->t_ms[k];
-  if (out_launches) *out_launches = u->launches;
+  if (out_counts) { out_counts[0] = u->launches; out_counts[1] = u->force_launches; }
   if (reset) {
     for (int k = 0; k < 6; k++) u->t_ms[k] = 0.0;
     u->launches = 0;
+    u->force_launches = 0;
   }
   return MDB200_OK;
 }
 int mdb200_set_profiling(mdb200_unit *h, int on) {
   if (!h) return MDB200_EINVAL;
-  h->u.profiling = on != 0;
+  h->u.profiling = on < 0 ? 0 : (on > 2 ? 2 : on);
+  return MDB200_OK;
+}
+int mdb200_event_record(mdb200_unit *h, int slot) {
+  if (!h || slot < 0 || slot >= 8) return MDB200_EINVAL;
+  Unit *u = &h->u;
+  DeviceGuard g(u->device);
+  if (!u->ev_ready) {
+    for (int k = 0; k < 8; k++) MDB_CUDA(cudaEventCreate(&u->ev[k]));
+    u->ev_ready = true;
+  }
+  MDB_CUDA(cudaEventRecord(u->ev[slot], u->stream));
+  return MDB200_OK;
+}
+int mdb200_event_elapsed_ms(mdb200_unit *h, int a, int b, double *ms) {
+  if (!h || !ms || a < 0 || a >= 8 || b < 0 || b >= 8 || !h->u.ev_ready) return MDB200_EINVAL;
+  Unit *u = &h->u;
+  DeviceGuard g(u->device);
+  MDB_CUDA(cudaEventSynchronize(u->ev[b]));
+  float f = 0.f;
+  MDB_CUDA(cudaEventElapsedTime(&f, u->ev[a], u->ev[b]));
+  *ms = f;
   return MDB200_OK;
 }
 int mdb200_synchronize(mdb200_unit *h) {

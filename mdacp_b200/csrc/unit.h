@@ -163,11 +163,14 @@ struct Unit {
   bool comm_ready = false;
 
   // profiling
-  bool profiling = false;
+  int profiling = 0;               // 0 off, 1 force kernel only (no extra syncs), 2 every phase
   double t_ms[6] = {0, 0, 0, 0, 0, 0};
   long long launches = 0;
-  cudaEvent_t ev[8];
+  long long force_launches = 0;    // force kernels timed so far (level >= 1)
+  cudaEvent_t ev[8];               // user stopwatch slots
   bool ev_ready = false;
+  cudaEvent_t fev[2];              // light force timer
+  bool fev_ready = false, fev_pending = false;
 };
 
 inline int sentinel_index(const Unit *u) { return (int)u->cap_t; }
