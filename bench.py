@@ -58,56 +58,63 @@ def measured_peaks():
 # clocks sampler (nvidia-smi during the timed region)
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and throttle reasons through NVML (nvidia-ml-py) every 10 ms from a
+    thread while the timed region runs -- the recipe's nvidia-smi clocks line, without the
+    process start-up latency that would miss a sub-second region."""
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.proc = None
-        self.path = None
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.h = None
+        self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.samples.append((sm, rs, pw))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
         try:
-            fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv = nv
+            self.h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.thread = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
+        if self.thread is None:
             return out
-        try:
-            self.proc.terminate()
-            self.proc.wait(timeout=5)
-        except Exception:
-            pass
-        sm, mx, reasons = [], [], set()
-        try:
-            for line in open(self.path):
-                f = [x.strip() for x in line.split(",")]
-                if len(f) < 8:
-                    continue
-                try:
-                    sm.append(float(f[1]))
-                    mx.append(float(f[2]))
-                except ValueError:
-                    continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
-                                   f[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            os.remove(self.path)
-        except Exception:
-            pass
-        if sm:
-            sm.sort()
-            out.update({"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                        "samples": len(sm)})
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        nv = self.nv
+        if not self.samples:
+            return out
+        sm = sorted(s[0] for s in self.samples)
+        bits = 0
+        for s in self.samples:
+            bits |= s[1]
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = sorted(k for k, v in names.items() if bits & v)
+        out.update({"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "reasons": reasons,
+                    "samples": len(sm), "power_w_max": max(s[2] for s in self.samples)})
         return out
 
 

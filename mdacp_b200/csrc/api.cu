@@ -384,6 +384,7 @@ static int calculate(Unit **us, int n) {
     // MDManager::CalculateForce (mdmanager.cc:151-157)
     for (int i = 0; i < n; i++) {
       DeviceGuard g(us[i]->device);
+      MDB_TRY(force_prepare(us[i]));
       {
         PhaseTimer t(us[i], PH_FORCE);
         force_timer_begin(us[i]);

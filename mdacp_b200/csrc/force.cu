@@ -66,9 +66,19 @@ __device__ __forceinline__ void ld_q256(const double4 *p, double &x, double &y, 
   asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(p));
 }
 
+__global__ void k_split_positions(const double4 *__restrict__ q, double *__restrict__ x, double *__restrict__ y,
+                                  double *__restrict__ z, double2 *__restrict__ xy, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 v = q[i];
+  x[i] = v.x; y[i] = v.y; z[i] = v.z;
+  xy[i] = make_double2(v.x, v.y);
+}
+
 template <int VARIANT, bool KICK>
 __global__ void __launch_bounds__(128)
-k_force(const double4 *__restrict__ q, double4 *__restrict__ p, double *__restrict__ fout,
+k_force(const double4 *__restrict__ q, const double *__restrict__ sx, const double *__restrict__ sy,
+        const double *__restrict__ sz, const double2 *__restrict__ sxy, double4 *__restrict__ p, double *__restrict__ fout,
         const int *__restrict__ list, const long long *__restrict__ warp_off, const int *__restrict__ warp_len,
         const int *__restrict__ ref_of_slot, int pn, ForceConsts fc) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -89,7 +99,12 @@ k_force(const double4 *__restrict__ q, double4 *__restrict__ p, double *__restri
     const int j = jn;
     if (t + 1 < len) jn = __ldg(lp + (long long)(t + 1) * 32);
     double jx, jy, jz;
-    if (VARIANT >= 2) {
+    if (VARIANT == 3) {
+      jx = __ldg(sx + j); jy = __ldg(sy + j); jz = __ldg(sz + j);
+    } else if (VARIANT == 4) {
+      const double2 jxy = __ldg(sxy + j);
+      jx = jxy.x; jy = jxy.y; jz = __ldg(sz + j);
+    } else if (VARIANT == 2) {
       ld_q256(q + j, jx, jy, jz);
     } else {
       const double2 jxy = __ldg(reinterpret_cast<const double2 *>(q + j));
@@ -126,7 +141,7 @@ static int force_variant() {
   if (v < 0) {
     const char *e = getenv("MDB200_FORCE_VARIANT");
     v = e ? atoi(e) : 2;
-    if (v < 0 || v > 2) v = 2;
+    if (v < 0 || v > 4) v = 2;
   }
   return v;
 }
@@ -142,20 +157,32 @@ static ForceConsts make_fc(const Unit *u) {
   return fc;
 }
 
+static DevBuf<double> g_sx, g_sy, g_sz;
+static DevBuf<double2> g_sxy;
+int force_prepare(Unit *u) {
+  const int v = force_variant();
+  if (v != 3 && v != 4) return MDB200_OK;
+  MDB_TRY(g_sx.ensure((size_t)u->cap_t + 2)); MDB_TRY(g_sy.ensure((size_t)u->cap_t + 2));
+  MDB_TRY(g_sz.ensure((size_t)u->cap_t + 2)); MDB_TRY(g_sxy.ensure((size_t)u->cap_t + 2));
+  const long long n = u->cap_t + 1;
+  k_split_positions<<<(unsigned)((n + 255) / 256), 256, 0, u->stream>>>(u->q.ptr, g_sx.ptr, g_sy.ptr, g_sz.ptr, g_sxy.ptr, n);
+  u->launches++;
+  return MDB200_OK;
+}
+#define FORCE_ARGS(F) u->q.ptr, g_sx.ptr, g_sy.ptr, g_sz.ptr, g_sxy.ptr, u->p.ptr, F, u->list.ptr, u->warp_off.ptr, \
+                      u->warp_len.ptr, u->ref_of_slot.ptr, (int)u->pn, fc
 int force_kick(Unit *u) {
   if (u->pn == 0) return MDB200_OK;
   const int tpb = 128;
   const unsigned grid = (unsigned)((u->pn + tpb - 1) / tpb);
   ForceConsts fc = make_fc(u);
-  if (force_variant() == 0)
-    k_force<0, true><<<grid, tpb, 0, u->stream>>>(u->q.ptr, u->p.ptr, nullptr, u->list.ptr, u->warp_off.ptr,
-                                                   u->warp_len.ptr, u->ref_of_slot.ptr, (int)u->pn, fc);
-  else if (force_variant() == 2)
-    k_force<2, true><<<grid, tpb, 0, u->stream>>>(u->q.ptr, u->p.ptr, nullptr, u->list.ptr, u->warp_off.ptr,
-                                                   u->warp_len.ptr, u->ref_of_slot.ptr, (int)u->pn, fc);
-  else
-    k_force<1, true><<<grid, tpb, 0, u->stream>>>(u->q.ptr, u->p.ptr, nullptr, u->list.ptr, u->warp_off.ptr,
-                                                   u->warp_len.ptr, u->ref_of_slot.ptr, (int)u->pn, fc);
+  switch (force_variant()) {
+    case 0: k_force<0, true><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(nullptr)); break;
+    case 1: k_force<1, true><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(nullptr)); break;
+    case 3: k_force<3, true><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(nullptr)); break;
+    case 4: k_force<4, true><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(nullptr)); break;
+    default: k_force<2, true><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(nullptr)); break;
+  }
   u->launches++;
   MDB_CUDA(cudaGetLastError());
   return MDB200_OK;
@@ -172,15 +199,14 @@ int force_impulse(Unit *u, double *f3_host, long long cap_rows) {
   const int tpb = 128;
   const unsigned grid = (unsigned)((u->pn + tpb - 1) / tpb);
   ForceConsts fc = make_fc(u);
-  if (force_variant() == 0)
-    k_force<0, false><<<grid, tpb, 0, u->stream>>>(u->q.ptr, u->p.ptr, f.ptr, u->list.ptr, u->warp_off.ptr,
-                                                    u->warp_len.ptr, u->ref_of_slot.ptr, (int)u->pn, fc);
-  else if (force_variant() == 2)
-    k_force<2, false><<<grid, tpb, 0, u->stream>>>(u->q.ptr, u->p.ptr, f.ptr, u->list.ptr, u->warp_off.ptr,
-                                                    u->warp_len.ptr, u->ref_of_slot.ptr, (int)u->pn, fc);
-  else
-    k_force<1, false><<<grid, tpb, 0, u->stream>>>(u->q.ptr, u->p.ptr, f.ptr, u->list.ptr, u->warp_off.ptr,
-                                                    u->warp_len.ptr, u->ref_of_slot.ptr, (int)u->pn, fc);
+  MDB_TRY(force_prepare(u));
+  switch (force_variant()) {
+    case 0: k_force<0, false><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(f.ptr)); break;
+    case 1: k_force<1, false><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(f.ptr)); break;
+    case 3: k_force<3, false><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(f.ptr)); break;
+    case 4: k_force<4, false><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(f.ptr)); break;
+    default: k_force<2, false><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(f.ptr)); break;
+  }
   u->launches++;
   MDB_CUDA(cudaGetLastError());
   MDB_CUDA(cudaMemcpyAsync(f3_host, f.ptr, sizeof(double) * 3 * (size_t)u->pn, cudaMemcpyDeviceToHost, u->stream));

@@ -209,6 +209,7 @@ int langevin_kick(Unit *u);
 int expiry_check_local(Unit *u, int *expired);                           // sync
 
 // force.cu
+int force_prepare(Unit *u);  // experiment: SoA copies of the positions for gather variants 3/4
 int force_kick(Unit *u);
 int force_impulse(Unit *u, double *f3_host, long long cap_rows);         // sync
 
