@@ -284,7 +284,8 @@ def run_ours(args):
 
     # --- synthetic input: the reference's own benchmark generator semantics (host side, C++) ---
     t0 = time.time()
-    cap = int((e[0] - s[0]) * (e[1] - s[1]) * (e[2] - s[2]) * DENSITY) + 64
+    cap0 = int((e[0] - s[0]) * (e[1] - s[1]) * (e[2] - s[2]) * DENSITY) + 64
+    cap = int(cap0 * 1.02) + 65536  # head-room: migration changes the per-unit count
     q_pin = torch.zeros((cap, 4), dtype=torch.float64).pin_memory()
     p_pin = torch.zeros((cap, 4), dtype=torch.float64).pin_memory()
     qh, ph = q_pin.numpy(), p_pin.numpy()
@@ -361,11 +362,12 @@ def run_ours(args):
                          "flops_per_pair": 30}}
 
     # --- timed region 2: `e2e` through the C-ABI with HOST buffers ---
-    unit.download(want_type=False, out=(qh, ph))  # current state -> pinned host (untimed)
+    dd = unit.download(want_type=False, out=(qh, ph))  # current state -> pinned host (untimed)
+    n_now = dd["pn"]
     unit.synchronize()
     barrier()
     te0 = time.time()
-    unit.upload4(qh[:n_local], ph[:n_local])       # H2D inside the timed region
+    unit.upload4(qh[:n_now], ph[:n_now])           # H2D inside the timed region
     for i in range(K):
         mdm.Calculate()                            # first call rebuilds the list (pairlist.cc:27-29)
         if i % OBSERVE_LOOP == 0:
@@ -376,8 +378,8 @@ def run_ours(args):
     te1 = time.time()
     e2e_s = allmax(te1 - te0)
     e2e_val = n_total * K / e2e_s
-    h2d = (2 * n_local * 32) / K
-    d2h = ((n_local + c1["tn"]) * 32 + n_obs * 32) / K
+    h2d = (2 * n_now * 32) / K
+    d2h = (2 * n_now * 32 + n_obs * 32) / K
 
     out = None
     if rank == 0:

@@ -1,0 +1,47 @@
+"""GPU: the stand-alone C++ driver (mdacp_b200/host/main.cpp) on benchmark.cfg AS SHIPPED
+(BASELINE.json configs[0]) prints the reference's own observe lines.
+
+Expected text = stdout of the unmodified scalar reference, `OMP_NUM_THREADS=1 mdacp benchmark.cfg` with
+TotalLoop cut to 201 (recorded in the build container; SURVEY.md section 8c lists the same known answers:
+N = 87,500, T = 0.219084, P = -3.4862, E = -4.43809 at t = 0.151)."""
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "mdacp_b200", "lib", "mdacp_b200")
+
+BENCHMARK_CFG = """Mode=Benchmark
+ThermalizeLoop=150
+SystemSize=50
+#UnitLength=25
+#SystemSizeX=50
+#SystemSizeY=25
+#SystemSizeZ=25
+TimeStep=0.001
+TotalLoop=201
+Restart=yes
+AimedTemperature=1.5
+ControlTemperature=no
+InitialVelocity=1.0
+"""
+EXPECTED = ["0.151 0.219084 -3.4862 -4.43809 #observe", "0.251 0.227322 -3.0562 -4.43804 #observe",
+            "0.351 0.230586 -2.92141 -4.43804 #observe"]
+
+
+def test_benchmark_cfg_as_shipped(tmp_path):
+    if not os.path.exists(EXE):
+        pytest.skip("C++ driver not built")
+    (tmp_path / "benchmark.cfg").write_text(BENCHMARK_CFG)
+    res = subprocess.run([EXE, "benchmark.cfg"], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                         text=True, timeout=600)
+    assert res.returncode == 0, res.stdout
+    lines = [l.strip() for l in res.stdout.splitlines()]
+    assert "# Number of Particles = 87500" in lines
+    assert "# Cutoff Length  = 3" in lines
+    got = [l for l in lines if l.endswith("#observe")]
+    assert got == EXPECTED, res.stdout
+    assert any(l.startswith("# N = 87500 ") and l.endswith("[MUPS]") for l in lines)
+    print(lines[-1])
