@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmdacp_b200.so")
+LIB_PATH = os.environ.get("MDB200_LIB_PATH") or os.path.join(_HERE, "lib", "libmdacp_b200.so")
 
 OK, ECUDA, ECAPACITY, ETOOFAST, EPOSITION, ECELL, EINVAL, ECOMM = range(8)
 HT_NOSEHOOVER, HT_LANGEVIN = 0, 1
@@ -24,7 +24,7 @@ SYMBOLS = [
     "mdb200_heatbath_zeta", "mdb200_heatbath_momenta", "mdb200_langevin", "mdb200_set_seed", "mdb200_get_zeta",
     "mdb200_set_zeta", "mdb200_set_control_temperature", "mdb200_set_aimed_temperature", "mdb200_observe",
     "mdb200_observe_unit", "mdb200_get_pairs", "mdb200_get_impulse", "mdb200_timers", "mdb200_set_profiling",
-    "mdb200_synchronize", "mdb200_event_record", "mdb200_event_elapsed_ms",
+    "mdb200_synchronize", "mdb200_event_record", "mdb200_event_elapsed_ms", "mdb200_list_stats",
 ]
 
 
@@ -88,6 +88,7 @@ def lib():
         L.mdb200_synchronize.argtypes = [vp]
         L.mdb200_event_record.argtypes = [vp, C.c_int]
         L.mdb200_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, dp]
+        L.mdb200_list_stats.argtypes = [vp, dp]
         _lib = L
     return _lib
 
@@ -219,6 +220,12 @@ class Unit:
         """0 off; 1 force kernel only (no extra syncs); 2 / True every phase"""
         level = 2 if level is True else int(level)
         check(lib().mdb200_set_profiling(self.handle, level))
+
+    def list_stats(self):
+        o = (C.c_double * 8)()
+        check(lib().mdb200_list_stats(self.handle, o))
+        return {"threads": int(o[0]), "padded_entries": int(o[1]), "max_row": int(o[2]), "entries": int(o[3]),
+                "single_threads": int(o[4]), "entries_two": int(o[5])}
 
     def event_record(self, slot):
         check(lib().mdb200_event_record(self.handle, slot))

@@ -752,6 +752,32 @@ int mdb200_set_profiling(mdb200_unit *h, int on) {
   h->u.profiling = on < 0 ? 0 : (on > 2 ? 2 : on);
   return MDB200_OK;
 }
+int mdb200_list_stats(mdb200_unit *h, double out[8]) {
+  if (!h || !out) return MDB200_EINVAL;
+  Unit *u = &h->u;
+  DeviceGuard g(u->device);
+  for (int k = 0; k < 8; k++) out[k] = 0.0;
+  out[0] = (double)u->nthreads;
+  out[1] = (double)u->list_entries;
+  out[2] = (double)u->max_row;
+  if (u->nthreads > 0 && u->list_initialized) {
+    std::vector<int> rc((size_t)u->nthreads);
+    std::vector<unsigned> ti((size_t)u->nthreads);
+    MDB_CUDA(cudaMemcpyAsync(rc.data(), u->row_count.ptr, sizeof(int) * rc.size(), cudaMemcpyDeviceToHost, u->stream));
+    MDB_CUDA(cudaMemcpyAsync(ti.data(), u->tp_info.ptr, sizeof(unsigned) * ti.size(), cudaMemcpyDeviceToHost, u->stream));
+    MDB_CUDA(cudaStreamSynchronize(u->stream));
+    double s = 0, s2 = 0, singles = 0;
+    for (size_t k = 0; k < rc.size(); k++) {
+      s += rc[k];
+      if (!(ti[k] & 0x40000000u)) singles += 1;
+      else s2 += rc[k];
+    }
+    out[3] = s;                       // sum of row lengths (unpadded entries)
+    out[4] = singles;                 // threads that own a single local
+    out[5] = s2;                      // entries in rows of two-local threads
+  }
+  return MDB200_OK;
+}
 int mdb200_event_record(mdb200_unit *h, int slot) {
   if (!h || slot < 0 || slot >= 8) return MDB200_EINVAL;
   Unit *u = &h->u;

@@ -288,6 +288,62 @@ __global__ void k_cell_sort_buckets(const int *__restrict__ cell_start, int *__r
   }
 }
 
+// Greedy nearest-neighbour matching inside each cell.  The force kernel gives every thread TWO local
+// particles (slots a, a+1 of one cell) that share each gathered partner position, so the closer the two
+// are, the smaller the union of their neighbour rows.  Thread per cell, O(n^2/2) float distances on
+// ~25 particles, deterministic (input order = ascending reference index); heuristic only -- any order
+// gives the same physics.
+#define MATCH_MAX 64
+__global__ void k_cell_match(const double4 *__restrict__ q, const int *__restrict__ ord,
+                             const int *__restrict__ cell_start, int *__restrict__ items, int ncell) {
+  int ci = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ci >= ncell) return;
+  const int b = cell_start[ci];
+  int n = cell_start[ci + 1] - b;
+  if (n < 3) return;
+  if (n > MATCH_MAX) n = MATCH_MAX;
+  int id[MATCH_MAX];
+  float x[MATCH_MAX], y[MATCH_MAX], z[MATCH_MAX];
+  for (int k = 0; k < n; k++) {
+    id[k] = items[b + k];
+    const double4 v = q[ord[id[k]]];
+    x[k] = (float)v.x; y[k] = (float)v.y; z[k] = (float)v.z;
+  }
+  for (int s = 0; s + 2 < n; s += 2) {
+    int best = s + 1;
+    float bd = 3.0e38f;
+    for (int m = s + 1; m < n; m++) {
+      const float dx = x[m] - x[s], dy = y[m] - y[s], dz = z[m] - z[s];
+      const float d = dx * dx + dy * dy + dz * dz;
+      if (d < bd) { bd = d; best = m; }
+    }
+    if (best != s + 1) {
+      int ti = id[best]; id[best] = id[s + 1]; id[s + 1] = ti;
+      float tf = x[best]; x[best] = x[s + 1]; x[s + 1] = tf;
+      tf = y[best]; y[best] = y[s + 1]; y[s + 1] = tf;
+      tf = z[best]; z[best] = z[s + 1]; z[s + 1] = tf;
+    }
+  }
+  for (int k = 0; k < n; k++) items[b + k] = id[k];
+}
+
+// thread table of the force / pair-search kernels: cell c owns ceil(n_c / 2) threads, thread k of the cell
+// owns slots a = start + 2k and (if it exists in the same cell) a + 1.  tp_info = a | two << 30 | ab << 31
+// (ab = the two are listed partners of each other; set by the pair search).
+__global__ void k_cell_nthreads(const int *__restrict__ cell_start, int *__restrict__ nthr, int ncell) {
+  int ci = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ci >= ncell) return;
+  nthr[ci] = (cell_start[ci + 1] - cell_start[ci] + 1) >> 1;
+}
+__global__ void k_thread_table(const int *__restrict__ cell_start, const int *__restrict__ thr_start,
+                               unsigned *__restrict__ tp_info, int ncell) {
+  int ci = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ci >= ncell) return;
+  const int b = cell_start[ci], e = cell_start[ci + 1];
+  int t = thr_start[ci];
+  for (int a = b; a < e; a += 2, t++) tp_info[t] = (unsigned)a | ((a + 1 < e) ? 0x40000000u : 0u);
+}
+
 __global__ void k_permute_locals(const double4 *__restrict__ q, const double4 *__restrict__ p,
                                  const int *__restrict__ type, const int *__restrict__ ord,
                                  const int *__restrict__ items, double4 *__restrict__ q2,
@@ -341,6 +397,9 @@ int cell_sort_locals(Unit *u) {
   MDB_TRY(ensure_capacity(u, u->pn, u->pn));
   MDB_TRY(bin_items(u, u->cell_count, u->cell_start, u->cell_cursor, u->cell_items, 0, u->pn, false));
   if (u->pn > 0) {
+    k_cell_match<<<nblk(u->c.ncell, 64), 64, 0, u->stream>>>(u->q.ptr, u->ord.ptr, u->cell_start.ptr, u->cell_items.ptr,
+                                                             u->c.ncell);
+    u->launches++;
     k_permute_locals<<<nblk(u->pn), TPB, 0, u->stream>>>(u->q.ptr, u->p.ptr, u->type.ptr, u->ord.ptr,
                                                           u->cell_items.ptr, u->q_alt.ptr, u->p_alt.ptr,
                                                           u->type_alt.ptr, u->ref_of_slot.ptr, u->slot_of_ref.ptr,
@@ -420,6 +479,12 @@ int find_border(Unit *u, int dir, long long *n_border) {
 // multiply-add, exactly as the scalar x86-64 reference does (meshlist.cc:262-266), so the
 // pair SET is bit-identical to the reference's.  Ghost-ghost pairs never arise because rows
 // exist for locals only (meshlist.cc:261).
+//
+// One thread owns the two locals (a, a+1) of its table entry and walks the 27 neighbouring cells
+// ONCE for both: an entry is the partner slot j plus two flag bits (bit 31: j is a listed partner of
+// a, bit 30: of b).  The row is the UNION of the two neighbour rows; the a-b pair itself is kept in the
+// table entry (bit 31 of tp_info).  Rows come out in ascending slot order (cells are visited in
+// ascending index; ghosts after locals inside each (y,z) range).
 __device__ __forceinline__ bool within_search(const double4 &a, const double4 &b, double SL2) {
   double dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
   double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
@@ -430,71 +495,104 @@ template <bool FILL>
 __global__ void __launch_bounds__(128)
 k_pair_search(const double4 *__restrict__ q, const int *__restrict__ cell_start,
               const int *__restrict__ gcell_start, const int *__restrict__ gcell_items,
-              const int *__restrict__ ref_of_slot, int *__restrict__ row_count,
-              const long long *__restrict__ warp_off, int *warp_len,
-              int *__restrict__ list, int pn, int sentinel, Consts c, Ctrl *ctrl) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int lane = threadIdx.x & 31;
-  int w = i >> 5;
-  bool act = i < pn;
-  double4 qi = act ? q[i] : make_double4(0, 0, 0, 0);
+              const int *__restrict__ ref_of_slot, unsigned *tp_info, int *__restrict__ row_count,
+              const long long *__restrict__ warp_off, int *warp_len, unsigned *__restrict__ list, int nt, int pn,
+              int sentinel, Consts c, Ctrl *ctrl) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int w = t >> 5;
+  const bool act = t < nt;
   int n = 0;
   unsigned long long nref = 0;
   long long base = 0;
   int wl = 0;
   if (FILL) {
-    if ((long long)w * 32 < pn) {
+    if ((long long)w * 32 < nt) {
       base = warp_off[w] + lane;
       wl = warp_len[w];
     }
   }
   if (act) {
-    int ci = cell_index(qi, c, 0);
-    int cx = ci % c.m[0];
-    int cy = (ci / c.m[0]) % c.m[1];
-    int cz = ci / (c.m[0] * c.m[1]);
-    int ri = ref_of_slot[i];
-    int x0 = max(cx - 1, 0), x1 = min(cx + 1, c.m[0] - 1);
+    const unsigned info = tp_info[t];
+    const int a = (int)(info & 0x3FFFFFFFu);
+    const bool two = (info & 0x40000000u) != 0;
+    const int b = a + 1;
+    const double4 qa = q[a];
+    const double4 qb = two ? q[b] : qa;
+    const int ra = ref_of_slot[a];
+    const int rb = two ? ref_of_slot[b] : 0;
+    const int ci = cell_index(qa, c, 0);
+    const int cx = ci % c.m[0];
+    const int cy = (ci / c.m[0]) % c.m[1];
+    const int cz = ci / (c.m[0] * c.m[1]);
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, c.m[0] - 1);
     for (int dz = -1; dz <= 1; dz++) {
-      int z = cz + dz;
+      const int z = cz + dz;
       if (z < 0 || z >= c.m[2]) continue;
       for (int dy = -1; dy <= 1; dy++) {
-        int y = cy + dy;
+        const int y = cy + dy;
         if (y < 0 || y >= c.m[1]) continue;
-        int rowc = c.m[0] * (y + c.m[1] * z);
+        const int rowc = c.m[0] * (y + c.m[1] * z);
         // the three x-neighbours are contiguous in cell order: one range per (y,z)
-        int jb = cell_start[rowc + x0], je = cell_start[rowc + x1 + 1];
+        const int jb = cell_start[rowc + x0], je = cell_start[rowc + x1 + 1];
         for (int j = jb; j < je; j++) {
-          if (j == i) continue;
-          if (within_search(qi, q[j], c.SL2)) {
-            if (FILL) list[base + (long long)n * 32] = j;
-            else nref += (ref_of_slot[j] > ri) ? 1ull : 0ull;
-            n++;
-          }
-        }
-        int gb = gcell_start[rowc + x0], ge = gcell_start[rowc + x1 + 1];
-        for (int t = gb; t < ge; t++) {
-          int g = gcell_items[t];
-          if (within_search(qi, q[g], c.SL2)) {
-            if (FILL) list[base + (long long)n * 32] = g;
-            else nref++;
+          if (j == a || (two && j == b)) continue;
+          const double4 qj = q[j];
+          const bool ina = within_search(qa, qj, c.SL2);
+          const bool inb = two && within_search(qb, qj, c.SL2);
+          if (ina | inb) {
+            if (FILL) {
+              list[base + (long long)n * 32] = (unsigned)j | (ina ? 0x80000000u : 0u) | (inb ? 0x40000000u : 0u);
+            } else {
+              const int rj = ref_of_slot[j];
+              nref += (ina && rj > ra) ? 1ull : 0ull;
+              nref += (inb && rj > rb) ? 1ull : 0ull;
+            }
             n++;
           }
         }
       }
     }
+    // ghosts after all locals, so that a row is ascending in slot
+    for (int dz = -1; dz <= 1; dz++) {
+      const int z = cz + dz;
+      if (z < 0 || z >= c.m[2]) continue;
+      for (int dy = -1; dy <= 1; dy++) {
+        const int y = cy + dy;
+        if (y < 0 || y >= c.m[1]) continue;
+        const int rowc = c.m[0] * (y + c.m[1] * z);
+        const int gb = gcell_start[rowc + x0], ge = gcell_start[rowc + x1 + 1];
+        for (int k = gb; k < ge; k++) {
+          const int g = gcell_items[k];
+          const double4 qj = q[g];
+          const bool ina = within_search(qa, qj, c.SL2);
+          const bool inb = two && within_search(qb, qj, c.SL2);
+          if (ina | inb) {
+            if (FILL) list[base + (long long)n * 32] = (unsigned)g | (ina ? 0x80000000u : 0u) | (inb ? 0x40000000u : 0u);
+            else nref += (ina ? 1ull : 0ull) + (inb ? 1ull : 0ull);
+            n++;
+          }
+        }
+      }
+    }
+    if (!FILL) {
+      if (two && within_search(qa, qb, c.SL2)) {
+        tp_info[t] = info | 0x80000000u;
+        nref += 1ull;
+      }
+      row_count[t] = n;
+    }
   }
   if (FILL) {
-    for (int t = n; t < wl; t++) list[base + (long long)t * 32] = sentinel;
+    for (int k = n; k < wl; k++) list[base + (long long)k * 32] = (unsigned)sentinel;
   } else {
-    if (act) row_count[i] = n;
     int mx = n;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       nref += __shfl_xor_sync(0xffffffffu, nref, o);
     }
-    if (lane == 0 && (long long)w * 32 < pn) {
+    if (lane == 0 && (long long)w * 32 < nt) {
       warp_len[w] = mx;
       if (nref) atomicAdd(&ctrl->npairs, nref);
       atomicMax(&ctrl->max_row, mx);
@@ -504,42 +602,55 @@ k_pair_search(const double4 *__restrict__ q, const int *__restrict__ cell_start,
 
 int build_pair_list(Unit *u) {
   const long long pn = u->pn;
-  const long long nw = (pn + 31) / 32;
-  MDB_TRY(u->warp_len.ensure((size_t)nw + 2));
-  MDB_TRY(u->warp_off.ensure((size_t)nw + 2));
-  MDB_TRY(u->row_count.ensure((size_t)pn + 32));
-  DevBuf<long long> &ws64 = u->scan_ws64;
-  MDB_TRY(ws64.ensure(scan_workspace_ints(nw + 2)));
+  const int nc = u->c.ncell;
   MDB_CUDA(cudaMemsetAsync(&u->ctrl->npairs, 0, sizeof(unsigned long long), u->stream));
   MDB_CUDA(cudaMemsetAsync(&u->ctrl->max_row, 0, sizeof(int), u->stream));
   u->list_entries = 0;
   u->npairs = 0;
-  if (pn > 0) {
-    const int tpb = 128;
-    k_pair_search<false><<<nblk(pn, tpb), tpb, 0, u->stream>>>(
-        u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr, u->gcell_items.ptr, u->ref_of_slot.ptr, u->row_count.ptr,
-        u->warp_off.ptr, u->warp_len.ptr, u->list.ptr, (int)pn, sentinel_index(u), u->c, u->ctrl);
-    u->launches++;
-    MDB_TRY(exclusive_scan_i32_to_i64(u->warp_len.ptr, u->warp_off.ptr, nw, ws64.ptr, u->stream, &u->launches, 32));
-    MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->scratch[2], u->warp_off.ptr + nw, sizeof(long long),
-                             cudaMemcpyDeviceToHost, u->stream));
-    MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->npairs, &u->ctrl->npairs, sizeof(unsigned long long),
-                             cudaMemcpyDeviceToHost, u->stream));
-    MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->max_row, &u->ctrl->max_row, sizeof(int), cudaMemcpyDeviceToHost,
-                             u->stream));
-    MDB_CUDA(cudaStreamSynchronize(u->stream));
-    long long entries;
-    memcpy(&entries, &u->ctrl_host->scratch[2], sizeof(long long));
-    u->list_entries = entries;
-    u->npairs = (long long)u->ctrl_host->npairs;
-    u->max_row = u->ctrl_host->max_row;
-    MDB_TRY(u->list.ensure((size_t)entries + 64));
-    k_pair_search<true><<<nblk(pn, tpb), tpb, 0, u->stream>>>(
-        u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr, u->gcell_items.ptr, u->ref_of_slot.ptr, u->row_count.ptr,
-        u->warp_off.ptr, u->warp_len.ptr, u->list.ptr, (int)pn, sentinel_index(u), u->c, u->ctrl);
-    u->launches++;
-    MDB_CUDA(cudaGetLastError());
-  }
+  u->nthreads = 0;
+  if (pn == 0) return MDB200_OK;
+  // thread table
+  MDB_TRY(u->cell_nthr.ensure((size_t)nc + 2));
+  MDB_TRY(u->cell_thr_start.ensure((size_t)nc + 2));
+  k_cell_nthreads<<<nblk(nc), TPB, 0, u->stream>>>(u->cell_start.ptr, u->cell_nthr.ptr, nc);
+  u->launches++;
+  MDB_TRY(exclusive_scan_i32(u->cell_nthr.ptr, u->cell_thr_start.ptr, nc, u->scan_ws.ptr, u->stream, &u->launches));
+  MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->scratch[3], u->cell_thr_start.ptr + nc, sizeof(int), cudaMemcpyDeviceToHost,
+                           u->stream));
+  MDB_CUDA(cudaStreamSynchronize(u->stream));
+  const long long nt = u->ctrl_host->scratch[3];
+  u->nthreads = nt;
+  const long long nw = (nt + 31) / 32;
+  MDB_TRY(u->tp_info.ensure((size_t)nt + 32));
+  MDB_TRY(u->row_count.ensure((size_t)nt + 32));
+  MDB_TRY(u->warp_len.ensure((size_t)nw + 2));
+  MDB_TRY(u->warp_off.ensure((size_t)nw + 2));
+  MDB_TRY(u->scan_ws64.ensure(scan_workspace_ints(nw + 2)));
+  k_thread_table<<<nblk(nc), TPB, 0, u->stream>>>(u->cell_start.ptr, u->cell_thr_start.ptr, u->tp_info.ptr, nc);
+  u->launches++;
+  const int tpb = 128;
+  k_pair_search<false><<<nblk(nt, tpb), tpb, 0, u->stream>>>(
+      u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr, u->gcell_items.ptr, u->ref_of_slot.ptr, u->tp_info.ptr,
+      u->row_count.ptr, u->warp_off.ptr, u->warp_len.ptr, u->list.ptr, (int)nt, (int)pn, sentinel_index(u), u->c, u->ctrl);
+  u->launches++;
+  MDB_TRY(exclusive_scan_i32_to_i64(u->warp_len.ptr, u->warp_off.ptr, nw, u->scan_ws64.ptr, u->stream, &u->launches, 32));
+  MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->scratch[4], u->warp_off.ptr + nw, sizeof(long long), cudaMemcpyDeviceToHost,
+                           u->stream));
+  MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->npairs, &u->ctrl->npairs, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                           u->stream));
+  MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->max_row, &u->ctrl->max_row, sizeof(int), cudaMemcpyDeviceToHost, u->stream));
+  MDB_CUDA(cudaStreamSynchronize(u->stream));
+  long long entries;
+  memcpy(&entries, &u->ctrl_host->scratch[4], sizeof(long long));
+  u->list_entries = entries;
+  u->npairs = (long long)u->ctrl_host->npairs;
+  u->max_row = u->ctrl_host->max_row;
+  MDB_TRY(u->list.ensure((size_t)entries + 64));
+  k_pair_search<true><<<nblk(nt, tpb), tpb, 0, u->stream>>>(
+      u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr, u->gcell_items.ptr, u->ref_of_slot.ptr, u->tp_info.ptr,
+      u->row_count.ptr, u->warp_off.ptr, u->warp_len.ptr, u->list.ptr, (int)nt, (int)pn, sentinel_index(u), u->c, u->ctrl);
+  u->launches++;
+  MDB_CUDA(cudaGetLastError());
   return MDB200_OK;
 }
 
@@ -553,27 +664,35 @@ int snapshot_positions(Unit *u) {
 // ---------------------------------------------------------------------------------------------
 // parity helper: the list as the reference's raw (key, partner) arrays, reference indices
 // ---------------------------------------------------------------------------------------------
-__global__ void k_extract_pairs(const int *__restrict__ list, const long long *__restrict__ warp_off,
-                                const int *__restrict__ row_count, const int *__restrict__ ref_of_slot,
-                                int *__restrict__ key, int *__restrict__ partner, unsigned long long *cursor,
-                                unsigned long long cap, int pn) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= pn) return;
-  int lane = i & 31, w = i >> 5;
-  long long base = warp_off[w] + lane;
-  int n = row_count[i];
-  int ri = ref_of_slot[i];
-  for (int t = 0; t < n; t++) {
-    int j = list[base + (long long)t * 32];
-    int rj = (j < pn) ? ref_of_slot[j] : j;
-    if (ri < rj) {
-      unsigned long long pos = atomicAdd(cursor, 1ull);
-      if (pos < cap) {
-        key[pos] = ri;
-        partner[pos] = rj;
-      }
-    }
+__device__ __forceinline__ void emit_pair(int ri, int rj, int *key, int *partner, unsigned long long *cursor,
+                                          unsigned long long cap) {
+  unsigned long long pos = atomicAdd(cursor, 1ull);
+  if (pos < cap) {
+    key[pos] = ri < rj ? ri : rj;
+    partner[pos] = ri < rj ? rj : ri;
   }
+}
+__global__ void k_extract_pairs(const unsigned *__restrict__ list, const long long *__restrict__ warp_off,
+                                const int *__restrict__ row_count, const unsigned *__restrict__ tp_info,
+                                const int *__restrict__ ref_of_slot, int *__restrict__ key, int *__restrict__ partner,
+                                unsigned long long *cursor, unsigned long long cap, int nt, int pn) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nt) return;
+  const unsigned info = tp_info[t];
+  const int a = (int)(info & 0x3FFFFFFFu);
+  const bool two = (info & 0x40000000u) != 0;
+  const int ra = ref_of_slot[a];
+  const int rb = two ? ref_of_slot[a + 1] : 0;
+  const long long base = warp_off[t >> 5] + (t & 31);
+  const int n = row_count[t];
+  for (int k = 0; k < n; k++) {
+    const unsigned e = list[base + (long long)k * 32];
+    const int j = (int)(e & 0x3FFFFFFFu);
+    const int rj = (j < pn) ? ref_of_slot[j] : j;
+    if ((e & 0x80000000u) && ra < rj) emit_pair(ra, rj, key, partner, cursor, cap);
+    if ((e & 0x40000000u) && rb < rj) emit_pair(rb, rj, key, partner, cursor, cap);
+  }
+  if (info & 0x80000000u) emit_pair(ra, rb, key, partner, cursor, cap);
 }
 
 int extract_pairs(Unit *u, int *key, int *partner, long long cap, long long *npairs) {
@@ -587,9 +706,9 @@ int extract_pairs(Unit *u, int *key, int *partner, long long cap, long long *npa
   unsigned long long *cur = nullptr;
   MDB_CUDA(cudaMalloc(&cur, sizeof(unsigned long long)));
   MDB_CUDA(cudaMemsetAsync(cur, 0, sizeof(unsigned long long), u->stream));
-  k_extract_pairs<<<nblk(u->pn), TPB, 0, u->stream>>>(u->list.ptr, u->warp_off.ptr, u->row_count.ptr,
-                                                       u->ref_of_slot.ptr, dk.ptr, dp.ptr, cur,
-                                                       (unsigned long long)u->npairs, (int)u->pn);
+  k_extract_pairs<<<nblk(u->nthreads), TPB, 0, u->stream>>>(u->list.ptr, u->warp_off.ptr, u->row_count.ptr,
+                                                             u->tp_info.ptr, u->ref_of_slot.ptr, dk.ptr, dp.ptr, cur,
+                                                             (unsigned long long)u->npairs, (int)u->nthreads, (int)u->pn);
   u->launches++;
   unsigned long long got = 0;
   MDB_CUDA(cudaMemcpyAsync(&got, cur, sizeof(got), cudaMemcpyDeviceToHost, u->stream));

@@ -3,33 +3,42 @@
 //   for each listed pair (i,j): d = q_j - q_i, r2 = |d|^2; if r2 > CL2 the pair contributes 0;
 //   r6 = r2^3; df = ((24 r6 - 48)/(r6 r6 r2) + 8 C2) dt; p_i += df d; p_j -= df d.
 //
-// B200 formulation.  One thread per LOCAL particle walks its row of the FULL neighbour list
-// (both (i,j) and (j,i) are stored), so each thread owns p_i exclusively: no atomics, no
-// reaction term, deterministic summation order, and ghost momenta are never written (they are
-// scratch in the reference, fcalculator.cc:273-275 / SURVEY.md Q8).  The list is stored
-// warp-interleaved (entry t of lane l at base + 32 t + l) so every index load is one coalesced
-// 128-byte line per warp, and locals are cell-sorted so the gathered partner positions of a
-// warp sit in a few neighbouring cells and hit in L1/L2 instead of HBM.
+// B200 formulation.
+//  * FULL neighbour list, no atomics: every local's momentum is owned by exactly one thread, so the
+//    summation order is deterministic and ghost momenta are never written (they are scratch in the
+//    reference, fcalculator.cc:273-275 / SURVEY.md Q8).  RED.ADD.F64 for the reaction term of a half list
+//    would cost ~3 P atomics per particle at ~1.3 clk/lane/SM -- several times this whole kernel.
+//  * TWO locals per thread (slots a, a+1 of one cell, matched nearest neighbours, cells.cu:k_cell_match).
+//    ncu shows the thread-per-particle version bound by the L1 data pipe on the scattered gather of
+//    partner positions (~20 wavefronts per warp-gather, FP64 pipe ~30 %; profiles/r01_force_v*_ncu.txt);
+//    the cost tracks gathered bytes whatever the layout.  Sharing each gathered partner between two
+//    nearby locals cuts gathers per evaluation to ~0.65 at ~1.3x FP64 work (the union of two rows).
+//    The a-b interaction itself is evaluated once and applied to both (Newton's third law in-thread).
+//  * one 256-bit load per partner (LDG.E.256); list stored warp-interleaved (entry k of lane l at
+//    base + 32 k + l) so index loads are one coalesced 128-byte line per warp; locals cell-sorted.
+//  * cutoff / "is a listed partner of a (b)" tests run on the integer pipe (bit-pattern compare of the
+//    non-negative r2, flag bits 31/30 of the entry), keeping the FP64 pipe for arithmetic.
 //
-// Roofline: FP64 pipe.  Per evaluated (directed) pair: 3 sub + 3 (r2) + reciprocal
-// + 5 (LJ polynomial) + 3 fma; algorithmic HBM bytes per particle = 4 B x P (half-list indices)
-// + 96 B (q read, p read + write) with P listed unordered pairs per particle.
+// Roofline: algorithmic HBM bytes per particle = 4 B x P (half-list indices) + 96 B
+// (q read, p read + write), 30 flop per listed unordered pair.
 #include <stdlib.h>
 #include "unit.h"
 
 namespace mdb {
 
-// 1 / x to full double precision: hardware seed (MUFU.RCP64H, ~20+ bits) + one cubic
-// (Halley-type) refinement y (1 + e + e^2) + one linear Newton step as a guard; the latter
-// costs 2 DFMA and keeps the result within 1 ulp irrespective of the seed quality.
+// 1 / x: hardware seed (MUFU.RCP64H) + one cubic (Halley-type) refinement y (1 + e + e^2);
+// GUARD adds one linear Newton step (2 DFMA) that makes the result independent of the seed quality.
+template <bool GUARD>
 __device__ __forceinline__ double fast_rcp(double x) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   double e = fma(-x, y, 1.0);
   double t = fma(e, e, e);
   y = fma(y, t, y);
-  e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
+  if (GUARD) {
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+  }
   return y;
 }
 
@@ -43,14 +52,15 @@ struct ForceConsts {
 };
 
 // VARIANT 0: reference expression with an IEEE division (validation baseline)
-// VARIANT 1: reciprocal-polynomial form: s = 1/r2, df = s^4 (24 - 48 s^3) dt + 8 C2 dt
+// VARIANT 1: s = 1/r2 (seed + cubic + guard step), df = s^4 (24 - 48 s^3) dt + 8 C2 dt
+// VARIANT 2: same without the guard step
 template <int VARIANT>
 __device__ __forceinline__ double pair_df(double r2, const ForceConsts &fc) {
   if (VARIANT == 0) {
     double r6 = r2 * r2 * r2;
     return ((24.0 * r6 - 48.0) / (r6 * r6 * r2) + fc.c2x8) * fc.dt;
   } else {
-    double s = fast_rcp(r2);
+    double s = fast_rcp<VARIANT == 1>(r2);
     double s2 = s * s;
     double s3 = s2 * s;
     double s4 = s2 * s2;
@@ -59,80 +69,92 @@ __device__ __forceinline__ double pair_df(double r2, const ForceConsts &fc) {
   }
 }
 
-// one 256-bit load per gathered partner (LDG.E.256, sm_100+): a single L1 request per pair
-// instead of a 128-bit + 64-bit pair of requests that each walk the same 32 sectors
 __device__ __forceinline__ void ld_q256(const double4 *p, double &x, double &y, double &z) {
   double w;
   asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(p));
+  (void)w;
 }
 
-__global__ void k_split_positions(const double4 *__restrict__ q, double *__restrict__ x, double *__restrict__ y,
-                                  double *__restrict__ z, double2 *__restrict__ xy, long long n) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double4 v = q[i];
-  x[i] = v.x; y[i] = v.y; z[i] = v.z;
-  xy[i] = make_double2(v.x, v.y);
-}
-
+#ifndef FORCE_UNROLL
+#define FORCE_UNROLL 2
+#endif
+#ifndef FORCE_MINBLK
+#define FORCE_MINBLK 8
+#endif
 template <int VARIANT, bool KICK>
-__global__ void __launch_bounds__(128)
-k_force(const double4 *__restrict__ q, const double *__restrict__ sx, const double *__restrict__ sy,
-        const double *__restrict__ sz, const double2 *__restrict__ sxy, double4 *__restrict__ p, double *__restrict__ fout,
-        const int *__restrict__ list, const long long *__restrict__ warp_off, const int *__restrict__ warp_len,
-        const int *__restrict__ ref_of_slot, int pn, ForceConsts fc) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int w = i >> 5;
-  if ((long long)w * 32 >= pn) return;
+__global__ void __launch_bounds__(128, FORCE_MINBLK)
+k_force(const double4 *__restrict__ q, double4 *__restrict__ p, double *__restrict__ fout,
+        const unsigned *__restrict__ list, const long long *__restrict__ warp_off, const int *__restrict__ warp_len,
+        const unsigned *__restrict__ tp_info, const int *__restrict__ ref_of_slot, int nt, ForceConsts fc) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = t >> 5;
+  if ((long long)w * 32 >= nt) return;
   const int lane = threadIdx.x & 31;
-  const bool act = i < pn;
-  const int ii = act ? i : pn - 1;
-  const double2 qxy = __ldg(reinterpret_cast<const double2 *>(q + ii));
-  const double qz = __ldg(reinterpret_cast<const double *>(q + ii) + 2);
+  const bool act = t < nt;
+  const unsigned info = tp_info[act ? t : nt - 1];
+  const int a = (int)(info & 0x3FFFFFFFu);
+  const bool two = (info & 0x40000000u) != 0;
+  double ax, ay, az, bx, by, bz;
+  ld_q256(q + a, ax, ay, az);
+  ld_q256(q + (two ? a + 1 : a), bx, by, bz);
   const int len = warp_len[w];
-  const int *__restrict__ lp = list + warp_off[w] + lane;
-  double fx = 0.0, fy = 0.0, fz = 0.0;
+  const unsigned *__restrict__ lp = list + warp_off[w] + lane;
+  double fax = 0.0, fay = 0.0, faz = 0.0, fbx = 0.0, fby = 0.0, fbz = 0.0;
   const long long cl2b = __double_as_longlong(fc.CL2);
 
-  int jn = (len > 0) ? __ldg(lp) : 0;
-  for (int t = 0; t < len; t++) {
-    const int j = jn;
-    if (t + 1 < len) jn = __ldg(lp + (long long)(t + 1) * 32);
+  constexpr int UNR = FORCE_UNROLL;
+  unsigned en = (len > 0) ? __ldg(lp) : 0u;
+#pragma unroll UNR
+  for (int k = 0; k < len; k++) {
+    const unsigned e = en;
+    if (k + 1 < len) en = __ldg(lp + (long long)(k + 1) * 32);
     double jx, jy, jz;
-    if (VARIANT == 3) {
-      jx = __ldg(sx + j); jy = __ldg(sy + j); jz = __ldg(sz + j);
-    } else if (VARIANT == 4) {
-      const double2 jxy = __ldg(sxy + j);
-      jx = jxy.x; jy = jxy.y; jz = __ldg(sz + j);
-    } else if (VARIANT == 2) {
-      ld_q256(q + j, jx, jy, jz);
-    } else {
-      const double2 jxy = __ldg(reinterpret_cast<const double2 *>(q + j));
-      jx = jxy.x; jy = jxy.y;
-      jz = __ldg(reinterpret_cast<const double *>(q + j) + 2);
+    ld_q256(q + (e & 0x3FFFFFFFu), jx, jy, jz);
+    {
+      const double dx = jx - ax, dy = jy - ay, dz = jz - az;
+      const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+      double df = pair_df<VARIANT>(r2, fc);
+      // r2 > CL2 (fcalculator.cc:209-211) or not a listed partner of a: no contribution
+      if ((__double_as_longlong(r2) > cl2b) || !(e & 0x80000000u)) df = 0.0;
+      fax = fma(df, dx, fax);
+      fay = fma(df, dy, fay);
+      faz = fma(df, dz, faz);
     }
-    const double dx = jx - qxy.x;
-    const double dy = jy - qxy.y;
-    const double dz = jz - qz;
-    const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-    double df = pair_df<VARIANT>(r2, fc);
-    // r2 > CL2 on non-negative doubles == integer compare of the bit patterns: runs on the
-    // integer pipe, keeping the FP64 pipe for arithmetic (fcalculator.cc:209-211: df = 0)
-    if (__double_as_longlong(r2) > cl2b) df = 0.0;
-    fx = fma(df, dx, fx);
-    fy = fma(df, dy, fy);
-    fz = fma(df, dz, fz);
+    {
+      const double dx = jx - bx, dy = jy - by, dz = jz - bz;
+      const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+      double df = pair_df<VARIANT>(r2, fc);
+      if ((__double_as_longlong(r2) > cl2b) || !(e & 0x40000000u)) df = 0.0;
+      fbx = fma(df, dx, fbx);
+      fby = fma(df, dy, fby);
+      fbz = fma(df, dz, fbz);
+    }
   }
   if (!act) return;
+  if (info & 0x80000000u) {  // the two locals of this thread are listed partners of each other
+    const double dx = bx - ax, dy = by - ay, dz = bz - az;
+    const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+    double df = pair_df<VARIANT>(r2, fc);
+    if (__double_as_longlong(r2) > cl2b) df = 0.0;
+    fax = fma(df, dx, fax); fay = fma(df, dy, fay); faz = fma(df, dz, faz);
+    fbx = fma(-df, dx, fbx); fby = fma(-df, dy, fby); fbz = fma(-df, dz, fbz);
+  }
   if (KICK) {
-    double4 pp = p[i];
-    pp.x += fx; pp.y += fy; pp.z += fz;
-    p[i] = pp;
+    double4 pa = p[a];
+    pa.x += fax; pa.y += fay; pa.z += faz;
+    p[a] = pa;
+    if (two) {
+      double4 pb = p[a + 1];
+      pb.x += fbx; pb.y += fby; pb.z += fbz;
+      p[a + 1] = pb;
+    }
   } else {
-    const int r = ref_of_slot[i];
-    fout[3 * (long long)r + 0] = fx;
-    fout[3 * (long long)r + 1] = fy;
-    fout[3 * (long long)r + 2] = fz;
+    const long long ra = ref_of_slot[a];
+    fout[3 * ra + 0] = fax; fout[3 * ra + 1] = fay; fout[3 * ra + 2] = faz;
+    if (two) {
+      const long long rb = ref_of_slot[a + 1];
+      fout[3 * rb + 0] = fbx; fout[3 * rb + 1] = fby; fout[3 * rb + 2] = fbz;
+    }
   }
 }
 
@@ -140,8 +162,8 @@ static int force_variant() {
   static int v = -1;
   if (v < 0) {
     const char *e = getenv("MDB200_FORCE_VARIANT");
-    v = e ? atoi(e) : 2;
-    if (v < 0 || v > 4) v = 2;
+    v = e ? atoi(e) : 1;
+    if (v < 0 || v > 2) v = 1;
   }
   return v;
 }
@@ -157,31 +179,20 @@ static ForceConsts make_fc(const Unit *u) {
   return fc;
 }
 
-static DevBuf<double> g_sx, g_sy, g_sz;
-static DevBuf<double2> g_sxy;
-int force_prepare(Unit *u) {
-  const int v = force_variant();
-  if (v != 3 && v != 4) return MDB200_OK;
-  MDB_TRY(g_sx.ensure((size_t)u->cap_t + 2)); MDB_TRY(g_sy.ensure((size_t)u->cap_t + 2));
-  MDB_TRY(g_sz.ensure((size_t)u->cap_t + 2)); MDB_TRY(g_sxy.ensure((size_t)u->cap_t + 2));
-  const long long n = u->cap_t + 1;
-  k_split_positions<<<(unsigned)((n + 255) / 256), 256, 0, u->stream>>>(u->q.ptr, g_sx.ptr, g_sy.ptr, g_sz.ptr, g_sxy.ptr, n);
-  u->launches++;
-  return MDB200_OK;
-}
-#define FORCE_ARGS(F) u->q.ptr, g_sx.ptr, g_sy.ptr, g_sz.ptr, g_sxy.ptr, u->p.ptr, F, u->list.ptr, u->warp_off.ptr, \
-                      u->warp_len.ptr, u->ref_of_slot.ptr, (int)u->pn, fc
+#define FORCE_ARGS(F) u->q.ptr, u->p.ptr, F, u->list.ptr, u->warp_off.ptr, u->warp_len.ptr, u->tp_info.ptr, \
+                      u->ref_of_slot.ptr, (int)u->nthreads, fc
+
+int force_prepare(Unit *) { return MDB200_OK; }
+
 int force_kick(Unit *u) {
-  if (u->pn == 0) return MDB200_OK;
+  if (u->pn == 0 || u->nthreads == 0) return MDB200_OK;
   const int tpb = 128;
-  const unsigned grid = (unsigned)((u->pn + tpb - 1) / tpb);
+  const unsigned grid = (unsigned)((u->nthreads + tpb - 1) / tpb);
   ForceConsts fc = make_fc(u);
   switch (force_variant()) {
     case 0: k_force<0, true><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(nullptr)); break;
-    case 1: k_force<1, true><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(nullptr)); break;
-    case 3: k_force<3, true><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(nullptr)); break;
-    case 4: k_force<4, true><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(nullptr)); break;
-    default: k_force<2, true><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(nullptr)); break;
+    case 2: k_force<2, true><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(nullptr)); break;
+    default: k_force<1, true><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(nullptr)); break;
   }
   u->launches++;
   MDB_CUDA(cudaGetLastError());
@@ -197,15 +208,12 @@ int force_impulse(Unit *u, double *f3_host, long long cap_rows) {
   DevBuf<double> f;
   MDB_TRY(f.ensure((size_t)u->pn * 3));
   const int tpb = 128;
-  const unsigned grid = (unsigned)((u->pn + tpb - 1) / tpb);
+  const unsigned grid = (unsigned)((u->nthreads + tpb - 1) / tpb);
   ForceConsts fc = make_fc(u);
-  MDB_TRY(force_prepare(u));
   switch (force_variant()) {
     case 0: k_force<0, false><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(f.ptr)); break;
-    case 1: k_force<1, false><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(f.ptr)); break;
-    case 3: k_force<3, false><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(f.ptr)); break;
-    case 4: k_force<4, false><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(f.ptr)); break;
-    default: k_force<2, false><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(f.ptr)); break;
+    case 2: k_force<2, false><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(f.ptr)); break;
+    default: k_force<1, false><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(f.ptr)); break;
   }
   u->launches++;
   MDB_CUDA(cudaGetLastError());

@@ -137,12 +137,17 @@ struct Unit {
   DevBuf<double4> mig_send_q, mig_send_p, mig_recv_q, mig_recv_p;
   DevBuf<int> mig_send_t, mig_recv_t;
 
-  // full neighbour list, warp-interleaved: entry t of lane l of warp w at
-  // list[warp_off[w] + t*32 + l]; rows padded to the warp maximum with the sentinel index
-  DevBuf<int> row_count;          // listed partners per local slot
+  // full neighbour list, warp-interleaved: entry k of lane l of warp w at
+  // list[warp_off[w] + k*32 + l]; rows padded to the warp maximum with the sentinel index
+  // One force/search THREAD owns two locals of one cell (slots a, a+1): tp_info[t] = a | two<<30 | ab<<31.
+  // Its row is the union of the two neighbour rows; entry = partner slot | (partner of a)<<31 | (of b)<<30.
+  DevBuf<unsigned> tp_info;
+  DevBuf<int> cell_nthr, cell_thr_start;
+  long long nthreads = 0;
+  DevBuf<int> row_count;          // entries per thread
   DevBuf<int> warp_len;
   DevBuf<long long> warp_off;
-  DevBuf<int> list;
+  DevBuf<unsigned> list;
   long long list_entries = 0;
   long long npairs = 0;
   int max_row = 0;
