@@ -224,8 +224,8 @@ class Unit:
     def list_stats(self):
         o = (C.c_double * 8)()
         check(lib().mdb200_list_stats(self.handle, o))
-        return {"threads": int(o[0]), "padded_entries": int(o[1]), "max_row": int(o[2]), "entries": int(o[3]),
-                "single_threads": int(o[4]), "entries_two": int(o[5])}
+        return {"warps": int(o[0]), "padded_entries": int(o[1]), "max_row": int(o[2]), "entries": int(o[3]),
+                "lanes_per_local": int(o[4])}
 
     def event_record(self, slot):
         check(lib().mdb200_event_record(self.handle, slot))

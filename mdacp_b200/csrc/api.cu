@@ -384,7 +384,6 @@ static int calculate(Unit **us, int n) {
     // MDManager::CalculateForce (mdmanager.cc:151-157)
     for (int i = 0; i < n; i++) {
       DeviceGuard g(us[i]->device);
-      MDB_TRY(force_prepare(us[i]));
       {
         PhaseTimer t(us[i], PH_FORCE);
         force_timer_begin(us[i]);
@@ -488,7 +487,7 @@ int mdb200_destroy(mdb200_unit *h) {
   for (int d = 0; d < 6; d++) u->border[d].release();
   u->send_buf.release(); u->mig_send_q.release(); u->mig_send_p.release(); u->mig_recv_q.release();
   u->mig_recv_p.release(); u->mig_send_t.release(); u->mig_recv_t.release();
-  u->row_count.release(); u->warp_len.release(); u->warp_off.release(); u->list.release();
+  u->row_count.release(); u->row_cls.release(); u->warp_len.release(); u->warp_off.release(); u->list.release();
   u->disp.release(); u->cand.release(); u->partial.release();
   if (u->ctrl) cudaFree(u->ctrl);
   if (u->ctrl_host) cudaFreeHost(u->ctrl_host);
@@ -757,24 +756,17 @@ int mdb200_list_stats(mdb200_unit *h, double out[8]) {
   Unit *u = &h->u;
   DeviceGuard g(u->device);
   for (int k = 0; k < 8; k++) out[k] = 0.0;
-  out[0] = (double)u->nthreads;
-  out[1] = (double)u->list_entries;
+  out[0] = (double)u->nwarps;
+  out[1] = (double)u->list_entries;   // padded list words
   out[2] = (double)u->max_row;
-  if (u->nthreads > 0 && u->list_initialized) {
-    std::vector<int> rc((size_t)u->nthreads);
-    std::vector<unsigned> ti((size_t)u->nthreads);
+  out[4] = (double)kG;
+  if (u->pn > 0 && u->list_initialized) {
+    std::vector<int> rc((size_t)u->pn);
     MDB_CUDA(cudaMemcpyAsync(rc.data(), u->row_count.ptr, sizeof(int) * rc.size(), cudaMemcpyDeviceToHost, u->stream));
-    MDB_CUDA(cudaMemcpyAsync(ti.data(), u->tp_info.ptr, sizeof(unsigned) * ti.size(), cudaMemcpyDeviceToHost, u->stream));
     MDB_CUDA(cudaStreamSynchronize(u->stream));
-    double s = 0, s2 = 0, singles = 0;
-    for (size_t k = 0; k < rc.size(); k++) {
-      s += rc[k];
-      if (!(ti[k] & 0x40000000u)) singles += 1;
-      else s2 += rc[k];
-    }
+    double s = 0;
+    for (size_t k = 0; k < rc.size(); k++) s += rc[k];
     out[3] = s;                       // sum of row lengths (unpadded entries)
-    out[4] = singles;                 // threads that own a single local
-    out[5] = s2;                      // entries in rows of two-local threads
   }
   return MDB200_OK;
 }

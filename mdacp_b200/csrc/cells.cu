@@ -288,62 +288,6 @@ __global__ void k_cell_sort_buckets(const int *__restrict__ cell_start, int *__r
   }
 }
 
-// Greedy nearest-neighbour matching inside each cell.  The force kernel gives every thread TWO local
-// particles (slots a, a+1 of one cell) that share each gathered partner position, so the closer the two
-// are, the smaller the union of their neighbour rows.  Thread per cell, O(n^2/2) float distances on
-// ~25 particles, deterministic (input order = ascending reference index); heuristic only -- any order
-// gives the same physics.
-#define MATCH_MAX 64
-__global__ void k_cell_match(const double4 *__restrict__ q, const int *__restrict__ ord,
-                             const int *__restrict__ cell_start, int *__restrict__ items, int ncell) {
-  int ci = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ci >= ncell) return;
-  const int b = cell_start[ci];
-  int n = cell_start[ci + 1] - b;
-  if (n < 3) return;
-  if (n > MATCH_MAX) n = MATCH_MAX;
-  int id[MATCH_MAX];
-  float x[MATCH_MAX], y[MATCH_MAX], z[MATCH_MAX];
-  for (int k = 0; k < n; k++) {
-    id[k] = items[b + k];
-    const double4 v = q[ord[id[k]]];
-    x[k] = (float)v.x; y[k] = (float)v.y; z[k] = (float)v.z;
-  }
-  for (int s = 0; s + 2 < n; s += 2) {
-    int best = s + 1;
-    float bd = 3.0e38f;
-    for (int m = s + 1; m < n; m++) {
-      const float dx = x[m] - x[s], dy = y[m] - y[s], dz = z[m] - z[s];
-      const float d = dx * dx + dy * dy + dz * dz;
-      if (d < bd) { bd = d; best = m; }
-    }
-    if (best != s + 1) {
-      int ti = id[best]; id[best] = id[s + 1]; id[s + 1] = ti;
-      float tf = x[best]; x[best] = x[s + 1]; x[s + 1] = tf;
-      tf = y[best]; y[best] = y[s + 1]; y[s + 1] = tf;
-      tf = z[best]; z[best] = z[s + 1]; z[s + 1] = tf;
-    }
-  }
-  for (int k = 0; k < n; k++) items[b + k] = id[k];
-}
-
-// thread table of the force / pair-search kernels: cell c owns ceil(n_c / 2) threads, thread k of the cell
-// owns slots a = start + 2k and (if it exists in the same cell) a + 1.  tp_info = a | two << 30 | ab << 31
-// (ab = the two are listed partners of each other; set by the pair search).
-__global__ void k_cell_nthreads(const int *__restrict__ cell_start, int *__restrict__ nthr, int ncell) {
-  int ci = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ci >= ncell) return;
-  nthr[ci] = (cell_start[ci + 1] - cell_start[ci] + 1) >> 1;
-}
-__global__ void k_thread_table(const int *__restrict__ cell_start, const int *__restrict__ thr_start,
-                               unsigned *__restrict__ tp_info, int ncell) {
-  int ci = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ci >= ncell) return;
-  const int b = cell_start[ci], e = cell_start[ci + 1];
-  int t = thr_start[ci];
-  for (int a = b; a < e; a += 2, t++) tp_info[t] = (unsigned)a | ((a + 1 < e) ? 0x40000000u : 0u);
-}
-
 __global__ void k_permute_locals(const double4 *__restrict__ q, const double4 *__restrict__ p,
                                  const int *__restrict__ type, const int *__restrict__ ord,
                                  const int *__restrict__ items, double4 *__restrict__ q2,
@@ -397,9 +341,6 @@ int cell_sort_locals(Unit *u) {
   MDB_TRY(ensure_capacity(u, u->pn, u->pn));
   MDB_TRY(bin_items(u, u->cell_count, u->cell_start, u->cell_cursor, u->cell_items, 0, u->pn, false));
   if (u->pn > 0) {
-    k_cell_match<<<nblk(u->c.ncell, 64), 64, 0, u->stream>>>(u->q.ptr, u->ord.ptr, u->cell_start.ptr, u->cell_items.ptr,
-                                                             u->c.ncell);
-    u->launches++;
     k_permute_locals<<<nblk(u->pn), TPB, 0, u->stream>>>(u->q.ptr, u->p.ptr, u->type.ptr, u->ord.ptr,
                                                           u->cell_items.ptr, u->q_alt.ptr, u->p_alt.ptr,
                                                           u->type_alt.ptr, u->ref_of_slot.ptr, u->slot_of_ref.ptr,
@@ -480,47 +421,85 @@ int find_border(Unit *u, int dir, long long *n_border) {
 // pair SET is bit-identical to the reference's.  Ghost-ghost pairs never arise because rows
 // exist for locals only (meshlist.cc:261).
 //
-// One thread owns the two locals (a, a+1) of its table entry and walks the 27 neighbouring cells
-// ONCE for both: an entry is the partner slot j plus two flag bits (bit 31: j is a listed partner of
-// a, bit 30: of b).  The row is the UNION of the two neighbour rows; the a-b pair itself is kept in the
-// table entry (bit 31 of tp_info).  Rows come out in ascending slot order (cells are visited in
-// ascending index; ghosts after locals inside each (y,z) range).
+// Search: one thread per local slot walks the 27 neighbouring cells (9 contiguous (y,z) ranges of
+// locals, then the same 9 ranges of binned ghosts).  Two passes (count, then fill) because the list
+// layout depends on the per-warp maxima.  Layout of the list: see unit.h (kG lanes per local, kPW
+// locals per force-warp).
+//
+// Order of a row ("rainbow" order, kG == 4).  A position record is 32 bytes, so a partner's index mod 4
+// is the sector slot of its 128-byte line = the L1 data-bank group the gather hits.  Measured on B200
+// (scripts/ubench/gather.cu): a warp-wide LDG.256 gather costs ~18.6 clk with random slots, ~11 clk when
+// every slot is hit by exactly 8 lanes, 32 clk when all lanes hit one slot -- the number of distinct
+// lines hardly matters.  So the 4 lanes of a local take, at every step, partners of 4 DIFFERENT classes
+// c = j mod 4 for as long as all classes last (steps < m = min class count: lane c takes the t-th
+// smallest partner of class c at step t); what is left over is dealt out class-round-robin.  No padding
+// is added and within a class the partners stay ascending.
 __device__ __forceinline__ bool within_search(const double4 &a, const double4 &b, double SL2) {
   double dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
   double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
   return !(r2 > SL2);
 }
 
+// Entry index (step * kG + lane-in-group) of a row's partners; see the header above.
+struct RowOrder {
+  unsigned cls = 0;       // count pass: partners per class, 4 x 8 bits; fill pass: running ordinals
+  unsigned tot = 0;       // fill pass: the class counts of the finished row
+  int m = 0, seq = 0;
+  bool overflow = false;
+  __device__ __forceinline__ void count(int j) {
+    if (kG != 4) return;
+    const int sh = 8 * (j & 3);
+    if (((cls >> sh) & 0xFFu) == 0xFFu) overflow = true;
+    else cls += 1u << sh;
+  }
+  __device__ __forceinline__ void init(unsigned totals) {
+    tot = totals;
+    cls = 0;
+    m = (int)min(min(tot & 0xFFu, (tot >> 8) & 0xFFu), min((tot >> 16) & 0xFFu, (tot >> 24) & 0xFFu));
+  }
+  __device__ __forceinline__ int place(int j) {
+    if (kG != 4) return seq++;
+    const int c = j & 3;
+    const int t = (int)((cls >> (8 * c)) & 0xFFu);
+    cls += 1u << (8 * c);
+    if (t < m) return 4 * t + c;
+    // leftovers in (ordinal, class) order: how many leftover entries precede (t, c)
+    int r = 0;
+#pragma unroll
+    for (int cc = 0; cc < 4; cc++) {
+      const int left = (int)((tot >> (8 * cc)) & 0xFFu) - m;
+      r += min(left, (t - m) + (cc < c ? 1 : 0));
+    }
+    return 4 * m + r;
+  }
+};
+
 template <bool FILL>
 __global__ void __launch_bounds__(128)
 k_pair_search(const double4 *__restrict__ q, const int *__restrict__ cell_start,
               const int *__restrict__ gcell_start, const int *__restrict__ gcell_items,
-              const int *__restrict__ ref_of_slot, unsigned *tp_info, int *__restrict__ row_count,
-              const long long *__restrict__ warp_off, int *warp_len, unsigned *__restrict__ list, int nt, int pn,
+              const int *__restrict__ ref_of_slot, int *__restrict__ row_count, unsigned *__restrict__ row_cls,
+              const long long *__restrict__ warp_off, int *warp_len, unsigned *__restrict__ list, int pn,
               int sentinel, Consts c, Ctrl *ctrl) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;  // local slot
   const int lane = threadIdx.x & 31;
-  const int w = t >> 5;
-  const bool act = t < nt;
+  const int fw = a / kPW;                               // force-warp of this slot
+  const int flane0 = (a % kPW) * kG;                    // first lane of its group
+  const bool act = a < pn;
+  const bool in_tail = (long long)fw * kPW < pn;        // slot belongs to an existing force-warp
   int n = 0;
   unsigned long long nref = 0;
   long long base = 0;
   int wl = 0;
-  if (FILL) {
-    if ((long long)w * 32 < nt) {
-      base = warp_off[w] + lane;
-      wl = warp_len[w];
-    }
+  RowOrder ro;
+  if (FILL && in_tail) {
+    base = warp_off[fw];
+    wl = warp_len[fw];
   }
   if (act) {
-    const unsigned info = tp_info[t];
-    const int a = (int)(info & 0x3FFFFFFFu);
-    const bool two = (info & 0x40000000u) != 0;
-    const int b = a + 1;
+    if (FILL) ro.init(row_cls[a]);
     const double4 qa = q[a];
-    const double4 qb = two ? q[b] : qa;
     const int ra = ref_of_slot[a];
-    const int rb = two ? ref_of_slot[b] : 0;
     const int ci = cell_index(qa, c, 0);
     const int cx = ci % c.m[0];
     const int cy = (ci / c.m[0]) % c.m[1];
@@ -536,17 +515,14 @@ k_pair_search(const double4 *__restrict__ q, const int *__restrict__ cell_start,
         // the three x-neighbours are contiguous in cell order: one range per (y,z)
         const int jb = cell_start[rowc + x0], je = cell_start[rowc + x1 + 1];
         for (int j = jb; j < je; j++) {
-          if (j == a || (two && j == b)) continue;
-          const double4 qj = q[j];
-          const bool ina = within_search(qa, qj, c.SL2);
-          const bool inb = two && within_search(qb, qj, c.SL2);
-          if (ina | inb) {
+          if (j == a) continue;
+          if (within_search(qa, q[j], c.SL2)) {
             if (FILL) {
-              list[base + (long long)n * 32] = (unsigned)j | (ina ? 0x80000000u : 0u) | (inb ? 0x40000000u : 0u);
+              const int e = ro.place(j);
+              list[base + list_word(e / kG, flane0 + e % kG)] = (unsigned)j;
             } else {
-              const int rj = ref_of_slot[j];
-              nref += (ina && rj > ra) ? 1ull : 0ull;
-              nref += (inb && rj > rb) ? 1ull : 0ull;
+              nref += (ref_of_slot[j] > ra) ? 1ull : 0ull;
+              ro.count(j);
             }
             n++;
           }
@@ -564,74 +540,67 @@ k_pair_search(const double4 *__restrict__ q, const int *__restrict__ cell_start,
         const int gb = gcell_start[rowc + x0], ge = gcell_start[rowc + x1 + 1];
         for (int k = gb; k < ge; k++) {
           const int g = gcell_items[k];
-          const double4 qj = q[g];
-          const bool ina = within_search(qa, qj, c.SL2);
-          const bool inb = two && within_search(qb, qj, c.SL2);
-          if (ina | inb) {
-            if (FILL) list[base + (long long)n * 32] = (unsigned)g | (ina ? 0x80000000u : 0u) | (inb ? 0x40000000u : 0u);
-            else nref += (ina ? 1ull : 0ull) + (inb ? 1ull : 0ull);
+          if (within_search(qa, q[g], c.SL2)) {
+            if (FILL) {
+              const int e = ro.place(g);
+              list[base + list_word(e / kG, flane0 + e % kG)] = (unsigned)g;
+            } else {
+              nref += 1ull;
+              ro.count(g);
+            }
             n++;
           }
         }
       }
     }
     if (!FILL) {
-      if (two && within_search(qa, qb, c.SL2)) {
-        tp_info[t] = info | 0x80000000u;
-        nref += 1ull;
-      }
-      row_count[t] = n;
+      row_count[a] = n;
+      row_cls[a] = ro.cls;
+      if (ro.overflow) atomicOr(&ctrl->err, (int)DE_CAPACITY);
     }
   }
   if (FILL) {
-    for (int k = n; k < wl; k++) list[base + (long long)k * 32] = (unsigned)sentinel;
+    if (in_tail)
+      for (int e = n; e < wl * kG; e++) list[base + list_word(e / kG, flane0 + e % kG)] = (unsigned)sentinel;
   } else {
-    int mx = n;
+    // steps of this local, maximum over the kPW locals of its force-warp, rounded up to even
+    int mx = (n + kG - 1) / kG;
+    int mrow = n;
+#pragma unroll
+    for (int o = kPW / 2; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      mrow = max(mrow, __shfl_xor_sync(0xffffffffu, mrow, o));
       nref += __shfl_xor_sync(0xffffffffu, nref, o);
     }
-    if (lane == 0 && (long long)w * 32 < nt) {
-      warp_len[w] = mx;
+    if (in_tail && (a % kPW) == 0) warp_len[fw] = (mx + 1) & ~1;
+    if (lane == 0) {
       if (nref) atomicAdd(&ctrl->npairs, nref);
-      atomicMax(&ctrl->max_row, mx);
+      atomicMax(&ctrl->max_row, mrow);
     }
   }
 }
 
 int build_pair_list(Unit *u) {
   const long long pn = u->pn;
-  const int nc = u->c.ncell;
   MDB_CUDA(cudaMemsetAsync(&u->ctrl->npairs, 0, sizeof(unsigned long long), u->stream));
   MDB_CUDA(cudaMemsetAsync(&u->ctrl->max_row, 0, sizeof(int), u->stream));
   u->list_entries = 0;
   u->npairs = 0;
-  u->nthreads = 0;
+  u->nwarps = 0;
   if (pn == 0) return MDB200_OK;
-  // thread table
-  MDB_TRY(u->cell_nthr.ensure((size_t)nc + 2));
-  MDB_TRY(u->cell_thr_start.ensure((size_t)nc + 2));
-  k_cell_nthreads<<<nblk(nc), TPB, 0, u->stream>>>(u->cell_start.ptr, u->cell_nthr.ptr, nc);
-  u->launches++;
-  MDB_TRY(exclusive_scan_i32(u->cell_nthr.ptr, u->cell_thr_start.ptr, nc, u->scan_ws.ptr, u->stream, &u->launches));
-  MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->scratch[3], u->cell_thr_start.ptr + nc, sizeof(int), cudaMemcpyDeviceToHost,
-                           u->stream));
-  MDB_CUDA(cudaStreamSynchronize(u->stream));
-  const long long nt = u->ctrl_host->scratch[3];
-  u->nthreads = nt;
-  const long long nw = (nt + 31) / 32;
-  MDB_TRY(u->tp_info.ensure((size_t)nt + 32));
-  MDB_TRY(u->row_count.ensure((size_t)nt + 32));
+  const long long nw = (pn + kPW - 1) / kPW;
+  u->nwarps = nw;
+  MDB_TRY(u->row_count.ensure((size_t)pn + 32));
+  MDB_TRY(u->row_cls.ensure((size_t)pn + 32));
   MDB_TRY(u->warp_len.ensure((size_t)nw + 2));
   MDB_TRY(u->warp_off.ensure((size_t)nw + 2));
   MDB_TRY(u->scan_ws64.ensure(scan_workspace_ints(nw + 2)));
-  k_thread_table<<<nblk(nc), TPB, 0, u->stream>>>(u->cell_start.ptr, u->cell_thr_start.ptr, u->tp_info.ptr, nc);
-  u->launches++;
   const int tpb = 128;
-  k_pair_search<false><<<nblk(nt, tpb), tpb, 0, u->stream>>>(
-      u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr, u->gcell_items.ptr, u->ref_of_slot.ptr, u->tp_info.ptr,
-      u->row_count.ptr, u->warp_off.ptr, u->warp_len.ptr, u->list.ptr, (int)nt, (int)pn, sentinel_index(u), u->c, u->ctrl);
+  const long long nthr = nw * kPW;  // threads past pn only pad the tail warp
+  k_pair_search<false><<<nblk(nthr, tpb), tpb, 0, u->stream>>>(
+      u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr, u->gcell_items.ptr, u->ref_of_slot.ptr, u->row_count.ptr, u->row_cls.ptr,
+      u->warp_off.ptr, u->warp_len.ptr, u->list.ptr, (int)pn, sentinel_index(u), u->c, u->ctrl);
   u->launches++;
   MDB_TRY(exclusive_scan_i32_to_i64(u->warp_len.ptr, u->warp_off.ptr, nw, u->scan_ws64.ptr, u->stream, &u->launches, 32));
   MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->scratch[4], u->warp_off.ptr + nw, sizeof(long long), cudaMemcpyDeviceToHost,
@@ -646,9 +615,9 @@ int build_pair_list(Unit *u) {
   u->npairs = (long long)u->ctrl_host->npairs;
   u->max_row = u->ctrl_host->max_row;
   MDB_TRY(u->list.ensure((size_t)entries + 64));
-  k_pair_search<true><<<nblk(nt, tpb), tpb, 0, u->stream>>>(
-      u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr, u->gcell_items.ptr, u->ref_of_slot.ptr, u->tp_info.ptr,
-      u->row_count.ptr, u->warp_off.ptr, u->warp_len.ptr, u->list.ptr, (int)nt, (int)pn, sentinel_index(u), u->c, u->ctrl);
+  k_pair_search<true><<<nblk(nthr, tpb), tpb, 0, u->stream>>>(
+      u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr, u->gcell_items.ptr, u->ref_of_slot.ptr, u->row_count.ptr, u->row_cls.ptr,
+      u->warp_off.ptr, u->warp_len.ptr, u->list.ptr, (int)pn, sentinel_index(u), u->c, u->ctrl);
   u->launches++;
   MDB_CUDA(cudaGetLastError());
   return MDB200_OK;
@@ -673,26 +642,20 @@ __device__ __forceinline__ void emit_pair(int ri, int rj, int *key, int *partner
   }
 }
 __global__ void k_extract_pairs(const unsigned *__restrict__ list, const long long *__restrict__ warp_off,
-                                const int *__restrict__ row_count, const unsigned *__restrict__ tp_info,
-                                const int *__restrict__ ref_of_slot, int *__restrict__ key, int *__restrict__ partner,
-                                unsigned long long *cursor, unsigned long long cap, int nt, int pn) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nt) return;
-  const unsigned info = tp_info[t];
-  const int a = (int)(info & 0x3FFFFFFFu);
-  const bool two = (info & 0x40000000u) != 0;
+                                const int *__restrict__ row_count, const int *__restrict__ ref_of_slot,
+                                int *__restrict__ key, int *__restrict__ partner, unsigned long long *cursor,
+                                unsigned long long cap, int pn) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= pn) return;
   const int ra = ref_of_slot[a];
-  const int rb = two ? ref_of_slot[a + 1] : 0;
-  const long long base = warp_off[t >> 5] + (t & 31);
-  const int n = row_count[t];
-  for (int k = 0; k < n; k++) {
-    const unsigned e = list[base + (long long)k * 32];
-    const int j = (int)(e & 0x3FFFFFFFu);
+  const long long base = warp_off[a / kPW];
+  const int flane0 = (a % kPW) * kG;
+  const int n = row_count[a];
+  for (int e = 0; e < n; e++) {
+    const int j = (int)list[base + list_word(e / kG, flane0 + e % kG)];
     const int rj = (j < pn) ? ref_of_slot[j] : j;
-    if ((e & 0x80000000u) && ra < rj) emit_pair(ra, rj, key, partner, cursor, cap);
-    if ((e & 0x40000000u) && rb < rj) emit_pair(rb, rj, key, partner, cursor, cap);
+    if (ra < rj) emit_pair(ra, rj, key, partner, cursor, cap);
   }
-  if (info & 0x80000000u) emit_pair(ra, rb, key, partner, cursor, cap);
 }
 
 int extract_pairs(Unit *u, int *key, int *partner, long long cap, long long *npairs) {
@@ -706,9 +669,9 @@ int extract_pairs(Unit *u, int *key, int *partner, long long cap, long long *npa
   unsigned long long *cur = nullptr;
   MDB_CUDA(cudaMalloc(&cur, sizeof(unsigned long long)));
   MDB_CUDA(cudaMemsetAsync(cur, 0, sizeof(unsigned long long), u->stream));
-  k_extract_pairs<<<nblk(u->nthreads), TPB, 0, u->stream>>>(u->list.ptr, u->warp_off.ptr, u->row_count.ptr,
-                                                             u->tp_info.ptr, u->ref_of_slot.ptr, dk.ptr, dp.ptr, cur,
-                                                             (unsigned long long)u->npairs, (int)u->nthreads, (int)u->pn);
+  k_extract_pairs<<<nblk(u->pn), TPB, 0, u->stream>>>(u->list.ptr, u->warp_off.ptr, u->row_count.ptr,
+                                                       u->ref_of_slot.ptr, dk.ptr, dp.ptr, cur,
+                                                       (unsigned long long)u->npairs, (int)u->pn);
   u->launches++;
   unsigned long long got = 0;
   MDB_CUDA(cudaMemcpyAsync(&got, cur, sizeof(got), cudaMemcpyDeviceToHost, u->stream));

@@ -4,20 +4,21 @@
 //   r6 = r2^3; df = ((24 r6 - 48)/(r6 r6 r2) + 8 C2) dt; p_i += df d; p_j -= df d.
 //
 // B200 formulation.
-//  * FULL neighbour list, no atomics: every local's momentum is owned by exactly one thread, so the
-//    summation order is deterministic and ghost momenta are never written (they are scratch in the
-//    reference, fcalculator.cc:273-275 / SURVEY.md Q8).  RED.ADD.F64 for the reaction term of a half list
-//    would cost ~3 P atomics per particle at ~1.3 clk/lane/SM -- several times this whole kernel.
-//  * TWO locals per thread (slots a, a+1 of one cell, matched nearest neighbours, cells.cu:k_cell_match).
-//    ncu shows the thread-per-particle version bound by the L1 data pipe on the scattered gather of
-//    partner positions (~20 wavefronts per warp-gather, FP64 pipe ~30 %; profiles/r01_force_v*_ncu.txt);
-//    the cost tracks gathered bytes whatever the layout.  Sharing each gathered partner between two
-//    nearby locals cuts gathers per evaluation to ~0.65 at ~1.3x FP64 work (the union of two rows).
-//    The a-b interaction itself is evaluated once and applied to both (Newton's third law in-thread).
-//  * one 256-bit load per partner (LDG.E.256); list stored warp-interleaved (entry k of lane l at
-//    base + 32 k + l) so index loads are one coalesced 128-byte line per warp; locals cell-sorted.
-//  * cutoff / "is a listed partner of a (b)" tests run on the integer pipe (bit-pattern compare of the
-//    non-negative r2, flag bits 31/30 of the entry), keeping the FP64 pipe for arithmetic.
+//  * FULL neighbour list, no atomics: every local's momentum is owned by one lane group, so the summation
+//    order is deterministic and ghost momenta are never written (they are scratch in the reference,
+//    fcalculator.cc:273-275 / SURVEY.md Q8).  RED.ADD.F64 for the reaction term of a half list would cost
+//    ~3 P atomics per particle at ~1.3 clk/lane/SM -- several times this whole kernel.
+//  * kG = 4 LANES PER LOCAL (unit.h): a warp owns 8 consecutive cell-sorted locals; the 4 lanes of a group
+//    take 4 consecutive entries of that local's ascending row per step and a 2-stage shuffle reduction
+//    combines them at the end.  Why: ncu shows the thread-per-local version bound by the L1 data pipe on the
+//    scattered gather of partner positions (~20 distinct 128-byte lines = ~20 wavefronts per warp-gather,
+//    FP64 pipe ~30 %; profiles/r01_force_v*_ncu.txt).  Consecutive entries of one row sit in the same or
+//    adjacent lines and 8 neighbouring locals share most of their partner lines, which cuts the distinct
+//    lines per warp-gather to ~13 (scripts/gather_model.py) at identical FP64 work.
+//  * one 256-bit load per partner (LDG.E.256); list words for two steps come from one 8-byte load per lane
+//    (a contiguous 256-byte run per warp); locals cell-sorted.
+//  * the cutoff test runs on the integer pipe (bit-pattern compare of the non-negative r2), keeping the
+//    FP64 pipe for arithmetic.
 //
 // Roofline: algorithmic HBM bytes per particle = 4 B x P (half-list indices) + 96 B
 // (q read, p read + write), 30 flop per listed unordered pair.
@@ -79,82 +80,66 @@ __device__ __forceinline__ void ld_q256(const double4 *p, double &x, double &y, 
 #define FORCE_UNROLL 2
 #endif
 #ifndef FORCE_MINBLK
-#define FORCE_MINBLK 8
+#define FORCE_MINBLK 10
 #endif
+
+template <int VARIANT>
+__device__ __forceinline__ void pair_accumulate(double ax, double ay, double az, double jx, double jy, double jz,
+                                                long long cl2b, const ForceConsts &fc, double &fx, double &fy,
+                                                double &fz) {
+  const double dx = jx - ax, dy = jy - ay, dz = jz - az;
+  const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+  double df = pair_df<VARIANT>(r2, fc);
+  // r2 > CL2: the pair contributes nothing (fcalculator.cc:209-211); also kills the sentinel padding
+  if (__double_as_longlong(r2) > cl2b) df = 0.0;
+  fx = fma(df, dx, fx);
+  fy = fma(df, dy, fy);
+  fz = fma(df, dz, fz);
+}
+
 template <int VARIANT, bool KICK>
 __global__ void __launch_bounds__(128, FORCE_MINBLK)
 k_force(const double4 *__restrict__ q, double4 *__restrict__ p, double *__restrict__ fout,
         const unsigned *__restrict__ list, const long long *__restrict__ warp_off, const int *__restrict__ warp_len,
-        const unsigned *__restrict__ tp_info, const int *__restrict__ ref_of_slot, int nt, ForceConsts fc) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int w = t >> 5;
-  if ((long long)w * 32 >= nt) return;
+        const int *__restrict__ ref_of_slot, int pn, long long nwarps, ForceConsts fc) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= nwarps) return;
   const int lane = threadIdx.x & 31;
-  const bool act = t < nt;
-  const unsigned info = tp_info[act ? t : nt - 1];
-  const int a = (int)(info & 0x3FFFFFFFu);
-  const bool two = (info & 0x40000000u) != 0;
-  double ax, ay, az, bx, by, bz;
-  ld_q256(q + a, ax, ay, az);
-  ld_q256(q + (two ? a + 1 : a), bx, by, bz);
-  const int len = warp_len[w];
-  const unsigned *__restrict__ lp = list + warp_off[w] + lane;
-  double fax = 0.0, fay = 0.0, faz = 0.0, fbx = 0.0, fby = 0.0, fbz = 0.0;
+  const long long a = w * kPW + lane / kG;
+  const bool act = a < pn;
+  double ax, ay, az;
+  ld_q256(q + (act ? a : (long long)pn - 1), ax, ay, az);
+  const int len2 = warp_len[w] >> 1;
+  const uint2 *__restrict__ lp = reinterpret_cast<const uint2 *>(list + warp_off[w]) + lane;
+  double fx = 0.0, fy = 0.0, fz = 0.0;
   const long long cl2b = __double_as_longlong(fc.CL2);
 
   constexpr int UNR = FORCE_UNROLL;
-  unsigned en = (len > 0) ? __ldg(lp) : 0u;
+  uint2 en = (len2 > 0) ? __ldg(lp) : make_uint2(0u, 0u);
 #pragma unroll UNR
-  for (int k = 0; k < len; k++) {
-    const unsigned e = en;
-    if (k + 1 < len) en = __ldg(lp + (long long)(k + 1) * 32);
-    double jx, jy, jz;
-    ld_q256(q + (e & 0x3FFFFFFFu), jx, jy, jz);
-    {
-      const double dx = jx - ax, dy = jy - ay, dz = jz - az;
-      const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-      double df = pair_df<VARIANT>(r2, fc);
-      // r2 > CL2 (fcalculator.cc:209-211) or not a listed partner of a: no contribution
-      if ((__double_as_longlong(r2) > cl2b) || !(e & 0x80000000u)) df = 0.0;
-      fax = fma(df, dx, fax);
-      fay = fma(df, dy, fay);
-      faz = fma(df, dz, faz);
-    }
-    {
-      const double dx = jx - bx, dy = jy - by, dz = jz - bz;
-      const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-      double df = pair_df<VARIANT>(r2, fc);
-      if ((__double_as_longlong(r2) > cl2b) || !(e & 0x40000000u)) df = 0.0;
-      fbx = fma(df, dx, fbx);
-      fby = fma(df, dy, fby);
-      fbz = fma(df, dz, fbz);
-    }
+  for (int k = 0; k < len2; k++) {
+    const uint2 e = en;
+    if (k + 1 < len2) en = __ldg(lp + (long long)(k + 1) * 32);
+    double j0x, j0y, j0z, j1x, j1y, j1z;
+    ld_q256(q + e.x, j0x, j0y, j0z);
+    ld_q256(q + e.y, j1x, j1y, j1z);
+    pair_accumulate<VARIANT>(ax, ay, az, j0x, j0y, j0z, cl2b, fc, fx, fy, fz);
+    pair_accumulate<VARIANT>(ax, ay, az, j1x, j1y, j1z, cl2b, fc, fx, fy, fz);
   }
-  if (!act) return;
-  if (info & 0x80000000u) {  // the two locals of this thread are listed partners of each other
-    const double dx = bx - ax, dy = by - ay, dz = bz - az;
-    const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-    double df = pair_df<VARIANT>(r2, fc);
-    if (__double_as_longlong(r2) > cl2b) df = 0.0;
-    fax = fma(df, dx, fax); fay = fma(df, dy, fay); faz = fma(df, dz, faz);
-    fbx = fma(-df, dx, fbx); fby = fma(-df, dy, fby); fbz = fma(-df, dz, fbz);
+#pragma unroll
+  for (int o = kG / 2; o > 0; o >>= 1) {
+    fx += __shfl_xor_sync(0xffffffffu, fx, o);
+    fy += __shfl_xor_sync(0xffffffffu, fy, o);
+    fz += __shfl_xor_sync(0xffffffffu, fz, o);
   }
+  if (!act || (lane % kG) != 0) return;
   if (KICK) {
     double4 pa = p[a];
-    pa.x += fax; pa.y += fay; pa.z += faz;
+    pa.x += fx; pa.y += fy; pa.z += fz;
     p[a] = pa;
-    if (two) {
-      double4 pb = p[a + 1];
-      pb.x += fbx; pb.y += fby; pb.z += fbz;
-      p[a + 1] = pb;
-    }
   } else {
     const long long ra = ref_of_slot[a];
-    fout[3 * ra + 0] = fax; fout[3 * ra + 1] = fay; fout[3 * ra + 2] = faz;
-    if (two) {
-      const long long rb = ref_of_slot[a + 1];
-      fout[3 * rb + 0] = fbx; fout[3 * rb + 1] = fby; fout[3 * rb + 2] = fbz;
-    }
+    fout[3 * ra + 0] = fx; fout[3 * ra + 1] = fy; fout[3 * ra + 2] = fz;
   }
 }
 
@@ -179,15 +164,13 @@ static ForceConsts make_fc(const Unit *u) {
   return fc;
 }
 
-#define FORCE_ARGS(F) u->q.ptr, u->p.ptr, F, u->list.ptr, u->warp_off.ptr, u->warp_len.ptr, u->tp_info.ptr, \
-                      u->ref_of_slot.ptr, (int)u->nthreads, fc
-
-int force_prepare(Unit *) { return MDB200_OK; }
+#define FORCE_ARGS(F) u->q.ptr, u->p.ptr, F, u->list.ptr, u->warp_off.ptr, u->warp_len.ptr, u->ref_of_slot.ptr, \
+                      (int)u->pn, u->nwarps, fc
 
 int force_kick(Unit *u) {
-  if (u->pn == 0 || u->nthreads == 0) return MDB200_OK;
+  if (u->pn == 0 || u->nwarps == 0) return MDB200_OK;
   const int tpb = 128;
-  const unsigned grid = (unsigned)((u->nthreads + tpb - 1) / tpb);
+  const unsigned grid = (unsigned)((u->nwarps * 32 + tpb - 1) / tpb);
   ForceConsts fc = make_fc(u);
   switch (force_variant()) {
     case 0: k_force<0, true><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(nullptr)); break;
@@ -208,7 +191,7 @@ int force_impulse(Unit *u, double *f3_host, long long cap_rows) {
   DevBuf<double> f;
   MDB_TRY(f.ensure((size_t)u->pn * 3));
   const int tpb = 128;
-  const unsigned grid = (unsigned)((u->nthreads + tpb - 1) / tpb);
+  const unsigned grid = (unsigned)((u->nwarps * 32 + tpb - 1) / tpb);
   ForceConsts fc = make_fc(u);
   switch (force_variant()) {
     case 0: k_force<0, false><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(f.ptr)); break;

@@ -40,13 +40,12 @@ __device__ __forceinline__ void pair_uw(double dx, double dy, double dz, double 
   we += ((24.0 * r6 - 48.0) / (r6 * r6 * r2) + C2 * 8.0) * r2;
 }
 
-// K over locals (grid-stride over particles) and U, W over the list (grid-stride over the force
-// kernel's threads: two locals per thread, union rows with per-entry flag bits, cells.cu).
+// K over locals (grid-stride over particles) and U, W over the list (grid-stride over force-warps: kG lanes
+// per local, each lane takes every kG-th entry of the row, unit.h).
 __global__ void __launch_bounds__(TPB)
 k_observe(const double4 *__restrict__ q, const double4 *__restrict__ p, const unsigned *__restrict__ list,
-          const long long *__restrict__ warp_off, const int *__restrict__ row_count,
-          const unsigned *__restrict__ tp_info, int pn, int nt, int have_list, double CL2, double C2, double C0,
-          double *__restrict__ partial) {
+          const long long *__restrict__ warp_off, const int *__restrict__ warp_len, int pn, long long nwarps,
+          int have_list, double CL2, double C2, double C0, double *__restrict__ partial) {
   __shared__ double sh[TPB / 32];
   double k = 0.0, uu = 0.0, ww = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pn;
@@ -58,26 +57,22 @@ k_observe(const double4 *__restrict__ q, const double4 *__restrict__ p, const un
     k += 0.5 * pp.w * pp.w;
   }
   if (have_list) {
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nt;
-         t += (long long)gridDim.x * blockDim.x) {
-      const unsigned info = tp_info[t];
-      const int a = (int)(info & 0x3FFFFFFFu);
-      const bool two = (info & 0x40000000u) != 0;
-      const double4 qa = q[a];
-      const double4 qb = two ? q[a + 1] : qa;
-      const long long base = warp_off[t >> 5] + (t & 31);
-      const int n = row_count[t];
+    const int lane = threadIdx.x & 31;
+    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < nwarps; w += wstride) {
+      const long long a = w * kPW + lane / kG;
+      const double4 qa = q[a < pn ? a : (long long)pn - 1];
+      const long long base = warp_off[w];
+      const int steps = warp_len[w];
       double ue = 0.0, we = 0.0;
-      for (int e = 0; e < n; e++) {
-        const unsigned en = list[base + (long long)e * 32];
-        const double4 qj = q[en & 0x3FFFFFFFu];
-        if (en & 0x80000000u) pair_uw(qj.x - qa.x, qj.y - qa.y, qj.z - qa.z, CL2, C2, C0, ue, we);
-        if (en & 0x40000000u) pair_uw(qj.x - qb.x, qj.y - qb.y, qj.z - qb.z, CL2, C2, C0, ue, we);
+      for (int s = 0; s < steps; s++) {
+        // padding entries point at the far-away sentinel particle: r2 > CL2, no contribution
+        const double4 qj = q[list[base + list_word(s, lane)]];
+        pair_uw(qj.x - qa.x, qj.y - qa.y, qj.z - qa.z, CL2, C2, C0, ue, we);
       }
-      // every directed entry carries weight 0.5 (see the header); the a-b pair is stored once: weight 1
+      // every directed entry carries weight 0.5 (see the header)
       uu += 0.5 * ue;
       ww += 0.5 * we;
-      if (info & 0x80000000u) pair_uw(qb.x - qa.x, qb.y - qa.y, qb.z - qa.z, CL2, C2, C0, uu, ww);
     }
   }
   double s0 = block_sum(k, sh), s1 = block_sum(uu, sh), s2 = block_sum(ww, sh);
@@ -108,11 +103,11 @@ static int observe_impl(Unit *u, double out[4], bool with_list) {
   out[0] = out[1] = out[2] = 0.0;
   out[3] = (double)u->pn;
   if (u->pn == 0) return MDB200_OK;
-  long long nb = (u->pn + TPB - 1) / TPB;
+  long long nb = (u->pn * kG + TPB - 1) / TPB;
   if (nb > MAXBLK) nb = MAXBLK;
   MDB_TRY(u->partial.ensure((size_t)3 * MAXBLK + 8));
-  k_observe<<<(unsigned)nb, TPB, 0, u->stream>>>(u->q.ptr, u->p.ptr, u->list.ptr, u->warp_off.ptr, u->row_count.ptr,
-                                                  u->tp_info.ptr, (int)u->pn, (int)u->nthreads,
+  k_observe<<<(unsigned)nb, TPB, 0, u->stream>>>(u->q.ptr, u->p.ptr, u->list.ptr, u->warp_off.ptr, u->warp_len.ptr,
+                                                  (int)u->pn, u->nwarps,
                                                   (with_list && u->list_initialized) ? 1 : 0, u->c.CL2, u->c.C2, u->c.C0,
                                                   u->partial.ptr);
   k_observe_final<<<1, TPB, 0, u->stream>>>(u->partial.ptr, (int)nb, u->ctrl);

@@ -137,19 +137,20 @@ struct Unit {
   DevBuf<double4> mig_send_q, mig_send_p, mig_recv_q, mig_recv_p;
   DevBuf<int> mig_send_t, mig_recv_t;
 
-  // full neighbour list, warp-interleaved: entry k of lane l of warp w at
-  // list[warp_off[w] + k*32 + l]; rows padded to the warp maximum with the sentinel index
-  // One force/search THREAD owns two locals of one cell (slots a, a+1): tp_info[t] = a | two<<30 | ab<<31.
-  // Its row is the union of the two neighbour rows; entry = partner slot | (partner of a)<<31 | (of b)<<30.
-  DevBuf<unsigned> tp_info;
-  DevBuf<int> cell_nthr, cell_thr_start;
-  long long nthreads = 0;
-  DevBuf<int> row_count;          // entries per thread
-  DevBuf<int> warp_len;
-  DevBuf<long long> warp_off;
+  // FULL neighbour list (every local's row holds all its partners), G = LANES_PER_LOCAL lanes per local:
+  // force-warp w owns the PW = 32 / G locals in slots [PW w, PW w + PW); entry e of the local in group m
+  // is handled by lane G m + (e % G) at step k = e / G and stored at
+  //   list[warp_off[w] + 64 (k >> 1) + 2 lane + (k & 1)]
+  // so that one 8-byte load per lane fetches two steps and a warp's load is one contiguous 256-byte run.
+  // Row order: cells.cu ("rainbow" order); rows are padded to the warp's (even) step count with the sentinel.
+  long long nwarps = 0;           // force-warps = ceil(pn / PW)
+  DevBuf<int> row_count;          // entries per local slot
+  DevBuf<unsigned> row_cls;       // entries per class (partner index mod 4), 4 x 8 bits
+  DevBuf<int> warp_len;           // steps per force-warp (even)
+  DevBuf<long long> warp_off;     // first list word of the force-warp (multiple of 64)
   DevBuf<unsigned> list;
-  long long list_entries = 0;
-  long long npairs = 0;
+  long long list_entries = 0;     // padded entries
+  long long npairs = 0;           // reference-style count of listed pairs (meshlist.cc:309)
   int max_row = 0;
 
   // expiry check
@@ -179,6 +180,15 @@ struct Unit {
 };
 
 inline int sentinel_index(const Unit *u) { return (int)u->cap_t; }
+
+// lanes that share one local in the force / observe kernels (power of two, <= 32)
+#ifndef LANES_PER_LOCAL
+#define LANES_PER_LOCAL 4
+#endif
+constexpr int kG = LANES_PER_LOCAL;
+constexpr int kPW = 32 / kG;  // locals per force-warp
+// list word of (step k, lane l) relative to the warp's first word
+__host__ __device__ inline long long list_word(int k, int lane) { return 64LL * (k >> 1) + 2 * lane + (k & 1); }
 
 // ---------------------------------------------------------------------------------------------
 // kernels / phases (host launchers; all asynchronous on u->stream unless stated)
@@ -214,7 +224,6 @@ int langevin_kick(Unit *u);
 int expiry_check_local(Unit *u, int *expired);                           // sync
 
 // force.cu
-int force_prepare(Unit *u);  // experiment: SoA copies of the positions for gather variants 3/4
 int force_kick(Unit *u);
 int force_impulse(Unit *u, double *f3_host, long long cap_rows);         // sync
 

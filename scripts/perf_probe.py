@@ -46,10 +46,9 @@ def main():
         print("L=%g N=%d tn=%d npairs=%d (%.2f/particle) upload %.3fs first build %.3fs" % (
             L, n, c["tn"], c["npairs"], c["npairs"] / n, t1 - t0, t2 - t1), flush=True)
         ls = u.list_stats()
-        print("  list: threads %d (singles %d) entries %d padded %d (+%.1f%%) mean row %.1f (two-local rows %.1f) max %d" % (
-            ls["threads"], ls["single_threads"], ls["entries"], ls["padded_entries"],
-            100.0 * (ls["padded_entries"] / max(ls["entries"], 1) - 1), ls["entries"] / max(ls["threads"], 1),
-            ls["entries_two"] / max(ls["threads"] - ls["single_threads"], 1), ls["max_row"]), flush=True)
+        print("  list: %d force-warps, %d lanes per local, entries %d padded %d (+%.1f%%) mean row %.1f max %d" % (
+            ls["warps"], ls["lanes_per_local"], ls["entries"], ls["padded_entries"],
+            100.0 * (ls["padded_entries"] / max(ls["entries"], 1) - 1), ls["entries"] / max(n, 1), ls["max_row"]), flush=True)
         mdm.Calculate(20)  # warm-up
         u.synchronize()
         o0 = mdm.observables()
