@@ -77,10 +77,13 @@ __device__ __forceinline__ void ld_q256(const double4 *p, double &x, double &y, 
 }
 
 #ifndef FORCE_UNROLL
-#define FORCE_UNROLL 2
+#define FORCE_UNROLL 1
 #endif
 #ifndef FORCE_MINBLK
 #define FORCE_MINBLK 10
+#endif
+#ifndef FORCE_TPB
+#define FORCE_TPB 128
 #endif
 
 template <int VARIANT>
@@ -98,7 +101,7 @@ __device__ __forceinline__ void pair_accumulate(double ax, double ay, double az,
 }
 
 template <int VARIANT, bool KICK>
-__global__ void __launch_bounds__(128, FORCE_MINBLK)
+__global__ void __launch_bounds__(FORCE_TPB, FORCE_MINBLK)
 k_force(const double4 *__restrict__ q, double4 *__restrict__ p, double *__restrict__ fout,
         const unsigned *__restrict__ list, const long long *__restrict__ warp_off, const int *__restrict__ warp_len,
         const int *__restrict__ ref_of_slot, int pn, long long nwarps, ForceConsts fc) {
@@ -169,7 +172,7 @@ static ForceConsts make_fc(const Unit *u) {
 
 int force_kick(Unit *u) {
   if (u->pn == 0 || u->nwarps == 0) return MDB200_OK;
-  const int tpb = 128;
+  const int tpb = FORCE_TPB;
   const unsigned grid = (unsigned)((u->nwarps * 32 + tpb - 1) / tpb);
   ForceConsts fc = make_fc(u);
   switch (force_variant()) {
@@ -190,7 +193,7 @@ int force_impulse(Unit *u, double *f3_host, long long cap_rows) {
   if (u->pn == 0) return MDB200_OK;
   DevBuf<double> f;
   MDB_TRY(f.ensure((size_t)u->pn * 3));
-  const int tpb = 128;
+  const int tpb = FORCE_TPB;
   const unsigned grid = (unsigned)((u->nwarps * 32 + tpb - 1) / tpb);
   ForceConsts fc = make_fc(u);
   switch (force_variant()) {
