@@ -3,7 +3,9 @@
 // cells.cu / exchange.cu / integrate.cu / force.cu / observe.cu.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <algorithm>
 #include <map>
 #include <set>
@@ -223,8 +225,31 @@ __global__ void k_gather_ref_order_i(const int *__restrict__ src, const int *__r
 // ---------------------------------------------------------------------------------------------
 // rebuild = MDManager::MakePairList (mdmanager.cc:262-280)
 // ---------------------------------------------------------------------------------------------
+struct DebugClock {
+  bool on;
+  double t0;
+  cudaStream_t st;
+  static double now() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+  }
+  explicit DebugClock(cudaStream_t s) : on(getenv("MDB200_DEBUG") != nullptr), t0(0), st(s) {
+    if (on) { cudaStreamSynchronize(st); t0 = now(); }
+  }
+  void lap(const char *what) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    const double t = now();
+    fprintf(stderr, "[mdb200] rebuild %-28s %9.3f ms\n", what, 1e3 * (t - t0));
+    t0 = t;
+  }
+};
+
 static int make_pairlist(Unit **us, int n) {
   std::vector<long long> cnt(n);
+  for (int i = 0; i < n; i++) us[i]->vmax_ready = false;  // migration changes the set of locals
+  DebugClock dbg(us[0]->stream);
   std::vector<PhaseTimer *> timers;
   struct TimerScope {
     std::vector<PhaseTimer *> &t;
@@ -251,12 +276,14 @@ static int make_pairlist(Unit **us, int n) {
     MDB_TRY(comm_migrate(us, n, dir, cnt.data()));
     MDB_TRY(stage_barrier(us, n));
   }
+  dbg.lap("migration");
   for (int i = 0; i < n; i++) {
     DeviceGuard g(us[i]->device);
     MDB_TRY(wrap_periodic(us[i]));
     // --- MeshList cell sort: locals become cell-ordered; tn := pn (mdmanager.cc:264-268)
     MDB_TRY(cell_sort_locals(us[i]));
   }
+  dbg.lap("wrap + cell sort");
   // --- border lists + first ghost exchange (mdmanager.cc:269-275)
   for (int dir = 0; dir < 6; dir++) {
     for (int i = 0; i < n; i++) {
@@ -267,6 +294,7 @@ static int make_pairlist(Unit **us, int n) {
     MDB_TRY(comm_border_setup(us, n, dir));
     MDB_TRY(stage_barrier(us, n));
   }
+  dbg.lap("border lists + ghosts");
   // --- per unit MDUnit::MakePairList (mdunit.cc:194-198)
   for (int i = 0; i < n; i++) {
     Unit *u = us[i];
@@ -282,6 +310,7 @@ static int make_pairlist(Unit **us, int n) {
     u->nbuilds++;
     MDB_TRY(pull_error_word(u));
   }
+  dbg.lap("ghost bins + snapshot + search");
   return MDB200_OK;
 }
 
@@ -385,12 +414,12 @@ static int calculate(Unit **us, int n) {
     for (int i = 0; i < n; i++) {
       DeviceGuard g(us[i]->device);
       {
+        // kick and second half drift in one kernel (force.cu, FORCE_KICK_DRIFT)
         PhaseTimer t(us[i], PH_FORCE);
         force_timer_begin(us[i]);
-        MDB_TRY(force_kick(us[i]));
+        MDB_TRY(force_kick_drift(us[i]));
         force_timer_end(us[i]);
       }
-      { PhaseTimer t(us[i], PH_INTEG); MDB_TRY(drift_half(us[i])); }
     }
   }
   for (int i = 0; i < n; i++) us[i]->step_count++;
@@ -535,6 +564,7 @@ int mdb200_upload(mdb200_unit *h, const double (*q)[4], const double (*p)[4], co
   u->tn = pn;
   u->scratch_tail = pn;
   u->list_initialized = false;
+  u->vmax_ready = false;
   u->npairs = 0;
   u->list_entries = 0;
   for (int d = 0; d < 6; d++) { u->n_border[d] = 0; u->recv_cnt[d] = 0; u->recv_off[d] = pn; }

@@ -20,6 +20,7 @@
 // force kernel's gathers of partner positions hit nearby lines; ghosts keep slot == reference
 // index in [pn,tn).  ref_of_slot / slot_of_ref translate; results handed back through the
 // C-ABI are always in reference indices.
+#include <stdlib.h>
 #include <string.h>
 #include <utility>
 #include "unit.h"
@@ -156,7 +157,7 @@ int ensure_capacity(Unit *u, long long need_p, long long need_t) {
   if (!grow) return MDB200_OK;
   cudaStream_t st = u->stream;
   MDB_TRY(u->q.ensure((size_t)nct + 1, true, st));
-  MDB_TRY(u->q_alt.ensure((size_t)nct + 1, false, st));
+  MDB_TRY(u->q_alt.ensure((size_t)nct + 1, true, st));  // ghosts live in both position buffers
   MDB_TRY(u->q0.ensure((size_t)nct + 1, true, st));
   MDB_TRY(u->p.ensure((size_t)ncp + 1, true, st));
   MDB_TRY(u->p_alt.ensure((size_t)ncp + 1, false, st));
@@ -614,7 +615,12 @@ int build_pair_list(Unit *u) {
   u->list_entries = entries;
   u->npairs = (long long)u->ctrl_host->npairs;
   u->max_row = u->ctrl_host->max_row;
-  MDB_TRY(u->list.ensure((size_t)entries + 64));
+  if ((size_t)entries + 64 > u->list.cap && getenv("MDB200_DEBUG"))
+    fprintf(stderr, "[mdb200] list grows: %lld entries > capacity %zu\n", entries, u->list.cap);
+  // Head-room: rows of a freshly generated lattice grow by ~20 % once it thermalises (the next FCC shell
+  // sits just outside the search radius), and re-allocating a multi-GB list inside the step loop stalls
+  // for hundreds of ms (cudaMalloc + cudaFree of several GB) -- so allocate 40 % more than needed.
+  if ((size_t)entries + 64 > u->list.cap) MDB_TRY(u->list.ensure((size_t)entries + (size_t)entries * 2 / 5 + 64));
   k_pair_search<true><<<nblk(nthr, tpb), tpb, 0, u->stream>>>(
       u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr, u->gcell_items.ptr, u->ref_of_slot.ptr, u->row_count.ptr, u->row_cls.ptr,
       u->warp_off.ptr, u->warp_len.ptr, u->list.ptr, (int)pn, sentinel_index(u), u->c, u->ctrl);

@@ -226,7 +226,7 @@ int comm_border_refresh(Unit **us, int n, int dir) {
     cudaSetDevice(u->device);
     if (!is_remote(u, dir)) {
       Unit *d = u->nbr[dir];
-      MDB_TRY(ghost_put_to(u, dir, d->q.ptr + d->recv_off[dir], u->stream));
+      MDB_TRY(ghost_put_to(u, dir, d->q.ptr + d->recv_off[dir], d->q_alt.ptr + d->recv_off[dir], u->stream));
       continue;
     }
     MDB_TRY(ghost_pack(u, dir));
@@ -238,6 +238,10 @@ int comm_border_refresh(Unit **us, int n, int dir) {
       MDB_NCCL(g_nccl.Recv(u->q.ptr + u->recv_off[dir], (size_t)u->recv_cnt[dir] * 4, ncclDouble, from, g_comm.comm,
                            u->stream));
     MDB_NCCL(g_nccl.GroupEnd());
+    // positions are double-buffered: the ghost window lives in both buffers
+    if (u->recv_cnt[dir] > 0)
+      MDB_CUDA(cudaMemcpyAsync(u->q_alt.ptr + u->recv_off[dir], u->q.ptr + u->recv_off[dir],
+                               sizeof(double4) * (size_t)u->recv_cnt[dir], cudaMemcpyDeviceToDevice, u->stream));
   }
   return MDB200_OK;
 }

@@ -18,7 +18,7 @@ int comm_border_refresh(Unit **us, int n, int dir);
 int comm_allreduce_or(Unit **us, int n, int *flag);
 int comm_allreduce_sum(Unit **us, int n, double *v, int cnt);
 
-int ghost_put_to(Unit *s, int dir, double4 *dst, cudaStream_t st);
+int ghost_put_to(Unit *s, int dir, double4 *dst, double4 *dst2, cudaStream_t st);
 int observe_kinetic(Unit *u, double out[4]);
 int expiry_check_launch(Unit *u);
 

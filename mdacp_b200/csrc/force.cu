@@ -23,6 +23,7 @@
 // Roofline: algorithmic HBM bytes per particle = 4 B x P (half-list indices) + 96 B
 // (q read, p read + write), 30 flop per listed unordered pair.
 #include <stdlib.h>
+#include <utility>
 #include "unit.h"
 
 namespace mdb {
@@ -44,6 +45,7 @@ __device__ __forceinline__ double fast_rcp(double x) {
 }
 
 struct ForceConsts {
+  double dt2;     // dt / 2
   double CL2;
   double c24dt;   // 24 dt
   double c48dt;   // 48 dt
@@ -82,6 +84,12 @@ __device__ __forceinline__ void ld_q256(const double4 *p, double &x, double &y, 
 #ifndef FORCE_MINBLK
 #define FORCE_MINBLK 10
 #endif
+#ifndef FORCE_PF_L1
+#define FORCE_PF_L1 2
+#endif
+#ifndef FORCE_PF_CHUNK
+#define FORCE_PF_CHUNK 0
+#endif
 #ifndef FORCE_TPB
 #define FORCE_TPB 128
 #endif
@@ -100,11 +108,19 @@ __device__ __forceinline__ void pair_accumulate(double ax, double ay, double az,
   fz = fma(df, dz, fz);
 }
 
-template <int VARIANT, bool KICK>
+// MODE 0: impulses to fout (parity probe).  MODE 1: kick, p += F dt (ForceCalculator::CalculateForce).
+// MODE 2: kick fused with the second half drift of MDManager::CalculateForce (mdmanager.cc:151-157):
+//   q_out[a] = q[a] + p_new dt/2 with the same non-fused mul/add as k_drift_half (bit-identical), written to
+//   the OTHER position buffer because q is still being gathered by other warps; the caller swaps the
+//   buffers.  It also leaves max |p_new|^2 in ctrl->vmax2_bits for the next step's velocity-budget test
+//   (pairlist.cc:48-65), so that test needs no pass of its own.
+enum { FORCE_IMPULSE = 0, FORCE_KICK = 1, FORCE_KICK_DRIFT = 2 };
+template <int VARIANT, int MODE>
 __global__ void __launch_bounds__(FORCE_TPB, FORCE_MINBLK)
 k_force(const double4 *__restrict__ q, double4 *__restrict__ p, double *__restrict__ fout,
         const unsigned *__restrict__ list, const long long *__restrict__ warp_off, const int *__restrict__ warp_len,
-        const int *__restrict__ ref_of_slot, int pn, long long nwarps, ForceConsts fc) {
+        const int *__restrict__ ref_of_slot, int pn, long long nwarps, double4 *__restrict__ q_out, Ctrl *ctrl,
+        ForceConsts fc) {
   const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= nwarps) return;
   const int lane = threadIdx.x & 31;
@@ -118,10 +134,21 @@ k_force(const double4 *__restrict__ q, double4 *__restrict__ p, double *__restri
   const long long cl2b = __double_as_longlong(fc.CL2);
 
   constexpr int UNR = FORCE_UNROLL;
+#if FORCE_PF_CHUNK
+  // one instruction: lane l pulls 128-byte line l of this warp's list chunk (len2 x 256 B) towards the SM
+  if (lane * 128 < len2 * 256)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(lp - lane) + lane * 128));
+#endif
   uint2 en = (len2 > 0) ? __ldg(lp) : make_uint2(0u, 0u);
 #pragma unroll UNR
   for (int k = 0; k < len2; k++) {
     const uint2 e = en;
+#if FORCE_PF_L1
+    // fire-and-forget: the list words of step-pair k + FORCE_PF_L1 into L1, so that the (compiler-scheduled)
+    // load of the next words never waits on L2 / HBM -- ptxas otherwise sinks that load below the arithmetic,
+    // which serialises its latency behind the gather's (1.15 -> 1.42 ms at 5.5 M particles)
+    if (k + FORCE_PF_L1 < len2) asm volatile("prefetch.global.L1 [%0];" ::"l"(lp + (long long)(k + FORCE_PF_L1) * 32));
+#endif
     if (k + 1 < len2) en = __ldg(lp + (long long)(k + 1) * 32);
     double j0x, j0y, j0z, j1x, j1y, j1z;
     ld_q256(q + e.x, j0x, j0y, j0z);
@@ -135,14 +162,35 @@ k_force(const double4 *__restrict__ q, double4 *__restrict__ p, double *__restri
     fy += __shfl_xor_sync(0xffffffffu, fy, o);
     fz += __shfl_xor_sync(0xffffffffu, fz, o);
   }
-  if (!act || (lane % kG) != 0) return;
-  if (KICK) {
+  const bool writer = act && (lane % kG) == 0;
+  if (MODE == FORCE_IMPULSE) {
+    if (writer) {
+      const long long ra = ref_of_slot[a];
+      fout[3 * ra + 0] = fx; fout[3 * ra + 1] = fy; fout[3 * ra + 2] = fz;
+    }
+    return;
+  }
+  double v2 = 0.0;
+  if (writer) {
     double4 pa = p[a];
     pa.x += fx; pa.y += fy; pa.z += fz;
     p[a] = pa;
-  } else {
-    const long long ra = ref_of_slot[a];
-    fout[3 * ra + 0] = fx; fout[3 * ra + 1] = fy; fout[3 * ra + 2] = fz;
+    if (MODE == FORCE_KICK_DRIFT) {
+      // fcalculator.cc:22-32, no FMA contraction: identical to k_drift_half
+      q_out[a] = make_double4(__dadd_rn(ax, __dmul_rn(pa.x, fc.dt2)), __dadd_rn(ay, __dmul_rn(pa.y, fc.dt2)),
+                              __dadd_rn(az, __dmul_rn(pa.z, fc.dt2)), 0.0);
+      v2 = __dadd_rn(__dadd_rn(__dmul_rn(pa.x, pa.x), __dmul_rn(pa.y, pa.y)), __dmul_rn(pa.z, pa.z));
+    }
+  }
+  if (MODE == FORCE_KICK_DRIFT) {
+#pragma unroll
+    for (int o = 16; o >= kG; o >>= 1) v2 = fmax(v2, __shfl_xor_sync(0xffffffffu, v2, o));
+    if (lane == 0) {
+      // non-negative doubles order like their bit patterns; the maximum settles after a few warps, so the
+      // plain read filters out almost every atomic
+      const unsigned long long b = (unsigned long long)__double_as_longlong(v2);
+      if (b > *(volatile unsigned long long *)&ctrl->vmax2_bits) atomicMax(&ctrl->vmax2_bits, b);
+    }
   }
 }
 
@@ -160,6 +208,7 @@ static ForceConsts make_fc(const Unit *u) {
   ForceConsts fc;
   fc.CL2 = u->c.CL2;
   fc.dt = u->c.dt;
+  fc.dt2 = u->c.dt2;
   fc.c24dt = 24.0 * u->c.dt;
   fc.c48dt = 48.0 * u->c.dt;
   fc.c2x8 = u->c.C2 * 8.0;
@@ -167,21 +216,43 @@ static ForceConsts make_fc(const Unit *u) {
   return fc;
 }
 
-#define FORCE_ARGS(F) u->q.ptr, u->p.ptr, F, u->list.ptr, u->warp_off.ptr, u->warp_len.ptr, u->ref_of_slot.ptr, \
-                      (int)u->pn, u->nwarps, fc
+#define FORCE_ARGS(F, QOUT) u->q.ptr, u->p.ptr, F, u->list.ptr, u->warp_off.ptr, u->warp_len.ptr, u->ref_of_slot.ptr, \
+                            (int)u->pn, u->nwarps, QOUT, u->ctrl, fc
 
-int force_kick(Unit *u) {
-  if (u->pn == 0 || u->nwarps == 0) return MDB200_OK;
+static int force_launch(Unit *u, int mode, double *fout) {
   const int tpb = FORCE_TPB;
   const unsigned grid = (unsigned)((u->nwarps * 32 + tpb - 1) / tpb);
   ForceConsts fc = make_fc(u);
+#define LAUNCH(V)                                                                                          \
+  do {                                                                                                     \
+    if (mode == FORCE_IMPULSE) k_force<V, FORCE_IMPULSE><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(fout, nullptr)); \
+    else if (mode == FORCE_KICK) k_force<V, FORCE_KICK><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(nullptr, nullptr)); \
+    else k_force<V, FORCE_KICK_DRIFT><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(nullptr, u->q_alt.ptr));     \
+  } while (0)
   switch (force_variant()) {
-    case 0: k_force<0, true><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(nullptr)); break;
-    case 2: k_force<2, true><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(nullptr)); break;
-    default: k_force<1, true><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(nullptr)); break;
+    case 0: LAUNCH(0); break;
+    case 2: LAUNCH(2); break;
+    default: LAUNCH(1); break;
   }
+#undef LAUNCH
   u->launches++;
   MDB_CUDA(cudaGetLastError());
+  return MDB200_OK;
+}
+
+// ForceCalculator::CalculateForce (fcalculator.cc:35-50)
+int force_kick(Unit *u) {
+  u->vmax_ready = false;
+  if (u->pn == 0 || u->nwarps == 0) return MDB200_OK;
+  return force_launch(u, FORCE_KICK, nullptr);
+}
+
+// CalculateForce + UpdatePositionHalf of MDManager::CalculateForce (mdmanager.cc:151-157) in one kernel
+int force_kick_drift(Unit *u) {
+  if (u->pn == 0 || u->nwarps == 0) return MDB200_OK;
+  MDB_TRY(force_launch(u, FORCE_KICK_DRIFT, nullptr));
+  std::swap(u->q, u->q_alt);  // ghosts live in both buffers (exchange.cu)
+  u->vmax_ready = true;
   return MDB200_OK;
 }
 
@@ -193,16 +264,7 @@ int force_impulse(Unit *u, double *f3_host, long long cap_rows) {
   if (u->pn == 0) return MDB200_OK;
   DevBuf<double> f;
   MDB_TRY(f.ensure((size_t)u->pn * 3));
-  const int tpb = FORCE_TPB;
-  const unsigned grid = (unsigned)((u->nwarps * 32 + tpb - 1) / tpb);
-  ForceConsts fc = make_fc(u);
-  switch (force_variant()) {
-    case 0: k_force<0, false><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(f.ptr)); break;
-    case 2: k_force<2, false><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(f.ptr)); break;
-    default: k_force<1, false><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(f.ptr)); break;
-  }
-  u->launches++;
-  MDB_CUDA(cudaGetLastError());
+  MDB_TRY(force_launch(u, FORCE_IMPULSE, f.ptr));
   MDB_CUDA(cudaMemcpyAsync(f3_host, f.ptr, sizeof(double) * 3 * (size_t)u->pn, cudaMemcpyDeviceToHost, u->stream));
   MDB_CUDA(cudaStreamSynchronize(u->stream));
   f.release();

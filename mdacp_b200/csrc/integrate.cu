@@ -69,6 +69,7 @@ __global__ void k_scale_p(double4 *__restrict__ p, int pn, double f) {
 }
 
 int heatbath_momenta(Unit *u) {
+  u->vmax_ready = false;
   if (u->pn == 0) return MDB200_OK;
   // exp() evaluated on the host exactly where the reference evaluates it (fcalculator.cc:756)
   const double exp1 = exp(-u->c.dt2 * u->zeta);
@@ -135,6 +136,7 @@ __global__ void k_langevin(double4 *__restrict__ p, const int *__restrict__ ref_
 }
 
 int langevin_kick(Unit *u) {
+  u->vmax_ready = false;
   if (u->pn == 0) return MDB200_OK;
   const double dt = u->c.dt;
   const double g = u->prm.heatbath_gamma;
@@ -156,6 +158,26 @@ int langevin_kick(Unit *u) {
 // Stage 1: velocity budget (pairlist.cc:34-36, 48-65).  max |p|^2 over locals; non-negative
 // doubles order like their bit patterns, so one 64-bit atomicMax per block suffices.  The last
 // block to finish does the scalar bookkeeping.
+// scalar bookkeeping of PairList::UpdatePairListValidity (pairlist.cc:48-65) once max |p|^2 is known
+__device__ __forceinline__ void expiry_budget(Ctrl *ctrl, double dt, double BL) {
+  double bl = ctrl->buffer_length;
+  if (bl > 0.0) {
+    double vmax = sqrt(bits_d(atomicAdd(&ctrl->vmax2_bits, 0ull)));
+    double dec = __dmul_rn(__dmul_rn(vmax, 2.0), dt);
+    if (dec > BL) atomicOr(&ctrl->err, (int)DE_TOOFAST);
+    bl = __dadd_rn(bl, -dec);
+    ctrl->buffer_length = bl;
+  }
+  ctrl->phase = (bl < 0.0) ? 1 : 0;
+  ctrl->expired = 0;
+  ctrl->vmax2_bits = 0ull;
+  ctrl->dr2max_bits = 0ull;
+  ctrl->cand_count = 0;
+  ctrl->ticket[0] = 0u;
+  ctrl->ticket[1] = 0u;
+  ctrl->ticket[2] = 0u;
+}
+
 __global__ void k_expiry_vmax(const double4 *__restrict__ p, int pn, Ctrl *ctrl, double dt, double BL) {
   __shared__ double sh[TPB / 32];
   __shared__ bool last;
@@ -175,24 +197,13 @@ __global__ void k_expiry_vmax(const double4 *__restrict__ p, int pn, Ctrl *ctrl,
   __syncthreads();
   if (last && threadIdx.x == 0) {
     __threadfence();
-    double bl = ctrl->buffer_length;
-    if (bl > 0.0) {
-      double vmax = sqrt(bits_d(atomicAdd(&ctrl->vmax2_bits, 0ull)));
-      double dec = __dmul_rn(__dmul_rn(vmax, 2.0), dt);
-      if (dec > BL) atomicOr(&ctrl->err, (int)DE_TOOFAST);
-      bl = __dadd_rn(bl, -dec);
-      ctrl->buffer_length = bl;
-    }
-    ctrl->phase = (bl < 0.0) ? 1 : 0;
-    ctrl->expired = 0;
-    ctrl->vmax2_bits = 0ull;
-    ctrl->dr2max_bits = 0ull;
-    ctrl->cand_count = 0;
-    ctrl->ticket[0] = 0u;
-    ctrl->ticket[1] = 0u;
-    ctrl->ticket[2] = 0u;
+    expiry_budget(ctrl, dt, BL);
   }
 }
+
+// The same bookkeeping when max |p|^2 is already in ctrl->vmax2_bits (left there by the fused kick + drift
+// kernel, force.cu): one thread.
+__global__ void k_expiry_budget(Ctrl *ctrl, double dt, double BL) { expiry_budget(ctrl, dt, BL); }
 
 // Stage 2: displacement since the snapshot over locals AND ghosts (pairlist.cc:69-83).
 __global__ void k_expiry_disp(const double4 *__restrict__ q, const double4 *__restrict__ q0,
@@ -284,7 +295,11 @@ int expiry_check_launch(Unit *u) {
   MDB_TRY(u->cand.ensure((size_t)(cll > 0 ? cll : 1) + 1));
   MDB_TRY(u->disp.ensure((size_t)u->cap_t + 1));
   u->lifetime++;
-  k_expiry_vmax<<<grid_p, TPB, 0, u->stream>>>(u->p.ptr, (int)u->pn, u->ctrl, u->c.dt, u->c.BL);
+  if (u->vmax_ready)
+    k_expiry_budget<<<1, 1, 0, u->stream>>>(u->ctrl, u->c.dt, u->c.BL);
+  else
+    k_expiry_vmax<<<grid_p, TPB, 0, u->stream>>>(u->p.ptr, (int)u->pn, u->ctrl, u->c.dt, u->c.BL);
+  u->vmax_ready = false;
   k_expiry_disp<<<grid_t, TPB, 0, u->stream>>>(u->q.ptr, u->q0.ptr, u->disp.ptr, (int)u->tn, u->ctrl, u->c.BL);
   k_expiry_cand<<<grid_t, TPB, 0, u->stream>>>(u->q.ptr, u->q0.ptr, u->disp.ptr, u->cand.ptr, (int)u->tn, Nl,
                                                u->ctrl, u->c.SL2, u->c.CL2);

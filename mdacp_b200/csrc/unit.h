@@ -109,6 +109,7 @@ struct Unit {
   long long step_count = 0;       // number of completed Calculate() calls
   int seed = 0;                   // MDUnit::SetSeed
   double zeta = 0.0;              // Variables::Zeta (variables.h:19)
+  bool vmax_ready = false;        // ctrl->vmax2_bits already holds max |p|^2 of the current momenta
 
   // particle store, SLOT order: locals [0,pn) cell-sorted, ghosts [pn,tn) in arrival order
   DevBuf<double4> q, q_alt;       // positions (x,y,z,0)
@@ -225,6 +226,7 @@ int expiry_check_local(Unit *u, int *expired);                           // sync
 
 // force.cu
 int force_kick(Unit *u);
+int force_kick_drift(Unit *u);                                           // kick + second half drift, swaps q / q_alt
 int force_impulse(Unit *u, double *f3_host, long long cap_rows);         // sync
 
 // observe.cu
