@@ -516,7 +516,7 @@ int mdb200_destroy(mdb200_unit *h) {
   for (int d = 0; d < 6; d++) u->border[d].release();
   u->send_buf.release(); u->mig_send_q.release(); u->mig_send_p.release(); u->mig_recv_q.release();
   u->mig_recv_p.release(); u->mig_send_t.release(); u->mig_recv_t.release();
-  u->row_count.release(); u->row_cls.release(); u->warp_len.release(); u->warp_off.release(); u->list.release();
+  u->row_count.release(); u->row_cls.release(); u->force_queue.release(); u->sm_rank.release(); u->warp_len.release(); u->warp_off.release(); u->list.release();
   u->disp.release(); u->cand.release(); u->partial.release();
   if (u->ctrl) cudaFree(u->ctrl);
   if (u->ctrl_host) cudaFreeHost(u->ctrl_host);

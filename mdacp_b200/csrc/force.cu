@@ -90,6 +90,9 @@ __device__ __forceinline__ void ld_q256(const double4 *p, double &x, double &y, 
 #ifndef FORCE_PF_CHUNK
 #define FORCE_PF_CHUNK 0
 #endif
+#ifndef FORCE_PERSIST
+#define FORCE_PERSIST 0
+#endif
 #ifndef FORCE_TPB
 #define FORCE_TPB 128
 #endif
@@ -115,15 +118,15 @@ __device__ __forceinline__ void pair_accumulate(double ax, double ay, double az,
 //   buffers.  It also leaves max |p_new|^2 in ctrl->vmax2_bits for the next step's velocity-budget test
 //   (pairlist.cc:48-65), so that test needs no pass of its own.
 enum { FORCE_IMPULSE = 0, FORCE_KICK = 1, FORCE_KICK_DRIFT = 2 };
+#define FORCE_PARAMS                                                                                              \
+  const double4 *__restrict__ q, double4 *__restrict__ p, double *__restrict__ fout,                             \
+      const unsigned *__restrict__ list, const long long *__restrict__ warp_off, const int *__restrict__ warp_len, \
+      const int *__restrict__ ref_of_slot, int pn, long long nwarps, double4 *__restrict__ q_out, Ctrl *ctrl
+#define FORCE_PASS q, p, fout, list, warp_off, warp_len, ref_of_slot, pn, nwarps, q_out, ctrl
+
+// One force-warp: the kPW locals in slots [w kPW, (w+1) kPW), kG lanes each.
 template <int VARIANT, int MODE>
-__global__ void __launch_bounds__(FORCE_TPB, FORCE_MINBLK)
-k_force(const double4 *__restrict__ q, double4 *__restrict__ p, double *__restrict__ fout,
-        const unsigned *__restrict__ list, const long long *__restrict__ warp_off, const int *__restrict__ warp_len,
-        const int *__restrict__ ref_of_slot, int pn, long long nwarps, double4 *__restrict__ q_out, Ctrl *ctrl,
-        ForceConsts fc) {
-  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= nwarps) return;
-  const int lane = threadIdx.x & 31;
+__device__ __forceinline__ void force_warp(long long w, int lane, FORCE_PARAMS, const ForceConsts &fc) {
   const long long a = w * kPW + lane / kG;
   const bool act = a < pn;
   double ax, ay, az;
@@ -194,6 +197,89 @@ k_force(const double4 *__restrict__ q, double4 *__restrict__ p, double *__restri
   }
 }
 
+// Plain grid: one force-warp per warp.
+template <int VARIANT, int MODE>
+__global__ void __launch_bounds__(FORCE_TPB, FORCE_MINBLK) k_force(FORCE_PARAMS, ForceConsts fc) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= nwarps) return;
+  force_warp<VARIANT, MODE>(w, threadIdx.x & 31, FORCE_PASS, fc);
+}
+
+// PERSISTENT grid with one work queue per SM (FORCE_PERSIST=1).  The force-warps are split into one
+// contiguous range per SM; every resident warp of SM s takes the next force-warp of range s (atomic ticket),
+// so at any moment the ~40 warps of an SM work on ~320 ADJACENT locals whose partners are the same few cell
+// rows and share L1 lines (a round-robin grid puts neighbouring blocks on different SMs).  A warp whose range
+// is exhausted steals from the following ranges, so the result does not depend on block placement.
+// queue[0..nsm) is this launch's tickets; queue_next[0..nsm) is zeroed for the next launch.
+template <int VARIANT, int MODE>
+__global__ void __launch_bounds__(FORCE_TPB, FORCE_MINBLK)
+k_force_persist(FORCE_PARAMS, int nsm, const int *__restrict__ sm_rank, int *queue, int *queue_next,
+                ForceConsts fc) {
+  const int lane = threadIdx.x & 31;
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < nsm; i += blockDim.x) queue_next[i] = 0;
+  unsigned smid;
+  asm("mov.u32 %0, %%smid;" : "=r"(smid));
+  const long long per = (nwarps + nsm - 1) / nsm;
+  int cur = sm_rank[smid & 1023];  // dense rank of this SM (hardware SM ids may have gaps)
+  int ticket = 0;
+  if (lane == 0) ticket = atomicAdd(&queue[cur], 1);
+  for (;;) {
+    const int t = __shfl_sync(0xffffffffu, ticket, 0);
+    const long long w = (long long)cur * per + t;
+    if (t >= per || w >= nwarps) {
+      // own range exhausted: look for a range that still has tickets, 32 queues per probe
+      int found = -1;
+      for (int off = 1; off < nsm && found < 0; off += 32) {
+        const int cand = (cur + off + lane) % nsm;
+        const bool has = (off + lane < nsm) && (*(volatile int *)&queue[cand] < per) &&
+                         ((long long)cand * per + *(volatile int *)&queue[cand] < nwarps);
+        const unsigned m = __ballot_sync(0xffffffffu, has);
+        if (m) found = (cur + off + (__ffs(m) - 1)) % nsm;
+      }
+      if (found < 0) break;
+      cur = found;
+      if (lane == 0) ticket = atomicAdd(&queue[cur], 1);
+      continue;
+    }
+    if (lane == 0) ticket = atomicAdd(&queue[cur], 1);  // next ticket, in flight while this one is processed
+    force_warp<VARIANT, MODE>(w, lane, FORCE_PASS, fc);
+  }
+}
+
+// Hardware SM ids (%smid) need not be dense: record which ids exist on this device and rank them.
+__global__ void k_probe_smid(int *seen) {
+  unsigned smid;
+  asm("mov.u32 %0, %%smid;" : "=r"(smid));
+  if (threadIdx.x == 0) seen[smid & 1023] = 1;
+  // stay resident for a moment so that the blocks of this probe spread over every SM
+  const long long t0 = clock64();
+  while (clock64() - t0 < 20000) {}
+}
+
+static int force_queue_init(Unit *u) {
+  int nsm = 0;
+  MDB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, u->device));
+  MDB_TRY(u->force_queue.ensure(2 * 1024));
+  MDB_TRY(u->sm_rank.ensure(1024));
+  MDB_CUDA(cudaMemsetAsync(u->force_queue.ptr, 0, sizeof(int) * 2 * 1024, u->stream));
+  MDB_CUDA(cudaMemsetAsync(u->sm_rank.ptr, 0, sizeof(int) * 1024, u->stream));
+  k_probe_smid<<<nsm * 16, 128, 0, u->stream>>>(u->sm_rank.ptr);
+  int seen[1024];
+  MDB_CUDA(cudaMemcpyAsync(seen, u->sm_rank.ptr, sizeof(seen), cudaMemcpyDeviceToHost, u->stream));
+  MDB_CUDA(cudaStreamSynchronize(u->stream));
+  int rank[1024], n = 0;
+  for (int i = 0; i < 1024; i++) rank[i] = seen[i] ? n++ : 0;
+  if (n == 0) { set_error("SM probe saw no SM"); return MDB200_ECUDA; }
+  for (int i = 0, k = 0; i < 1024; i++)
+    if (!seen[i]) rank[i] = (k++) % n;
+  MDB_CUDA(cudaMemcpyAsync(u->sm_rank.ptr, rank, sizeof(rank), cudaMemcpyHostToDevice, u->stream));
+  MDB_CUDA(cudaStreamSynchronize(u->stream));
+  u->nsm = n;
+  u->force_queue_parity = 0;
+  return MDB200_OK;
+}
+
 static int force_variant() {
   static int v = -1;
   if (v < 0) {
@@ -217,17 +303,32 @@ static ForceConsts make_fc(const Unit *u) {
 }
 
 #define FORCE_ARGS(F, QOUT) u->q.ptr, u->p.ptr, F, u->list.ptr, u->warp_off.ptr, u->warp_len.ptr, u->ref_of_slot.ptr, \
-                            (int)u->pn, u->nwarps, QOUT, u->ctrl, fc
+                            (int)u->pn, u->nwarps, QOUT, u->ctrl
 
 static int force_launch(Unit *u, int mode, double *fout) {
   const int tpb = FORCE_TPB;
-  const unsigned grid = (unsigned)((u->nwarps * 32 + tpb - 1) / tpb);
+  const long long want = (u->nwarps * 32 + tpb - 1) / tpb;
   ForceConsts fc = make_fc(u);
-#define LAUNCH(V)                                                                                          \
-  do {                                                                                                     \
-    if (mode == FORCE_IMPULSE) k_force<V, FORCE_IMPULSE><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(fout, nullptr)); \
-    else if (mode == FORCE_KICK) k_force<V, FORCE_KICK><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(nullptr, nullptr)); \
-    else k_force<V, FORCE_KICK_DRIFT><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(nullptr, u->q_alt.ptr));     \
+#if FORCE_PERSIST
+  if (!u->force_queue.ptr) MDB_TRY(force_queue_init(u));
+  const int nsm = u->nsm;
+  int *qcur = u->force_queue.ptr + 1024 * u->force_queue_parity;
+  int *qnext = u->force_queue.ptr + 1024 * (1 - u->force_queue_parity);
+  u->force_queue_parity ^= 1;
+  const long long resident = (long long)nsm * FORCE_MINBLK;
+  const unsigned grid = (unsigned)(want < resident ? want : resident);
+#define KLAUNCH(V, M, F, QOUT) \
+  k_force_persist<V, M><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(F, QOUT), nsm, u->sm_rank.ptr, qcur, qnext, fc)
+#else
+  (void)force_queue_init;
+  const unsigned grid = (unsigned)want;
+#define KLAUNCH(V, M, F, QOUT) k_force<V, M><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(F, QOUT), fc)
+#endif
+#define LAUNCH(V)                                                                  \
+  do {                                                                             \
+    if (mode == FORCE_IMPULSE) KLAUNCH(V, FORCE_IMPULSE, fout, nullptr);           \
+    else if (mode == FORCE_KICK) KLAUNCH(V, FORCE_KICK, nullptr, nullptr);         \
+    else KLAUNCH(V, FORCE_KICK_DRIFT, nullptr, u->q_alt.ptr);                      \
   } while (0)
   switch (force_variant()) {
     case 0: LAUNCH(0); break;
@@ -235,6 +336,7 @@ static int force_launch(Unit *u, int mode, double *fout) {
     default: LAUNCH(1); break;
   }
 #undef LAUNCH
+#undef KLAUNCH
   u->launches++;
   MDB_CUDA(cudaGetLastError());
   return MDB200_OK;

@@ -150,6 +150,10 @@ struct Unit {
   DevBuf<int> warp_len;           // steps per force-warp (even)
   DevBuf<long long> warp_off;     // first list word of the force-warp (multiple of 64)
   DevBuf<unsigned> list;
+  DevBuf<int> force_queue;        // per-SM work tickets of the persistent force kernel (2 x 1024, ping-pong)
+  int force_queue_parity = 0;
+  DevBuf<int> sm_rank;            // dense rank of each hardware SM id
+  int nsm = 0;                    // SMs seen on the device
   long long list_entries = 0;     // padded entries
   long long npairs = 0;           // reference-style count of listed pairs (meshlist.cc:309)
   int max_row = 0;
