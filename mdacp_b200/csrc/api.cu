@@ -373,14 +373,31 @@ static int calculate(Unit **us, int n) {
     PhaseTimer t(us[i], PH_INTEG);
     MDB_TRY(drift_half(us[i]));
   }
-  {
+  const bool ct = us[0]->prm.control_temperature != 0;
+  // one unit per process, neighbours behind NCCL, plain NVE: run the ghost exchange on a second stream and
+  // let the interior force-warps (no ghost in their rows) start without waiting for it
+  const bool split_test = getenv("MDB200_FORCE_SPLIT") != nullptr;
+  const bool overlap = !ct && n == 1 && comm_multi_process() && us[0]->profiling < 2 && us[0]->nwarps > 0 &&
+                       !getenv("MDB200_NO_OVERLAP");
+  if (overlap) {
+    Unit *u = us[0];
+    DeviceGuard g(u->device);
+    if (!u->cstream) {
+      MDB_CUDA(cudaStreamCreateWithFlags(&u->cstream, cudaStreamNonBlocking));
+      MDB_CUDA(cudaEventCreateWithFlags(&u->ev_drift, cudaEventDisableTiming));
+      MDB_CUDA(cudaEventCreateWithFlags(&u->ev_ghost, cudaEventDisableTiming));
+    }
+    MDB_CUDA(cudaEventRecord(u->ev_drift, u->stream));
+    MDB_CUDA(cudaStreamWaitEvent(u->cstream, u->ev_drift, 0));
+    for (int dir = 0; dir < 6; dir++) MDB_TRY(comm_border_refresh(us, n, dir, true));
+    MDB_CUDA(cudaEventRecord(u->ev_ghost, u->cstream));
+  } else {
     std::vector<PhaseTimer *> tm;
     for (int i = 0; i < n; i++) tm.push_back(new PhaseTimer(us[i], PH_COMM));
     int r = send_border_particles(us, n);
     for (auto *x : tm) delete x;
     MDB_TRY(r);
   }
-  const bool ct = us[0]->prm.control_temperature != 0;
   if (ct && us[0]->prm.heatbath_type == MDB200_HT_NOSEHOOVER) {
     // MDManager::CalculateNoseHoover (mdmanager.cc:160-175)
     double t = 0.0;
@@ -409,6 +426,16 @@ static int calculate(Unit **us, int n) {
       { PhaseTimer t(us[i], PH_FORCE); MDB_TRY(force_kick(us[i])); }
       MDB_TRY(langevin_kick(us[i]));
     }
+  } else if (overlap) {
+    // MDManager::CalculateForce (mdmanager.cc:151-157) with the ghost exchange (queued above on the second
+    // stream) overlapped by the interior part of the force kernel
+    Unit *u = us[0];
+    DeviceGuard g(u->device);
+    force_timer_begin(u);
+    MDB_TRY(force_kick_drift_interior(u));
+    MDB_CUDA(cudaStreamWaitEvent(u->stream, u->ev_ghost, 0));
+    MDB_TRY(force_kick_drift_boundary(u));
+    force_timer_end(u);
   } else {
     // MDManager::CalculateForce (mdmanager.cc:151-157)
     for (int i = 0; i < n; i++) {
@@ -417,7 +444,12 @@ static int calculate(Unit **us, int n) {
         // kick and second half drift in one kernel (force.cu, FORCE_KICK_DRIFT)
         PhaseTimer t(us[i], PH_FORCE);
         force_timer_begin(us[i]);
-        MDB_TRY(force_kick_drift(us[i]));
+        if (split_test) {  // test hook: the interior / boundary launches of the overlapped path, back to back
+          MDB_TRY(force_kick_drift_interior(us[i]));
+          MDB_TRY(force_kick_drift_boundary(us[i]));
+        } else {
+          MDB_TRY(force_kick_drift(us[i]));
+        }
         force_timer_end(us[i]);
       }
     }
@@ -516,7 +548,9 @@ int mdb200_destroy(mdb200_unit *h) {
   for (int d = 0; d < 6; d++) u->border[d].release();
   u->send_buf.release(); u->mig_send_q.release(); u->mig_send_p.release(); u->mig_recv_q.release();
   u->mig_recv_p.release(); u->mig_send_t.release(); u->mig_recv_t.release();
-  u->row_count.release(); u->row_cls.release(); u->force_queue.release(); u->sm_rank.release(); u->warp_len.release(); u->warp_off.release(); u->list.release();
+  u->row_count.release(); u->row_cls.release(); u->force_queue.release(); u->sm_rank.release(); u->warp_flag.release(); u->warp_order.release();
+  if (u->cstream) { cudaStreamDestroy(u->cstream); cudaEventDestroy(u->ev_drift); cudaEventDestroy(u->ev_ghost); }
+  u->warp_len.release(); u->warp_off.release(); u->list.release();
   u->disp.release(); u->cand.release(); u->partial.release();
   if (u->ctrl) cudaFree(u->ctrl);
   if (u->ctrl_host) cudaFreeHost(u->ctrl_host);

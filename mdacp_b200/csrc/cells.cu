@@ -480,15 +480,15 @@ __global__ void __launch_bounds__(128)
 k_pair_search(const double4 *__restrict__ q, const int *__restrict__ cell_start,
               const int *__restrict__ gcell_start, const int *__restrict__ gcell_items,
               const int *__restrict__ ref_of_slot, int *__restrict__ row_count, unsigned *__restrict__ row_cls,
-              const long long *__restrict__ warp_off, int *warp_len, unsigned *__restrict__ list, int pn,
-              int sentinel, Consts c, Ctrl *ctrl) {
+              const long long *__restrict__ warp_off, int *warp_len, unsigned *__restrict__ list,
+              int *__restrict__ warp_flag, int pn, int sentinel, Consts c, Ctrl *ctrl) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;  // local slot
   const int lane = threadIdx.x & 31;
   const int fw = a / kPW;                               // force-warp of this slot
   const int flane0 = (a % kPW) * kG;                    // first lane of its group
   const bool act = a < pn;
   const bool in_tail = (long long)fw * kPW < pn;        // slot belongs to an existing force-warp
-  int n = 0;
+  int n = 0, n_local_entries = 0;
   unsigned long long nref = 0;
   long long base = 0;
   int wl = 0;
@@ -530,6 +530,7 @@ k_pair_search(const double4 *__restrict__ q, const int *__restrict__ cell_start,
         }
       }
     }
+    n_local_entries = n;
     // ghosts after all locals, so that a row is ascending in slot
     for (int dz = -1; dz <= 1; dz++) {
       const int z = cz + dz;
@@ -563,6 +564,11 @@ k_pair_search(const double4 *__restrict__ q, const int *__restrict__ cell_start,
   if (FILL) {
     if (in_tail)
       for (int e = n; e < wl * kG; e++) list[base + list_word(e / kG, flane0 + e % kG)] = (unsigned)sentinel;
+    // boundary warp = one of its rows holds a ghost
+    int hg = (n > n_local_entries) ? 1 : 0;
+#pragma unroll
+    for (int o = kPW / 2; o > 0; o >>= 1) hg |= __shfl_xor_sync(0xffffffffu, hg, o);
+    if (in_tail && (a % kPW) == 0) warp_flag[fw] = hg;
   } else {
     // steps of this local, maximum over the kPW locals of its force-warp, rounded up to even
     int mx = (n + kG - 1) / kG;
@@ -582,6 +588,15 @@ k_pair_search(const double4 *__restrict__ q, const int *__restrict__ cell_start,
   }
 }
 
+__global__ void k_warp_order(const int *__restrict__ flag, const int *__restrict__ scanv, int *__restrict__ order,
+                             int nw, int n_interior) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nw) return;
+  const int nb = scanv[w];  // boundary warps before w
+  if (flag[w]) order[n_interior + nb] = w;
+  else order[w - nb] = w;
+}
+
 int build_pair_list(Unit *u) {
   const long long pn = u->pn;
   MDB_CUDA(cudaMemsetAsync(&u->ctrl->npairs, 0, sizeof(unsigned long long), u->stream));
@@ -596,12 +611,16 @@ int build_pair_list(Unit *u) {
   MDB_TRY(u->row_cls.ensure((size_t)pn + 32));
   MDB_TRY(u->warp_len.ensure((size_t)nw + 2));
   MDB_TRY(u->warp_off.ensure((size_t)nw + 2));
+  MDB_TRY(u->warp_flag.ensure((size_t)nw + 2));
+  MDB_TRY(u->warp_order.ensure((size_t)nw + 2));
+  MDB_TRY(u->scan.ensure((size_t)nw + 2));
+  MDB_TRY(u->scan_ws.ensure(2 * scan_workspace_ints(nw + 2)));
   MDB_TRY(u->scan_ws64.ensure(scan_workspace_ints(nw + 2)));
   const int tpb = 128;
   const long long nthr = nw * kPW;  // threads past pn only pad the tail warp
   k_pair_search<false><<<nblk(nthr, tpb), tpb, 0, u->stream>>>(
       u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr, u->gcell_items.ptr, u->ref_of_slot.ptr, u->row_count.ptr, u->row_cls.ptr,
-      u->warp_off.ptr, u->warp_len.ptr, u->list.ptr, (int)pn, sentinel_index(u), u->c, u->ctrl);
+      u->warp_off.ptr, u->warp_len.ptr, u->list.ptr, u->warp_flag.ptr, (int)pn, sentinel_index(u), u->c, u->ctrl);
   u->launches++;
   MDB_TRY(exclusive_scan_i32_to_i64(u->warp_len.ptr, u->warp_off.ptr, nw, u->scan_ws64.ptr, u->stream, &u->launches, 32));
   MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->scratch[4], u->warp_off.ptr + nw, sizeof(long long), cudaMemcpyDeviceToHost,
@@ -623,7 +642,15 @@ int build_pair_list(Unit *u) {
   if ((size_t)entries + 64 > u->list.cap) MDB_TRY(u->list.ensure((size_t)entries + (size_t)entries * 2 / 5 + 64));
   k_pair_search<true><<<nblk(nthr, tpb), tpb, 0, u->stream>>>(
       u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr, u->gcell_items.ptr, u->ref_of_slot.ptr, u->row_count.ptr, u->row_cls.ptr,
-      u->warp_off.ptr, u->warp_len.ptr, u->list.ptr, (int)pn, sentinel_index(u), u->c, u->ctrl);
+      u->warp_off.ptr, u->warp_len.ptr, u->list.ptr, u->warp_flag.ptr, (int)pn, sentinel_index(u), u->c, u->ctrl);
+  u->launches++;
+  // interior warps first, boundary warps last (stable within each class)
+  MDB_TRY(exclusive_scan_i32(u->warp_flag.ptr, u->scan.ptr, nw, u->scan_ws.ptr, u->stream, &u->launches));
+  MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->scratch[5], u->scan.ptr + nw, sizeof(int), cudaMemcpyDeviceToHost, u->stream));
+  MDB_CUDA(cudaStreamSynchronize(u->stream));
+  u->n_interior = nw - u->ctrl_host->scratch[5];
+  k_warp_order<<<nblk(nw), TPB, 0, u->stream>>>(u->warp_flag.ptr, u->scan.ptr, u->warp_order.ptr, (int)nw,
+                                                (int)u->n_interior);
   u->launches++;
   MDB_CUDA(cudaGetLastError());
   return MDB200_OK;

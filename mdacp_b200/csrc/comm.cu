@@ -220,28 +220,34 @@ int comm_border_setup(Unit **us, int n, int dir) {
   return MDB200_OK;
 }
 
-int comm_border_refresh(Unit **us, int n, int dir) {
+bool comm_multi_process() { return g_comm.nranks > 1 && g_comm.comm != nullptr; }
+
+// on_comm_stream: issue everything on the unit's second stream (u->cstream) so that the exchange overlaps
+// the interior force kernel running on u->stream (api.cu:calculate)
+int comm_border_refresh(Unit **us, int n, int dir, bool on_comm_stream) {
   for (int i = 0; i < n; i++) {
     Unit *u = us[i];  // u as SENDER
     cudaSetDevice(u->device);
+    cudaStream_t st = (on_comm_stream && u->cstream) ? u->cstream : u->stream;
     if (!is_remote(u, dir)) {
       Unit *d = u->nbr[dir];
-      MDB_TRY(ghost_put_to(u, dir, d->q.ptr + d->recv_off[dir], d->q_alt.ptr + d->recv_off[dir], u->stream));
+      MDB_TRY(ghost_put_to(u, dir, d->q.ptr + d->recv_off[dir], d->q_alt.ptr + d->recv_off[dir], st));
       continue;
     }
-    MDB_TRY(ghost_pack(u, dir));
+    MDB_TRY(u->send_buf.ensure((size_t)u->n_border[dir] + 1));
+    MDB_TRY(ghost_put_to(u, dir, u->send_buf.ptr, nullptr, st));
     const int to = u->prm.neighbor_rank[dir], from = u->prm.neighbor_rank[OPP[dir]];
     MDB_NCCL(g_nccl.GroupStart());
     if (u->n_border[dir] > 0)
-      MDB_NCCL(g_nccl.Send(u->send_buf.ptr, (size_t)u->n_border[dir] * 4, ncclDouble, to, g_comm.comm, u->stream));
+      MDB_NCCL(g_nccl.Send(u->send_buf.ptr, (size_t)u->n_border[dir] * 4, ncclDouble, to, g_comm.comm, st));
     if (u->recv_cnt[dir] > 0)
       MDB_NCCL(g_nccl.Recv(u->q.ptr + u->recv_off[dir], (size_t)u->recv_cnt[dir] * 4, ncclDouble, from, g_comm.comm,
-                           u->stream));
+                           st));
     MDB_NCCL(g_nccl.GroupEnd());
     // positions are double-buffered: the ghost window lives in both buffers
     if (u->recv_cnt[dir] > 0)
       MDB_CUDA(cudaMemcpyAsync(u->q_alt.ptr + u->recv_off[dir], u->q.ptr + u->recv_off[dir],
-                               sizeof(double4) * (size_t)u->recv_cnt[dir], cudaMemcpyDeviceToDevice, u->stream));
+                               sizeof(double4) * (size_t)u->recv_cnt[dir], cudaMemcpyDeviceToDevice, st));
   }
   return MDB200_OK;
 }

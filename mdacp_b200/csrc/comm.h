@@ -14,7 +14,8 @@ int comm_migrate(Unit **us, int n, int dir, const long long *n_leave);
 // rebuild-time ghost exchange in direction dir: sizes the receive windows, first transfer
 int comm_border_setup(Unit **us, int n, int dir);
 // per-step ghost refresh in direction dir (fixed windows)
-int comm_border_refresh(Unit **us, int n, int dir);
+int comm_border_refresh(Unit **us, int n, int dir, bool on_comm_stream = false);
+bool comm_multi_process();
 int comm_allreduce_or(Unit **us, int n, int *flag);
 int comm_allreduce_sum(Unit **us, int n, double *v, int cnt);
 

@@ -198,10 +198,14 @@ __device__ __forceinline__ void force_warp(long long w, int lane, FORCE_PARAMS, 
 }
 
 // Plain grid: one force-warp per warp.
+// worder (may be null): the launch covers force-warps worder[wbase .. wbase + wcount) -- the interior or
+// the boundary part of the unit (cells.cu:k_warp_order); null = force-warps [0, wcount).
 template <int VARIANT, int MODE>
-__global__ void __launch_bounds__(FORCE_TPB, FORCE_MINBLK) k_force(FORCE_PARAMS, ForceConsts fc) {
-  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= nwarps) return;
+__global__ void __launch_bounds__(FORCE_TPB, FORCE_MINBLK)
+k_force(FORCE_PARAMS, const int *__restrict__ worder, long long wbase, long long wcount, ForceConsts fc) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= wcount) return;
+  const long long w = worder ? (long long)worder[wbase + i] : i;
   force_warp<VARIANT, MODE>(w, threadIdx.x & 31, FORCE_PASS, fc);
 }
 
@@ -305,11 +309,17 @@ static ForceConsts make_fc(const Unit *u) {
 #define FORCE_ARGS(F, QOUT) u->q.ptr, u->p.ptr, F, u->list.ptr, u->warp_off.ptr, u->warp_len.ptr, u->ref_of_slot.ptr, \
                             (int)u->pn, u->nwarps, QOUT, u->ctrl
 
-static int force_launch(Unit *u, int mode, double *fout) {
+// part: 0 = every force-warp, 1 = interior warps only, 2 = boundary warps only
+static int force_launch(Unit *u, int mode, double *fout, int part = 0) {
   const int tpb = FORCE_TPB;
-  const long long want = (u->nwarps * 32 + tpb - 1) / tpb;
+  const int *worder = part ? u->warp_order.ptr : nullptr;
+  const long long wbase = (part == 2) ? u->n_interior : 0;
+  const long long wcount = (part == 0) ? u->nwarps : (part == 1 ? u->n_interior : u->nwarps - u->n_interior);
+  if (wcount <= 0) return MDB200_OK;
+  const long long want = (wcount * 32 + tpb - 1) / tpb;
   ForceConsts fc = make_fc(u);
 #if FORCE_PERSIST
+  if (part != 0) { set_error("FORCE_PERSIST build has no split launch"); return MDB200_EINVAL; }
   if (!u->force_queue.ptr) MDB_TRY(force_queue_init(u));
   const int nsm = u->nsm;
   int *qcur = u->force_queue.ptr + 1024 * u->force_queue_parity;
@@ -322,7 +332,7 @@ static int force_launch(Unit *u, int mode, double *fout) {
 #else
   (void)force_queue_init;
   const unsigned grid = (unsigned)want;
-#define KLAUNCH(V, M, F, QOUT) k_force<V, M><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(F, QOUT), fc)
+#define KLAUNCH(V, M, F, QOUT) k_force<V, M><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(F, QOUT), worder, wbase, wcount, fc)
 #endif
 #define LAUNCH(V)                                                                  \
   do {                                                                             \
@@ -354,6 +364,20 @@ int force_kick_drift(Unit *u) {
   if (u->pn == 0 || u->nwarps == 0) return MDB200_OK;
   MDB_TRY(force_launch(u, FORCE_KICK_DRIFT, nullptr));
   std::swap(u->q, u->q_alt);  // ghosts live in both buffers (exchange.cu)
+  u->vmax_ready = true;
+  return MDB200_OK;
+}
+
+// The same in two launches: interior warps (no ghost in any row) can run before the ghost exchange has
+// finished, boundary warps after it (api.cu:calculate, multi-process runs).
+int force_kick_drift_interior(Unit *u) {
+  if (u->pn == 0 || u->nwarps == 0) return MDB200_OK;
+  return force_launch(u, FORCE_KICK_DRIFT, nullptr, 1);
+}
+int force_kick_drift_boundary(Unit *u) {
+  if (u->pn == 0 || u->nwarps == 0) return MDB200_OK;
+  MDB_TRY(force_launch(u, FORCE_KICK_DRIFT, nullptr, 2));
+  std::swap(u->q, u->q_alt);
   u->vmax_ready = true;
   return MDB200_OK;
 }

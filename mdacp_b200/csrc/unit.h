@@ -150,6 +150,10 @@ struct Unit {
   DevBuf<int> warp_len;           // steps per force-warp (even)
   DevBuf<long long> warp_off;     // first list word of the force-warp (multiple of 64)
   DevBuf<unsigned> list;
+  // interior / boundary split of the force-warps (boundary = some row of the warp holds a ghost): lets the
+  // interior force run while the ghost exchange is still in flight (api.cu, multi-process runs)
+  DevBuf<int> warp_flag, warp_order;   // order: interior warps first, then boundary warps
+  long long n_interior = 0;
   DevBuf<int> force_queue;        // per-SM work tickets of the persistent force kernel (2 x 1024, ping-pong)
   int force_queue_parity = 0;
   DevBuf<int> sm_rank;            // dense rank of each hardware SM id
@@ -172,6 +176,8 @@ struct Unit {
   Unit *nbr[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // destination when sending in dir
   Unit *src[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // source when receiving in dir (neighbour in opposite dir)
   bool comm_ready = false;
+  cudaStream_t cstream = 0;       // second stream for the overlapped ghost exchange (created on demand)
+  cudaEvent_t ev_drift = 0, ev_ghost = 0;
 
   // profiling
   int profiling = 0;               // 0 off, 1 force kernel only (no extra syncs), 2 every phase
@@ -230,7 +236,9 @@ int expiry_check_local(Unit *u, int *expired);                           // sync
 
 // force.cu
 int force_kick(Unit *u);
-int force_kick_drift(Unit *u);                                           // kick + second half drift, swaps q / q_alt
+int force_kick_drift(Unit *u);
+int force_kick_drift_interior(Unit *u);                                  // first half of the split launch
+int force_kick_drift_boundary(Unit *u);                                  // second half + buffer swap                                           // kick + second half drift, swaps q / q_alt
 int force_impulse(Unit *u, double *f3_host, long long cap_rows);         // sync
 
 // observe.cu
