@@ -58,7 +58,7 @@ def measured_peaks():
 # clocks sampler (nvidia-smi during the timed region)
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Samples SM clock, power and throttle reasons through NVML (nvidia-ml-py) every 10 ms from a
+    """Samples SM clock, power and throttle reasons through NVML (nvidia-ml-py) every 50 ms from a
     thread while the timed region runs -- the recipe's nvidia-smi clocks line, without the
     process start-up latency that would miss a sub-second region."""
 
@@ -81,7 +81,7 @@ class ClockSampler:
                 self.samples.append((sm, rs, pw))
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.05)
 
     def start(self):
         try:
@@ -412,7 +412,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=150)  # ThermalizeLoop of benchmark.cfg (benchmark.cc:25-27)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--unit-length", type=float, default=float(os.environ.get("MDB200_BENCH_UNIT_LENGTH", "284")))
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -94,6 +94,12 @@ __global__ void k_mig_unpack(double4 *__restrict__ q, double4 *__restrict__ p, i
 int rebuild_begin_order(Unit *u) {
   MDB_TRY(u->ord.ensure((size_t)u->cap_p + 1));
   MDB_TRY(u->ord_alt.ensure((size_t)u->cap_p + 1));
+  // migration buffers sized once, well above the few per mille of pn that move per rebuild
+  {
+    const size_t m = (size_t)(u->pn / 64) + 4096;
+    MDB_TRY(u->mig_send_q.ensure(m)); MDB_TRY(u->mig_send_p.ensure(m)); MDB_TRY(u->mig_send_t.ensure(m));
+    MDB_TRY(u->mig_recv_q.ensure(m)); MDB_TRY(u->mig_recv_p.ensure(m)); MDB_TRY(u->mig_recv_t.ensure(m));
+  }
   if (u->pn > 0) {
     k_begin_order<<<nblk(u->pn), TPB, 0, u->stream>>>(u->slot_of_ref.ptr, u->ord.ptr, (int)u->pn);
     u->launches++;

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 #include "../../include/mdacp_b200.h"
@@ -41,8 +42,12 @@ struct DevBuf {
   size_t cap = 0;
   int ensure(size_t n, bool keep = false, cudaStream_t st = 0) {
     if (n <= cap) return MDB200_OK;
-    size_t ncap = n + n / 8 + 64;
+    // generous head-room: re-allocation (cudaMalloc + cudaFree, both device-synchronising) inside the step
+    // loop costs far more than the memory
+    size_t ncap = n + n / 4 + 64;
     T *np = nullptr;
+    if (cap && getenv("MDB200_DEBUG"))
+      fprintf(stderr, "[mdb200] realloc %zu -> %zu elements of %zu bytes\n", cap, ncap, sizeof(T));
     MDB_CUDA(cudaMalloc(&np, ncap * sizeof(T)));
     if (keep && ptr && cap) {
       MDB_CUDA(cudaMemcpyAsync(np, ptr, cap * sizeof(T), cudaMemcpyDeviceToDevice, st));
