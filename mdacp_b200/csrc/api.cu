@@ -377,13 +377,20 @@ static int calculate(Unit **us, int n) {
   // one unit per process, neighbours behind NCCL, plain NVE: run the ghost exchange on a second stream and
   // let the interior force-warps (no ghost in their rows) start without waiting for it
   const bool split_test = getenv("MDB200_FORCE_SPLIT") != nullptr;
-  const bool overlap = !ct && n == 1 && comm_multi_process() && us[0]->profiling < 2 && us[0]->nwarps > 0 &&
-                       !getenv("MDB200_NO_OVERLAP");
+  // Measured (profiles/): the split launch costs ~0.15 ms; the exchange it hides costs ~0.15 ms with 2 remote
+  // directions (2x1x1 units: no gain) and ~0.5 ms with 6 (2x2x2: 4.61 -> 4.34 ms/step), so overlap from 4 up.
+  const char *ov_env = getenv("MDB200_OVERLAP");  // 0 / 1 forces it off / on
+  const bool ov_want = ov_env ? (ov_env[0] == '1') : (n == 1 && comm_remote_directions(us[0]) >= 4);
+  const bool overlap = !ct && n == 1 && comm_multi_process() && us[0]->profiling < 2 && us[0]->nwarps > 0 && ov_want;
   if (overlap) {
     Unit *u = us[0];
     DeviceGuard g(u->device);
     if (!u->cstream) {
-      MDB_CUDA(cudaStreamCreateWithFlags(&u->cstream, cudaStreamNonBlocking));
+      // highest priority: the exchange kernels are tiny, but at equal priority their blocks would queue behind
+      // the ~500k blocks of the interior force launch and the "overlap" would serialise
+      int prio_lo = 0, prio_hi = 0;
+      MDB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      MDB_CUDA(cudaStreamCreateWithPriority(&u->cstream, cudaStreamNonBlocking, prio_hi));
       MDB_CUDA(cudaEventCreateWithFlags(&u->ev_drift, cudaEventDisableTiming));
       MDB_CUDA(cudaEventCreateWithFlags(&u->ev_ghost, cudaEventDisableTiming));
     }

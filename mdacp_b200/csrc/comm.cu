@@ -221,6 +221,11 @@ int comm_border_setup(Unit **us, int n, int dir) {
 }
 
 bool comm_multi_process() { return g_comm.nranks > 1 && g_comm.comm != nullptr; }
+int comm_remote_directions(const Unit *u) {
+  int k = 0;
+  for (int dir = 0; dir < 6; dir++) k += is_remote(u, dir) ? 1 : 0;
+  return k;
+}
 
 // on_comm_stream: issue everything on the unit's second stream (u->cstream) so that the exchange overlaps
 // the interior force kernel running on u->stream (api.cu:calculate)

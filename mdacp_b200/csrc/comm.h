@@ -16,6 +16,7 @@ int comm_border_setup(Unit **us, int n, int dir);
 // per-step ghost refresh in direction dir (fixed windows)
 int comm_border_refresh(Unit **us, int n, int dir, bool on_comm_stream = false);
 bool comm_multi_process();
+int comm_remote_directions(const Unit *u);  // how many of the 6 neighbours live in another process
 int comm_allreduce_or(Unit **us, int n, int *flag);
 int comm_allreduce_sum(Unit **us, int n, double *v, int cnt);
 
