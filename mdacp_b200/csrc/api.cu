@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <map>
 #include <set>
+#include <utility>
 #include <vector>
 #include "comm.h"
 #include "unit.h"
@@ -137,6 +138,16 @@ static int stage_barrier(Unit **us, int n) {
         MDB_CUDA(cudaStreamWaitEvent(streams[k], evs[j], 0));
       }
   for (size_t k = 0; k < streams.size(); k++) cudaEventDestroy(evs[k]);
+  return MDB200_OK;
+}
+
+// Undo the speculative pre-drift (unit.h, force.cu MODE 3): afterwards q holds the end-of-step positions.
+static int materialize(Unit *u) {
+  if (!u->predrifted) return MDB200_OK;
+  DeviceGuard g(u->device);
+  MDB_TRY(drift_half_buffer(u, u->q_alt.ptr));  // last half-step positions + p dt/2, bit-identical to the plain path
+  std::swap(u->q, u->q_alt);
+  u->predrifted = false;
   return MDB200_OK;
 }
 
@@ -367,13 +378,18 @@ static int kinetic_temperature(Unit **us, int n, double *T) {
 static int calculate(Unit **us, int n) {
   int expired = 0;
   MDB_TRY(any_expired(us, n, &expired));
+  const bool ct = us[0]->prm.control_temperature != 0;
+  if (expired || ct)
+    for (int i = 0; i < n; i++) MDB_TRY(materialize(us[i]));
   if (expired) MDB_TRY(make_pairlist(us, n));
   for (int i = 0; i < n; i++) {
     DeviceGuard g(us[i]->device);
     PhaseTimer t(us[i], PH_INTEG);
-    MDB_TRY(drift_half(us[i]));
+    if (us[i]->predrifted) us[i]->predrifted = false;  // the previous force kernel already did this half drift
+    else MDB_TRY(drift_half(us[i]));
   }
-  const bool ct = us[0]->prm.control_temperature != 0;
+  // plain NVE: let the force kernel also do the first half drift of the next step (undone on demand)
+  const bool predrift = !ct && !getenv("MDB200_NO_PREDRIFT");
   // one unit per process, neighbours behind NCCL, plain NVE: run the ghost exchange on a second stream and
   // let the interior force-warps (no ghost in their rows) start without waiting for it
   const bool split_test = getenv("MDB200_FORCE_SPLIT") != nullptr;
@@ -439,10 +455,11 @@ static int calculate(Unit **us, int n) {
     Unit *u = us[0];
     DeviceGuard g(u->device);
     force_timer_begin(u);
-    MDB_TRY(force_kick_drift_interior(u));
+    MDB_TRY(force_kick_drift(u, predrift, 1));
     MDB_CUDA(cudaStreamWaitEvent(u->stream, u->ev_ghost, 0));
-    MDB_TRY(force_kick_drift_boundary(u));
+    MDB_TRY(force_kick_drift(u, predrift, 2));
     force_timer_end(u);
+    u->predrifted = predrift;
   } else {
     // MDManager::CalculateForce (mdmanager.cc:151-157)
     for (int i = 0; i < n; i++) {
@@ -452,12 +469,13 @@ static int calculate(Unit **us, int n) {
         PhaseTimer t(us[i], PH_FORCE);
         force_timer_begin(us[i]);
         if (split_test) {  // test hook: the interior / boundary launches of the overlapped path, back to back
-          MDB_TRY(force_kick_drift_interior(us[i]));
-          MDB_TRY(force_kick_drift_boundary(us[i]));
+          MDB_TRY(force_kick_drift(us[i], predrift, 1));
+          MDB_TRY(force_kick_drift(us[i], predrift, 2));
         } else {
-          MDB_TRY(force_kick_drift(us[i]));
+          MDB_TRY(force_kick_drift(us[i], predrift, 0));
         }
         force_timer_end(us[i]);
+        us[i]->predrifted = predrift;
       }
     }
   }
@@ -606,6 +624,7 @@ int mdb200_upload(mdb200_unit *h, const double (*q)[4], const double (*p)[4], co
   u->scratch_tail = pn;
   u->list_initialized = false;
   u->vmax_ready = false;
+  u->predrifted = false;
   u->npairs = 0;
   u->list_entries = 0;
   for (int d = 0; d < 6; d++) { u->n_border[d] = 0; u->recv_cnt[d] = 0; u->recv_off[d] = pn; }
@@ -619,6 +638,7 @@ int mdb200_download(mdb200_unit *h, double (*q)[4], double (*p)[4], int *type, l
   if (!h) return MDB200_EINVAL;
   Unit *u = &h->u;
   DeviceGuard g(u->device);
+  MDB_TRY(materialize(u));
   if (pn) *pn = u->pn;
   if (tn) *tn = u->tn;
   if (!q && !p && !type) return MDB200_OK;
@@ -689,6 +709,7 @@ static int unpack_units(mdb200_unit **units, int n, std::vector<Unit *> &us) {
 int mdb200_make_pairlist(mdb200_unit **units, int n) {
   std::vector<Unit *> us;
   MDB_TRY(unpack_units(units, n, us));
+  for (int i = 0; i < n; i++) MDB_TRY(materialize(us[i]));
   return make_pairlist(us.data(), n);
 }
 
@@ -708,12 +729,14 @@ int mdb200_is_pairlist_expired(mdb200_unit **units, int n, int *expired) {
 int mdb200_update_position_half(mdb200_unit *h) {
   if (!h) return MDB200_EINVAL;
   DeviceGuard g(h->u.device);
+  MDB_TRY(materialize(&h->u));
   return drift_half(&h->u);
 }
 
 int mdb200_send_border_particles(mdb200_unit **units, int n) {
   std::vector<Unit *> us;
   MDB_TRY(unpack_units(units, n, us));
+  for (int i = 0; i < n; i++) MDB_TRY(materialize(us[i]));
   return send_border_particles(us.data(), n);
 }
 
@@ -721,6 +744,7 @@ int mdb200_calculate_force(mdb200_unit *h) {
   if (!h) return MDB200_EINVAL;
   if (!h->u.list_initialized) { set_error("pair list not built"); return MDB200_EINVAL; }
   DeviceGuard g(h->u.device);
+  MDB_TRY(materialize(&h->u));
   return force_kick(&h->u);
 }
 
@@ -734,11 +758,13 @@ int mdb200_heatbath_zeta(mdb200_unit *h, double t) {
 int mdb200_heatbath_momenta(mdb200_unit *h) {
   if (!h) return MDB200_EINVAL;
   DeviceGuard g(h->u.device);
+  MDB_TRY(materialize(&h->u));
   return heatbath_momenta(&h->u);
 }
 int mdb200_langevin(mdb200_unit *h) {
   if (!h) return MDB200_EINVAL;
   DeviceGuard g(h->u.device);
+  MDB_TRY(materialize(&h->u));
   return langevin_kick(&h->u);
 }
 int mdb200_set_seed(mdb200_unit *h, int seed) {
@@ -770,6 +796,7 @@ int mdb200_set_aimed_temperature(mdb200_unit *h, double t) {
 int mdb200_observe_unit(mdb200_unit *h, double out[4]) {
   if (!h || !out) return MDB200_EINVAL;
   DeviceGuard g(h->u.device);
+  MDB_TRY(materialize(&h->u));
   return observe_unit(&h->u, out);
 }
 
@@ -780,6 +807,7 @@ int mdb200_observe(mdb200_unit **units, int n, double out[4]) {
   for (int i = 0; i < n; i++) {
     DeviceGuard g(us[i]->device);
     double o[4];
+    MDB_TRY(materialize(us[i]));
     MDB_TRY(observe_unit(us[i], o));
     for (int k = 0; k < 4; k++) tot[k] += o[k];
   }
@@ -798,6 +826,7 @@ int mdb200_get_impulse(mdb200_unit *h, double *f3, long long cap_rows) {
   if (!h || !f3) return MDB200_EINVAL;
   if (!h->u.list_initialized) { set_error("pair list not built"); return MDB200_EINVAL; }
   DeviceGuard g(h->u.device);
+  MDB_TRY(materialize(&h->u));
   return force_impulse(&h->u, f3, cap_rows);
 }
 

@@ -117,7 +117,12 @@ __device__ __forceinline__ void pair_accumulate(double ax, double ay, double az,
 //   the OTHER position buffer because q is still being gathered by other warps; the caller swaps the
 //   buffers.  It also leaves max |p_new|^2 in ctrl->vmax2_bits for the next step's velocity-budget test
 //   (pairlist.cc:48-65), so that test needs no pass of its own.
-enum { FORCE_IMPULSE = 0, FORCE_KICK = 1, FORCE_KICK_DRIFT = 2 };
+// MODE 3: as MODE 2 plus the FIRST half drift of the NEXT step (mdmanager.cc:128-131), speculatively:
+//   q_out[a] = (q[a] + p_new dt/2) + p_new dt/2, two separately rounded additions exactly like two
+//   k_drift_half passes.  The end-of-step positions q[a] + p_new dt/2 are not stored; whoever needs them
+//   (rebuild, observation, download, displacement test) recomputes them bit-identically from the untouched
+//   input buffer and p_new (api.cu:materialize, integrate.cu).
+enum { FORCE_IMPULSE = 0, FORCE_KICK = 1, FORCE_KICK_DRIFT = 2, FORCE_KICK_DRIFT2 = 3 };
 #define FORCE_PARAMS                                                                                              \
   const double4 *__restrict__ q, double4 *__restrict__ p, double *__restrict__ fout,                             \
       const unsigned *__restrict__ list, const long long *__restrict__ warp_off, const int *__restrict__ warp_len, \
@@ -178,14 +183,16 @@ __device__ __forceinline__ void force_warp(long long w, int lane, FORCE_PARAMS, 
     double4 pa = p[a];
     pa.x += fx; pa.y += fy; pa.z += fz;
     p[a] = pa;
-    if (MODE == FORCE_KICK_DRIFT) {
+    if (MODE == FORCE_KICK_DRIFT || MODE == FORCE_KICK_DRIFT2) {
       // fcalculator.cc:22-32, no FMA contraction: identical to k_drift_half
-      q_out[a] = make_double4(__dadd_rn(ax, __dmul_rn(pa.x, fc.dt2)), __dadd_rn(ay, __dmul_rn(pa.y, fc.dt2)),
-                              __dadd_rn(az, __dmul_rn(pa.z, fc.dt2)), 0.0);
+      const double sx = __dmul_rn(pa.x, fc.dt2), sy = __dmul_rn(pa.y, fc.dt2), sz = __dmul_rn(pa.z, fc.dt2);
+      double nx = __dadd_rn(ax, sx), ny = __dadd_rn(ay, sy), nz = __dadd_rn(az, sz);
+      if (MODE == FORCE_KICK_DRIFT2) { nx = __dadd_rn(nx, sx); ny = __dadd_rn(ny, sy); nz = __dadd_rn(nz, sz); }
+      q_out[a] = make_double4(nx, ny, nz, 0.0);
       v2 = __dadd_rn(__dadd_rn(__dmul_rn(pa.x, pa.x), __dmul_rn(pa.y, pa.y)), __dmul_rn(pa.z, pa.z));
     }
   }
-  if (MODE == FORCE_KICK_DRIFT) {
+  if (MODE == FORCE_KICK_DRIFT || MODE == FORCE_KICK_DRIFT2) {
 #pragma unroll
     for (int o = 16; o >= kG; o >>= 1) v2 = fmax(v2, __shfl_xor_sync(0xffffffffu, v2, o));
     if (lane == 0) {
@@ -338,7 +345,8 @@ static int force_launch(Unit *u, int mode, double *fout, int part = 0) {
   do {                                                                             \
     if (mode == FORCE_IMPULSE) KLAUNCH(V, FORCE_IMPULSE, fout, nullptr);           \
     else if (mode == FORCE_KICK) KLAUNCH(V, FORCE_KICK, nullptr, nullptr);         \
-    else KLAUNCH(V, FORCE_KICK_DRIFT, nullptr, u->q_alt.ptr);                      \
+    else if (mode == FORCE_KICK_DRIFT) KLAUNCH(V, FORCE_KICK_DRIFT, nullptr, u->q_alt.ptr); \
+    else KLAUNCH(V, FORCE_KICK_DRIFT2, nullptr, u->q_alt.ptr);                     \
   } while (0)
   switch (force_variant()) {
     case 0: LAUNCH(0); break;
@@ -359,26 +367,17 @@ int force_kick(Unit *u) {
   return force_launch(u, FORCE_KICK, nullptr);
 }
 
-// CalculateForce + UpdatePositionHalf of MDManager::CalculateForce (mdmanager.cc:151-157) in one kernel
-int force_kick_drift(Unit *u) {
+// CalculateForce + UpdatePositionHalf of MDManager::CalculateForce (mdmanager.cc:151-157) in one kernel;
+// predrift = also the first half drift of the next step (MODE 3; the caller sets u->predrifted).
+// part 0 = every force-warp; 1 = interior warps only (no ghost in any row: may run before the ghost
+// exchange has finished); 2 = boundary warps.  The buffers swap after part 0 or 2.
+int force_kick_drift(Unit *u, bool predrift, int part) {
   if (u->pn == 0 || u->nwarps == 0) return MDB200_OK;
-  MDB_TRY(force_launch(u, FORCE_KICK_DRIFT, nullptr));
-  std::swap(u->q, u->q_alt);  // ghosts live in both buffers (exchange.cu)
-  u->vmax_ready = true;
-  return MDB200_OK;
-}
-
-// The same in two launches: interior warps (no ghost in any row) can run before the ghost exchange has
-// finished, boundary warps after it (api.cu:calculate, multi-process runs).
-int force_kick_drift_interior(Unit *u) {
-  if (u->pn == 0 || u->nwarps == 0) return MDB200_OK;
-  return force_launch(u, FORCE_KICK_DRIFT, nullptr, 1);
-}
-int force_kick_drift_boundary(Unit *u) {
-  if (u->pn == 0 || u->nwarps == 0) return MDB200_OK;
-  MDB_TRY(force_launch(u, FORCE_KICK_DRIFT, nullptr, 2));
-  std::swap(u->q, u->q_alt);
-  u->vmax_ready = true;
+  MDB_TRY(force_launch(u, predrift ? FORCE_KICK_DRIFT2 : FORCE_KICK_DRIFT, nullptr, part));
+  if (part != 1) {
+    std::swap(u->q, u->q_alt);  // ghosts live in both buffers (exchange.cu)
+    u->vmax_ready = true;
+  }
   return MDB200_OK;
 }
 

@@ -49,13 +49,14 @@ __global__ void k_drift_half(double4 *__restrict__ q, const double4 *__restrict_
   q[i] = qq;
 }
 
-int drift_half(Unit *u) {
+int drift_half_buffer(Unit *u, double4 *qbuf) {
   if (u->pn == 0) return MDB200_OK;
-  k_drift_half<<<nblk(u->pn), TPB, 0, u->stream>>>(u->q.ptr, u->p.ptr, (int)u->pn, u->c.dt2);
+  k_drift_half<<<nblk(u->pn), TPB, 0, u->stream>>>(qbuf, u->p.ptr, (int)u->pn, u->c.dt2);
   u->launches++;
   MDB_CUDA(cudaGetLastError());
   return MDB200_OK;
 }
+int drift_half(Unit *u) { return drift_half_buffer(u, u->q.ptr); }
 
 // ---------------------------------------------------------------------------------------------
 // thermostats
@@ -206,14 +207,28 @@ __global__ void k_expiry_vmax(const double4 *__restrict__ p, int pn, Ctrl *ctrl,
 __global__ void k_expiry_budget(Ctrl *ctrl, double dt, double BL) { expiry_budget(ctrl, dt, BL); }
 
 // Stage 2: displacement since the snapshot over locals AND ghosts (pairlist.cc:69-83).
-__global__ void k_expiry_disp(const double4 *__restrict__ q, const double4 *__restrict__ q0,
+// End-of-step position of item i.  Normally q[i]; in the pre-drifted state (unit.h) the locals' end-of-step
+// positions are recomputed from the previous half-step buffer and p exactly as k_drift_half would have.
+__device__ __forceinline__ double4 current_position(const double4 *__restrict__ q, const double4 *__restrict__ qprev,
+                                                    const double4 *__restrict__ p, int i, int pn, double dt2) {
+  if (qprev == nullptr || i >= pn) return q[i];
+  double4 v = qprev[i];
+  const double4 pp = p[i];
+  v.x = __dadd_rn(v.x, __dmul_rn(pp.x, dt2));
+  v.y = __dadd_rn(v.y, __dmul_rn(pp.y, dt2));
+  v.z = __dadd_rn(v.z, __dmul_rn(pp.z, dt2));
+  return v;
+}
+
+__global__ void k_expiry_disp(const double4 *__restrict__ q, const double4 *__restrict__ qprev,
+                              const double4 *__restrict__ p, int pn, double dt2, const double4 *__restrict__ q0,
                               double *__restrict__ disp, int tn, Ctrl *ctrl, double BL) {
   if (ctrl->phase == 0) return;
   __shared__ double sh[TPB / 32];
   __shared__ bool last;
   double v = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tn; i += (long long)gridDim.x * blockDim.x) {
-    const double4 a = q0[i], b = q[i];
+    const double4 a = q0[i], b = current_position(q, qprev, p, (int)i, pn, dt2);
     double dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
     double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
     disp[i] = d2;
@@ -237,7 +252,8 @@ __global__ void k_expiry_disp(const double4 *__restrict__ q, const double4 *__re
 
 // Stage 3: candidates (pairlist.cc:90-97) and, by the last block, the candidate-pair test
 // (pairlist.cc:104-119).  Both outcomes depend only on the candidate SET, not on its order.
-__global__ void k_expiry_cand(const double4 *__restrict__ q, const double4 *__restrict__ q0,
+__global__ void k_expiry_cand(const double4 *__restrict__ q, const double4 *__restrict__ qprev,
+                              const double4 *__restrict__ p, int pn, double dt2, const double4 *__restrict__ q0,
                               const double *__restrict__ disp, int *__restrict__ cand, int tn, int Nl, Ctrl *ctrl,
                               double SL2, double CL2) {
   if (ctrl->phase == 0) return;
@@ -278,7 +294,7 @@ __global__ void k_expiry_cand(const double4 *__restrict__ q, const double4 *__re
     double dx = o1.x - o2.x, dy = o1.y - o2.y, dz = o1.z - o2.z;
     double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
     if (d2 < SL2) continue;
-    const double4 n1 = q[i1], n2 = q[i2];
+    const double4 n1 = current_position(q, qprev, p, i1, pn, dt2), n2 = current_position(q, qprev, p, i2, pn, dt2);
     dx = n1.x - n2.x; dy = n1.y - n2.y; dz = n1.z - n2.z;
     d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
     if (d2 < CL2) hit = 1;
@@ -300,9 +316,11 @@ int expiry_check_launch(Unit *u) {
   else
     k_expiry_vmax<<<grid_p, TPB, 0, u->stream>>>(u->p.ptr, (int)u->pn, u->ctrl, u->c.dt, u->c.BL);
   u->vmax_ready = false;
-  k_expiry_disp<<<grid_t, TPB, 0, u->stream>>>(u->q.ptr, u->q0.ptr, u->disp.ptr, (int)u->tn, u->ctrl, u->c.BL);
-  k_expiry_cand<<<grid_t, TPB, 0, u->stream>>>(u->q.ptr, u->q0.ptr, u->disp.ptr, u->cand.ptr, (int)u->tn, Nl,
-                                               u->ctrl, u->c.SL2, u->c.CL2);
+  const double4 *qprev = u->predrifted ? u->q_alt.ptr : nullptr;
+  k_expiry_disp<<<grid_t, TPB, 0, u->stream>>>(u->q.ptr, qprev, u->p.ptr, (int)u->pn, u->c.dt2, u->q0.ptr, u->disp.ptr,
+                                               (int)u->tn, u->ctrl, u->c.BL);
+  k_expiry_cand<<<grid_t, TPB, 0, u->stream>>>(u->q.ptr, qprev, u->p.ptr, (int)u->pn, u->c.dt2, u->q0.ptr, u->disp.ptr,
+                                               u->cand.ptr, (int)u->tn, Nl, u->ctrl, u->c.SL2, u->c.CL2);
   u->launches += 3;
   MDB_CUDA(cudaGetLastError());
   MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->expired, &u->ctrl->expired, 2 * sizeof(int), cudaMemcpyDeviceToHost,

@@ -115,6 +115,10 @@ struct Unit {
   int seed = 0;                   // MDUnit::SetSeed
   double zeta = 0.0;              // Variables::Zeta (variables.h:19)
   bool vmax_ready = false;        // ctrl->vmax2_bits already holds max |p|^2 of the current momenta
+  // speculative pre-drift (force.cu MODE 3): q holds the locals ALREADY advanced by the next step's first half
+  // drift; q_alt still holds them at the last half step, from which the end-of-step positions are
+  // q_alt + p dt/2 (bit-identical).  api.cu:materialize() undoes it on demand.
+  bool predrifted = false;
 
   // particle store, SLOT order: locals [0,pn) cell-sorted, ghosts [pn,tn) in arrival order
   DevBuf<double4> q, q_alt;       // positions (x,y,z,0)
@@ -235,15 +239,14 @@ int ghost_pack(Unit *srcu, int dir);                                     // into
 
 // integrate.cu
 int drift_half(Unit *u);
+int drift_half_buffer(Unit *u, double4 *qbuf);                           // the same on a given position buffer
 int heatbath_momenta(Unit *u);
 int langevin_kick(Unit *u);
 int expiry_check_local(Unit *u, int *expired);                           // sync
 
 // force.cu
 int force_kick(Unit *u);
-int force_kick_drift(Unit *u);
-int force_kick_drift_interior(Unit *u);                                  // first half of the split launch
-int force_kick_drift_boundary(Unit *u);                                  // second half + buffer swap                                           // kick + second half drift, swaps q / q_alt
+int force_kick_drift(Unit *u, bool predrift, int part);                  // fused kick + drift(s); swaps q / q_alt                                           // kick + second half drift, swaps q / q_alt
 int force_impulse(Unit *u, double *f3_host, long long cap_rows);         // sync
 
 // observe.cu

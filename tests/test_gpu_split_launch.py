@@ -16,3 +16,19 @@ def test_split_force_launch_matches_reference_golden(name, monkeypatch):
     rec, cfg, steps, init_build = load_golden(name)
     worst = check_cuda_against_records(rec, steps, init_build, None)
     print(name, worst)
+
+
+# The fused force kernel also performs the NEXT step's first half drift speculatively (force.cu MODE 3) and
+# api.cu undoes it whenever end-of-step positions are needed.  Observing every step (test_gpu_golden.py) undoes
+# it every step; observing rarely lets the pre-drifted state run through rebuilds and expiry tests.
+@pytest.mark.parametrize("name", ["bench1", "bench8", "slab2", "collision2"])
+def test_predrifted_steps_match_reference_golden(name):
+    rec, cfg, steps, init_build = load_golden(name)
+    worst = check_cuda_against_records(rec, steps, init_build, None, observe_every=25)
+    print(name, worst)
+
+
+def test_plain_path_without_predrift(monkeypatch):
+    monkeypatch.setenv("MDB200_NO_PREDRIFT", "1")
+    rec, cfg, steps, init_build = load_golden("bench1")
+    check_cuda_against_records(rec, steps, init_build, None, observe_every=25)
