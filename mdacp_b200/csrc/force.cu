@@ -28,6 +28,32 @@
 
 namespace mdb {
 
+// tuning knobs (scripts/build_variants.sh)
+#ifndef FORCE_UNROLL
+#define FORCE_UNROLL 1
+#endif
+#ifndef FORCE_MINBLK
+#define FORCE_MINBLK 10
+#endif
+#ifndef FORCE_PF_L1
+#define FORCE_PF_L1 2
+#endif
+#ifndef FORCE_PF_CHUNK
+#define FORCE_PF_CHUNK 0
+#endif
+#ifndef FORCE_PERSIST
+#define FORCE_PERSIST 0
+#endif
+#ifndef FORCE_POS_EVICT_LAST
+#define FORCE_POS_EVICT_LAST 0
+#endif
+#ifndef FORCE_LIST_EVICT_FIRST
+#define FORCE_LIST_EVICT_FIRST 0
+#endif
+#ifndef FORCE_TPB
+#define FORCE_TPB 128
+#endif
+
 // 1 / x: hardware seed (MUFU.RCP64H) + one cubic (Halley-type) refinement y (1 + e + e^2);
 // GUARD adds one linear Newton step (2 DFMA) that makes the result independent of the seed quality.
 template <bool GUARD>
@@ -74,28 +100,26 @@ __device__ __forceinline__ double pair_df(double r2, const ForceConsts &fc) {
 
 __device__ __forceinline__ void ld_q256(const double4 *p, double &x, double &y, double &z) {
   double w;
+#if FORCE_POS_EVICT_LAST
+  asm("ld.global.nc.L1::evict_last.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(p));
+#else
   asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(p));
+#endif
   (void)w;
 }
 
-#ifndef FORCE_UNROLL
-#define FORCE_UNROLL 1
+
+// list words are streamed once: FORCE_LIST_EVICT_FIRST marks their L1 lines as first to go, so that they
+// displace fewer position lines
+__device__ __forceinline__ uint2 ld_list(const uint2 *p) {
+#if FORCE_LIST_EVICT_FIRST
+  uint2 v;
+  asm("ld.global.nc.L1::evict_first.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
 #endif
-#ifndef FORCE_MINBLK
-#define FORCE_MINBLK 10
-#endif
-#ifndef FORCE_PF_L1
-#define FORCE_PF_L1 2
-#endif
-#ifndef FORCE_PF_CHUNK
-#define FORCE_PF_CHUNK 0
-#endif
-#ifndef FORCE_PERSIST
-#define FORCE_PERSIST 0
-#endif
-#ifndef FORCE_TPB
-#define FORCE_TPB 128
-#endif
+}
 
 template <int VARIANT>
 __device__ __forceinline__ void pair_accumulate(double ax, double ay, double az, double jx, double jy, double jz,
@@ -147,7 +171,7 @@ __device__ __forceinline__ void force_warp(long long w, int lane, FORCE_PARAMS, 
   if (lane * 128 < len2 * 256)
     asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(lp - lane) + lane * 128));
 #endif
-  uint2 en = (len2 > 0) ? __ldg(lp) : make_uint2(0u, 0u);
+  uint2 en = (len2 > 0) ? ld_list(lp) : make_uint2(0u, 0u);
 #pragma unroll UNR
   for (int k = 0; k < len2; k++) {
     const uint2 e = en;
@@ -157,7 +181,7 @@ __device__ __forceinline__ void force_warp(long long w, int lane, FORCE_PARAMS, 
     // which serialises its latency behind the gather's (1.15 -> 1.42 ms at 5.5 M particles)
     if (k + FORCE_PF_L1 < len2) asm volatile("prefetch.global.L1 [%0];" ::"l"(lp + (long long)(k + FORCE_PF_L1) * 32));
 #endif
-    if (k + 1 < len2) en = __ldg(lp + (long long)(k + 1) * 32);
+    if (k + 1 < len2) en = ld_list(lp + (long long)(k + 1) * 32);
     double j0x, j0y, j0z, j1x, j1y, j1z;
     ld_q256(q + e.x, j0x, j0y, j0z);
     ld_q256(q + e.y, j1x, j1y, j1z);
