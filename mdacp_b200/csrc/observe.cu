@@ -31,13 +31,28 @@ __device__ __forceinline__ double block_sum(double v, double *sh) {
   return r;  // valid on thread 0
 }
 
+// 1 / x to full double precision without the division sequence: hardware seed (MUFU.RCP64H), one cubic and one
+// linear Newton step (as in force.cu)
+__device__ __forceinline__ double rcp_full(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, fma(e, e, e), y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+
+// observer.cc:18-79 with s3 = r^-6:  U term 4 (s3^2 - s3 + C2 r2 + C0);
+// W term ((24 r6 - 48) / (r6 r6 r2) + 8 C2) r2 = 24 s3 - 48 s3^2 + 8 C2 r2
 __device__ __forceinline__ void pair_uw(double dx, double dy, double dz, double CL2, double C2, double C0,
                                         double &ue, double &we) {
   const double r2 = dx * dx + dy * dy + dz * dz;
   if (r2 > CL2) return;
-  const double r6 = r2 * r2 * r2;
-  ue += 4.0 * (1.0 / (r6 * r6) - 1.0 / r6 + C2 * r2 + C0);
-  we += ((24.0 * r6 - 48.0) / (r6 * r6 * r2) + C2 * 8.0) * r2;
+  const double s = rcp_full(r2);
+  const double s3 = s * s * s;
+  const double c2r2 = C2 * r2;
+  ue += 4.0 * (fma(s3, s3, -s3) + c2r2 + C0);
+  we += fma(-48.0 * s3, s3, 24.0 * s3) + 8.0 * c2r2;
 }
 
 // K over locals (grid-stride over particles) and U, W over the list (grid-stride over force-warps: kG lanes
@@ -62,13 +77,15 @@ k_observe(const double4 *__restrict__ q, const double4 *__restrict__ p, const un
     for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < nwarps; w += wstride) {
       const long long a = w * kPW + lane / kG;
       const double4 qa = q[a < pn ? a : (long long)pn - 1];
-      const long long base = warp_off[w];
-      const int steps = warp_len[w];
+      const uint2 *__restrict__ lp = reinterpret_cast<const uint2 *>(list + warp_off[w]) + lane;
+      const int len2 = warp_len[w] >> 1;  // one 8-byte load = the entries of two steps (unit.h)
       double ue = 0.0, we = 0.0;
-      for (int s = 0; s < steps; s++) {
+      for (int k = 0; k < len2; k++) {
         // padding entries point at the far-away sentinel particle: r2 > CL2, no contribution
-        const double4 qj = q[list[base + list_word(s, lane)]];
-        pair_uw(qj.x - qa.x, qj.y - qa.y, qj.z - qa.z, CL2, C2, C0, ue, we);
+        const uint2 e = __ldg(lp + (long long)k * 32);
+        const double4 q0 = q[e.x], q1 = q[e.y];
+        pair_uw(q0.x - qa.x, q0.y - qa.y, q0.z - qa.z, CL2, C2, C0, ue, we);
+        pair_uw(q1.x - qa.x, q1.y - qa.y, q1.z - qa.z, CL2, C2, C0, ue, we);
       }
       // every directed entry carries weight 0.5 (see the header)
       uu += 0.5 * ue;
