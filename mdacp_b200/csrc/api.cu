@@ -603,6 +603,10 @@ int mdb200_upload(mdb200_unit *h, const double (*q)[4], const double (*p)[4], co
     ratio *= (w + 2.0 * u->c.SL) / w;
   }
   long long need_t = std::max<long long>(u->prm.tn_capacity, (long long)(need_p * std::min(ratio, 27.0) * 1.05) + 1024);
+  // arrivals of a migration are appended past the ghosts before the cell sort compacts them (cells.cu:
+  // migrate_unpack), so the per-local arrays must reach past tn as well -- matters for small boxes, where the
+  // ghost shell is as large as the box; sized here so that no rebuild re-allocates
+  need_p = std::max<long long>(need_p, need_t - need_p / 4);
   MDB_TRY(ensure_capacity(u, need_p, need_t));
   if (pn > 0) {
     // stage through the alt buffers (device-side repack keeps lane 3 == 0)

@@ -40,14 +40,15 @@ template <typename T>
 struct DevBuf {
   T *ptr = nullptr;
   size_t cap = 0;
-  int ensure(size_t n, bool keep = false, cudaStream_t st = 0) {
+  __attribute__((noinline)) int ensure(size_t n, bool keep = false, cudaStream_t st = 0) {
     if (n <= cap) return MDB200_OK;
     // generous head-room: re-allocation (cudaMalloc + cudaFree, both device-synchronising) inside the step
     // loop costs far more than the memory
     size_t ncap = n + n / 4 + 64;
     T *np = nullptr;
     if (cap && getenv("MDB200_DEBUG"))
-      fprintf(stderr, "[mdb200] realloc %zu -> %zu elements of %zu bytes\n", cap, ncap, sizeof(T));
+      fprintf(stderr, "[mdb200] realloc %zu -> %zu elements of %zu bytes (requested %zu, caller %p)\n", cap, ncap,
+              sizeof(T), n, __builtin_return_address(0));
     MDB_CUDA(cudaMalloc(&np, ncap * sizeof(T)));
     if (keep && ptr && cap) {
       MDB_CUDA(cudaMemcpyAsync(np, ptr, cap * sizeof(T), cudaMemcpyDeviceToDevice, st));
