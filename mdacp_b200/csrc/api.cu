@@ -629,6 +629,7 @@ int mdb200_upload(mdb200_unit *h, const double (*q)[4], const double (*p)[4], co
   u->list_initialized = false;
   u->vmax_ready = false;
   u->predrifted = false;
+  u->max_row = 0;
   u->npairs = 0;
   u->list_entries = 0;
   for (int d = 0; d < 6; d++) { u->n_border[d] = 0; u->recv_cnt[d] = 0; u->recv_off[d] = pn; }

@@ -22,6 +22,7 @@
 // C-ABI are always in reference indices.
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <utility>
 #include "unit.h"
 
@@ -594,6 +595,113 @@ k_pair_search(const double4 *__restrict__ q, const int *__restrict__ cell_start,
   }
 }
 
+// One-pass variant for every rebuild after the first.  Rows get a FIXED capacity of S steps per force-warp
+// (S = longest row of the previous build + head-room), so the layout is known up front (warp_off[w] =
+// 32 S w) and the distance tests run once: each thread buffers its hits in local memory, then deals them out
+// in rainbow order.  The force kernel reads warp_len[w] steps of each row as before, i.e. no extra traffic;
+// only the allocation is larger.  A warp that needs more than S steps raises ctrl->scratch[6] and writes
+// nothing; the host then falls back to the two-pass build (and the next rebuild uses a larger S).
+#define ONEPASS_HCAP 192
+__global__ void __launch_bounds__(128)
+k_pair_search_onepass(const double4 *__restrict__ q, const int *__restrict__ cell_start,
+                      const int *__restrict__ gcell_start, const int *__restrict__ gcell_items,
+                      int *__restrict__ row_count, unsigned *__restrict__ row_cls, long long *__restrict__ warp_off,
+                      int *__restrict__ warp_len, unsigned *__restrict__ list, int *__restrict__ warp_flag, int pn,
+                      int sentinel, int S, Consts c, Ctrl *ctrl) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;  // local slot
+  const int lane = threadIdx.x & 31;
+  const int fw = a / kPW;                               // force-warp of this slot
+  const int flane0 = (a % kPW) * kG;                    // first lane of its group
+  const bool act = a < pn;
+  const bool in_tail = (long long)fw * kPW < pn;        // slot belongs to an existing force-warp
+  const int cap = min(ONEPASS_HCAP, S * kG);
+  unsigned hits[ONEPASS_HCAP];
+  int n = 0, n_local_entries = 0;
+  unsigned cls = 0;
+  if (act) {
+    const double4 qa = q[a];
+    const int ci = cell_index(qa, c, 0);
+    const int cx = ci % c.m[0];
+    const int cy = (ci / c.m[0]) % c.m[1];
+    const int cz = ci / (c.m[0] * c.m[1]);
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, c.m[0] - 1);
+#pragma unroll 1
+    for (int ghosts = 0; ghosts < 2; ghosts++) {  // ghosts after all locals
+      const int *__restrict__ start = ghosts ? gcell_start : cell_start;
+      for (int dz = -1; dz <= 1; dz++) {
+        const int z = cz + dz;
+        if (z < 0 || z >= c.m[2]) continue;
+        for (int dy = -1; dy <= 1; dy++) {
+          const int y = cy + dy;
+          if (y < 0 || y >= c.m[1]) continue;
+          const int rowc = c.m[0] * (y + c.m[1] * z);
+          // the three x-neighbours are contiguous in cell order: one range per (y,z)
+          const int jb = start[rowc + x0], je = start[rowc + x1 + 1];
+          for (int k = jb; k < je; k++) {
+            const int j = ghosts ? gcell_items[k] : k;
+            if (j == a) continue;
+            if (within_search(qa, q[j], c.SL2)) {
+              if (n < cap) hits[n] = (unsigned)j;
+              cls += 1u << (8 * (j & 3));
+              n++;
+            }
+          }
+        }
+      }
+      if (!ghosts) n_local_entries = n;
+    }
+  }
+  // steps of this local, maximum over the kPW locals of its force-warp, rounded up to even
+  int wl = (n + kG - 1) / kG;
+  int over = (n > cap) ? 1 : 0;
+  int hg = (n > n_local_entries) ? 1 : 0;
+#pragma unroll
+  for (int o = kPW / 2; o > 0; o >>= 1) {
+    wl = max(wl, __shfl_xor_sync(0xffffffffu, wl, o));
+    over |= __shfl_xor_sync(0xffffffffu, over, o);
+    hg |= __shfl_xor_sync(0xffffffffu, hg, o);
+  }
+  wl = (wl + 1) & ~1;
+  if (wl > S) over = 1;
+  int mrow = n;
+  // reference-style pair count in half-pairs (see k_pair_search)
+  unsigned long long nref = (unsigned long long)(n_local_entries + 2 * (n - n_local_entries));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mrow = max(mrow, __shfl_xor_sync(0xffffffffu, mrow, o));
+    nref += __shfl_xor_sync(0xffffffffu, nref, o);
+  }
+  if (lane == 0) {
+    if (nref) atomicAdd(&ctrl->npairs, nref);
+    if (mrow > *(volatile int *)&ctrl->max_row) atomicMax(&ctrl->max_row, mrow);
+  }
+  if (over) {
+    if ((a % kPW) == 0) ctrl->scratch[6] = 1;
+    return;
+  }
+  const long long base = (long long)fw * S * 32;
+  if (in_tail && (a % kPW) == 0) {
+    warp_off[fw] = base;
+    warp_len[fw] = wl;
+    warp_flag[fw] = hg;  // boundary warp = one of its rows holds a ghost
+  }
+  if (act) {
+    row_count[a] = n;
+    row_cls[a] = cls;
+    RowOrder ro;
+    ro.init(cls);
+    if (((cls & 0xFFu) + ((cls >> 8) & 0xFFu) + ((cls >> 16) & 0xFFu) + (cls >> 24)) != (unsigned)n)
+      atomicOr(&ctrl->err, (int)DE_CAPACITY);  // a class count wrapped its 8 bits
+    for (int k = 0; k < n; k++) {
+      const unsigned j = hits[k];
+      const int e = ro.place((int)j);
+      list[base + list_word(e / kG, flane0 + e % kG)] = j;
+    }
+  }
+  if (in_tail)
+    for (int e = n; e < wl * kG; e++) list[base + list_word(e / kG, flane0 + e % kG)] = (unsigned)sentinel;
+}
+
 __global__ void k_warp_order(const int *__restrict__ flag, const int *__restrict__ scanv, int *__restrict__ order,
                              int nw, int n_interior) {
   int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -624,32 +732,68 @@ int build_pair_list(Unit *u) {
   MDB_TRY(u->scan_ws64.ensure(scan_workspace_ints(nw + 2)));
   const int tpb = 128;
   const long long nthr = nw * kPW;  // threads past pn only pad the tail warp
-  k_pair_search<false><<<nblk(nthr, tpb), tpb, 0, u->stream>>>(
-      u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr, u->gcell_items.ptr, u->ref_of_slot.ptr, u->row_count.ptr, u->row_cls.ptr,
-      u->warp_off.ptr, u->warp_len.ptr, u->list.ptr, u->warp_flag.ptr, (int)pn, sentinel_index(u), u->c, u->ctrl);
-  u->launches++;
-  MDB_TRY(exclusive_scan_i32_to_i64(u->warp_len.ptr, u->warp_off.ptr, nw, u->scan_ws64.ptr, u->stream, &u->launches, 32));
-  MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->scratch[4], u->warp_off.ptr + nw, sizeof(long long), cudaMemcpyDeviceToHost,
-                           u->stream));
-  MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->npairs, &u->ctrl->npairs, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                           u->stream));
-  MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->max_row, &u->ctrl->max_row, sizeof(int), cudaMemcpyDeviceToHost, u->stream));
-  MDB_CUDA(cudaStreamSynchronize(u->stream));
-  long long entries;
-  memcpy(&entries, &u->ctrl_host->scratch[4], sizeof(long long));
-  u->list_entries = entries;
-  u->npairs = (long long)u->ctrl_host->npairs;
-  u->max_row = u->ctrl_host->max_row;
-  if ((size_t)entries + 64 > u->list.cap && getenv("MDB200_DEBUG"))
-    fprintf(stderr, "[mdb200] list grows: %lld entries > capacity %zu\n", entries, u->list.cap);
-  // Head-room: rows of a freshly generated lattice grow by ~20 % once it thermalises (the next FCC shell
-  // sits just outside the search radius), and re-allocating a multi-GB list inside the step loop stalls
-  // for hundreds of ms (cudaMalloc + cudaFree of several GB) -- so allocate 40 % more than needed.
-  if ((size_t)entries + 64 > u->list.cap) MDB_TRY(u->list.ensure((size_t)entries + (size_t)entries * 2 / 5 + 64));
-  k_pair_search<true><<<nblk(nthr, tpb), tpb, 0, u->stream>>>(
-      u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr, u->gcell_items.ptr, u->ref_of_slot.ptr, u->row_count.ptr, u->row_cls.ptr,
-      u->warp_off.ptr, u->warp_len.ptr, u->list.ptr, u->warp_flag.ptr, (int)pn, sentinel_index(u), u->c, u->ctrl);
-  u->launches++;
+  bool built = false;
+  // ---- one pass with fixed-capacity rows, sized from the previous build (every rebuild but the first)
+  if (u->max_row > 0 && !getenv("MDB200_NO_ONEPASS")) {
+    const int S = (((u->max_row + kG - 1) / kG + 3) + 1) & ~1;  // longest row so far + 3 steps, even
+    if (S * kG <= ONEPASS_HCAP) {
+      const long long entries = nw * (long long)S * 32;
+      if ((size_t)entries + 64 > u->list.cap) {
+        if (getenv("MDB200_DEBUG")) fprintf(stderr, "[mdb200] list grows: %lld entries > capacity %zu\n", entries, u->list.cap);
+        MDB_TRY(u->list.ensure((size_t)entries + (size_t)entries / 8 + 64));
+      }
+      MDB_CUDA(cudaMemsetAsync(&u->ctrl->scratch[6], 0, sizeof(int), u->stream));
+      k_pair_search_onepass<<<nblk(nthr, tpb), tpb, 0, u->stream>>>(
+          u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr, u->gcell_items.ptr, u->row_count.ptr, u->row_cls.ptr,
+          u->warp_off.ptr, u->warp_len.ptr, u->list.ptr, u->warp_flag.ptr, (int)pn, sentinel_index(u), S, u->c, u->ctrl);
+      u->launches++;
+      MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->scratch[6], &u->ctrl->scratch[6], sizeof(int), cudaMemcpyDeviceToHost, u->stream));
+      MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->npairs, &u->ctrl->npairs, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                               u->stream));
+      MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->max_row, &u->ctrl->max_row, sizeof(int), cudaMemcpyDeviceToHost, u->stream));
+      MDB_CUDA(cudaStreamSynchronize(u->stream));
+      u->max_row = std::max(u->max_row, u->ctrl_host->max_row);  // also after an overflow: the next S fits
+      if (u->ctrl_host->scratch[6] == 0) {
+        built = true;
+        u->list_entries = entries;
+        u->npairs = (long long)(u->ctrl_host->npairs / 2);
+      } else {
+        if (getenv("MDB200_DEBUG")) fprintf(stderr, "[mdb200] one-pass list build overflowed S = %d steps; two-pass build\n", S);
+        MDB_CUDA(cudaMemsetAsync(&u->ctrl->npairs, 0, sizeof(unsigned long long), u->stream));
+        MDB_CUDA(cudaMemsetAsync(&u->ctrl->max_row, 0, sizeof(int), u->stream));
+      }
+    }
+  }
+  // ---- two passes (count, scan, fill): packed rows
+  if (!built) {
+    k_pair_search<false><<<nblk(nthr, tpb), tpb, 0, u->stream>>>(
+        u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr, u->gcell_items.ptr, u->ref_of_slot.ptr, u->row_count.ptr, u->row_cls.ptr,
+        u->warp_off.ptr, u->warp_len.ptr, u->list.ptr, u->warp_flag.ptr, (int)pn, sentinel_index(u), u->c, u->ctrl);
+    u->launches++;
+    MDB_TRY(exclusive_scan_i32_to_i64(u->warp_len.ptr, u->warp_off.ptr, nw, u->scan_ws64.ptr, u->stream, &u->launches, 32));
+    MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->scratch[4], u->warp_off.ptr + nw, sizeof(long long), cudaMemcpyDeviceToHost,
+                             u->stream));
+    MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->npairs, &u->ctrl->npairs, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                             u->stream));
+    MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->max_row, &u->ctrl->max_row, sizeof(int), cudaMemcpyDeviceToHost, u->stream));
+    MDB_CUDA(cudaStreamSynchronize(u->stream));
+    long long entries;
+    memcpy(&entries, &u->ctrl_host->scratch[4], sizeof(long long));
+    u->list_entries = entries;
+    u->npairs = (long long)u->ctrl_host->npairs;
+    u->max_row = std::max(u->max_row, u->ctrl_host->max_row);
+    if ((size_t)entries + 64 > u->list.cap && getenv("MDB200_DEBUG"))
+      fprintf(stderr, "[mdb200] list grows: %lld entries > capacity %zu\n", entries, u->list.cap);
+    // Head-room: rows of a freshly generated lattice grow by ~20 % once it thermalises (the next FCC shell
+    // sits just outside the search radius), the fixed-capacity rows of the one-pass rebuilds need more still,
+    // and re-allocating a multi-GB list inside the step loop stalls for hundreds of ms (cudaMalloc + cudaFree
+    // of several GB) -- so allocate 70 % more than needed.
+    if ((size_t)entries + 64 > u->list.cap) MDB_TRY(u->list.ensure((size_t)entries + (size_t)entries * 7 / 10 + 64));
+    k_pair_search<true><<<nblk(nthr, tpb), tpb, 0, u->stream>>>(
+        u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr, u->gcell_items.ptr, u->ref_of_slot.ptr, u->row_count.ptr, u->row_cls.ptr,
+        u->warp_off.ptr, u->warp_len.ptr, u->list.ptr, u->warp_flag.ptr, (int)pn, sentinel_index(u), u->c, u->ctrl);
+    u->launches++;
+  }
   // interior warps first, boundary warps last (stable within each class)
   MDB_TRY(exclusive_scan_i32(u->warp_flag.ptr, u->scan.ptr, nw, u->scan_ws.ptr, u->stream, &u->launches));
   MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->scratch[5], u->scan.ptr + nw, sizeof(int), cudaMemcpyDeviceToHost, u->stream));
