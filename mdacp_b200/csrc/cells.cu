@@ -599,8 +599,9 @@ k_pair_search(const double4 *__restrict__ q, const int *__restrict__ cell_start,
 // (S = longest row of the previous build + head-room), so the layout is known up front (warp_off[w] =
 // 32 S w) and the distance tests run once: each thread buffers its hits in local memory, then deals them out
 // in rainbow order.  The force kernel reads warp_len[w] steps of each row as before, i.e. no extra traffic;
-// only the allocation is larger.  A warp that needs more than S steps raises ctrl->scratch[6] and writes
-// nothing; the host then falls back to the two-pass build (and the next rebuild uses a larger S).
+// only the allocation is larger.  A warp that needs more than S steps raises ctrl->scratch[6] and writes no
+// entries; its counts are still complete, so the host falls back to scan + fill of the two-pass build (and the
+// next rebuild uses a larger S).
 #define ONEPASS_HCAP 192
 __global__ void __launch_bounds__(128)
 k_pair_search_onepass(const double4 *__restrict__ q, const int *__restrict__ cell_start,
@@ -675,23 +676,26 @@ k_pair_search_onepass(const double4 *__restrict__ q, const int *__restrict__ cel
     if (nref) atomicAdd(&ctrl->npairs, nref);
     if (mrow > *(volatile int *)&ctrl->max_row) atomicMax(&ctrl->max_row, mrow);
   }
-  if (over) {
-    if ((a % kPW) == 0) ctrl->scratch[6] = 1;
-    return;
-  }
-  const long long base = (long long)fw * S * 32;
+  // counts are complete even when a row overflowed its buffer: the fallback only needs scan + fill
   if (in_tail && (a % kPW) == 0) {
-    warp_off[fw] = base;
     warp_len[fw] = wl;
     warp_flag[fw] = hg;  // boundary warp = one of its rows holds a ghost
   }
   if (act) {
     row_count[a] = n;
     row_cls[a] = cls;
-    RowOrder ro;
-    ro.init(cls);
     if (((cls & 0xFFu) + ((cls >> 8) & 0xFFu) + ((cls >> 16) & 0xFFu) + (cls >> 24)) != (unsigned)n)
       atomicOr(&ctrl->err, (int)DE_CAPACITY);  // a class count wrapped its 8 bits
+  }
+  if (over) {
+    if ((a % kPW) == 0) ctrl->scratch[6] = 1;
+    return;
+  }
+  const long long base = (long long)fw * S * 32;
+  if (in_tail && (a % kPW) == 0) warp_off[fw] = base;
+  if (act) {
+    RowOrder ro;
+    ro.init(cls);
     for (int k = 0; k < n; k++) {
       const unsigned j = hits[k];
       const int e = ro.place((int)j);
@@ -732,7 +736,7 @@ int build_pair_list(Unit *u) {
   MDB_TRY(u->scan_ws64.ensure(scan_workspace_ints(nw + 2)));
   const int tpb = 128;
   const long long nthr = nw * kPW;  // threads past pn only pad the tail warp
-  bool built = false;
+  bool built = false, counted = false;
   // ---- one pass with fixed-capacity rows, sized from the previous build (every rebuild but the first)
   if (u->max_row > 0 && !getenv("MDB200_NO_ONEPASS")) {
     const int S = (((u->max_row + kG - 1) / kG + 3) + 1) & ~1;  // longest row so far + 3 steps, even
@@ -758,18 +762,20 @@ int build_pair_list(Unit *u) {
         u->list_entries = entries;
         u->npairs = (long long)(u->ctrl_host->npairs / 2);
       } else {
-        if (getenv("MDB200_DEBUG")) fprintf(stderr, "[mdb200] one-pass list build overflowed S = %d steps; two-pass build\n", S);
-        MDB_CUDA(cudaMemsetAsync(&u->ctrl->npairs, 0, sizeof(unsigned long long), u->stream));
-        MDB_CUDA(cudaMemsetAsync(&u->ctrl->max_row, 0, sizeof(int), u->stream));
+        if (getenv("MDB200_DEBUG")) fprintf(stderr, "[mdb200] one-pass list build overflowed S = %d steps; scan + fill\n", S);
+        counted = true;  // row_count / row_cls / warp_len / npairs / max_row are complete
+        u->npairs = (long long)(u->ctrl_host->npairs / 2);
       }
     }
   }
   // ---- two passes (count, scan, fill): packed rows
   if (!built) {
-    k_pair_search<false><<<nblk(nthr, tpb), tpb, 0, u->stream>>>(
-        u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr, u->gcell_items.ptr, u->ref_of_slot.ptr, u->row_count.ptr, u->row_cls.ptr,
-        u->warp_off.ptr, u->warp_len.ptr, u->list.ptr, u->warp_flag.ptr, (int)pn, sentinel_index(u), u->c, u->ctrl);
-    u->launches++;
+    if (!counted) {
+      k_pair_search<false><<<nblk(nthr, tpb), tpb, 0, u->stream>>>(
+          u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr, u->gcell_items.ptr, u->ref_of_slot.ptr, u->row_count.ptr, u->row_cls.ptr,
+          u->warp_off.ptr, u->warp_len.ptr, u->list.ptr, u->warp_flag.ptr, (int)pn, sentinel_index(u), u->c, u->ctrl);
+      u->launches++;
+    }
     MDB_TRY(exclusive_scan_i32_to_i64(u->warp_len.ptr, u->warp_off.ptr, nw, u->scan_ws64.ptr, u->stream, &u->launches, 32));
     MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->scratch[4], u->warp_off.ptr + nw, sizeof(long long), cudaMemcpyDeviceToHost,
                              u->stream));
@@ -780,7 +786,7 @@ int build_pair_list(Unit *u) {
     long long entries;
     memcpy(&entries, &u->ctrl_host->scratch[4], sizeof(long long));
     u->list_entries = entries;
-    u->npairs = (long long)u->ctrl_host->npairs;
+    if (!counted) u->npairs = (long long)u->ctrl_host->npairs;
     u->max_row = std::max(u->max_row, u->ctrl_host->max_row);
     if ((size_t)entries + 64 > u->list.cap && getenv("MDB200_DEBUG"))
       fprintf(stderr, "[mdb200] list grows: %lld entries > capacity %zu\n", entries, u->list.cap);
