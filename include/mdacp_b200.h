@@ -164,7 +164,7 @@ int mdb200_timers(mdb200_unit *u, double out_ms[6], long long out_counts[2], int
 /* Enable per-phase CUDA-event timing (adds event records to the stream; default off). */
 int mdb200_set_profiling(mdb200_unit *u, int on);
 /* Diagnostics of the device neighbour list: out = {force warps, padded list entries, longest row,
- * unpadded entries, lanes per local, 0, 0, 0}. */
+ * unpadded entries, lanes per local, list words the force kernel walks, 0, 0}. */
 int mdb200_list_stats(mdb200_unit *u, double out[8]);
 /* CUDA-event stopwatch on the unit's stream (the stream every kernel of the unit is launched on):
  * record slot 0..7, then elapsed milliseconds between two recorded slots (synchronises on b). */

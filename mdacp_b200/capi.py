@@ -225,7 +225,7 @@ class Unit:
         o = (C.c_double * 8)()
         check(lib().mdb200_list_stats(self.handle, o))
         return {"warps": int(o[0]), "padded_entries": int(o[1]), "max_row": int(o[2]), "entries": int(o[3]),
-                "lanes_per_local": int(o[4])}
+                "lanes_per_local": int(o[4]), "walked_entries": int(o[5])}
 
     def event_record(self, slot):
         check(lib().mdb200_event_record(self.handle, slot))

@@ -872,6 +872,12 @@ int mdb200_list_stats(mdb200_unit *h, double out[8]) {
     double s = 0;
     for (size_t k = 0; k < rc.size(); k++) s += rc[k];
     out[3] = s;                       // sum of row lengths (unpadded entries)
+    std::vector<int> wl((size_t)u->nwarps);
+    MDB_CUDA(cudaMemcpyAsync(wl.data(), u->warp_len.ptr, sizeof(int) * wl.size(), cudaMemcpyDeviceToHost, u->stream));
+    MDB_CUDA(cudaStreamSynchronize(u->stream));
+    double w = 0;
+    for (size_t k = 0; k < wl.size(); k++) w += wl[k];
+    out[5] = 32.0 * w;                // list words the force kernel walks (rows padded to their warp's steps)
   }
   return MDB200_OK;
 }

@@ -23,4 +23,8 @@ t1 = time.time()
 c = u.counts()
 print("L=%g N=%d: %d steps %.3f ms/step wall, %d builds, npairs/N %.2f" % (L, len(q), nsteps, 1e3 * (t1 - t0) / nsteps,
                                                                         c["nbuilds"], c["npairs"] / len(q)))
+ls = u.list_stats()
+print("  list: entries %d, rows mean %.1f max %d; walked by the force kernel %d (+%.1f%% padding)" % (
+    ls["entries"], ls["entries"] / len(q), ls["max_row"], ls["walked_entries"],
+    100.0 * (ls["walked_entries"] / max(ls["entries"], 1) - 1)))
 mdm.close()
