@@ -260,6 +260,7 @@ struct DebugClock {
 static int make_pairlist(Unit **us, int n) {
   std::vector<long long> cnt(n);
   for (int i = 0; i < n; i++) us[i]->vmax_ready = false;  // migration changes the set of locals
+  for (int i = 0; i < n; i++) us[i]->inner_valid = false;  // the inner list is derived from the list being replaced
   DebugClock dbg(us[0]->stream);
   std::vector<PhaseTimer *> timers;
   struct TimerScope {
@@ -334,9 +335,16 @@ static int send_border_particles(Unit **us, int n) {
   return MDB200_OK;
 }
 
+// Inner-list budget (force.cu PRUNE), shared by all units of the process group: how far any pair can still
+// have closed since the inner list was derived.  us[0]->inner_left < 0 = derive again at the next force launch.
+// (kept in the group's first unit: inner_left = remaining distance budget, inner_delta = the delta the next
+// derivation will use, 0 = pruning off)
+static const int INNER_STEPS = 16;   // steps one derivation should last
+
 static int any_expired(Unit **us, int n, int *expired) {
   int ex = 0;
   bool uninit = false;
+  unsigned long long vbits = 0ull;
   for (int i = 0; i < n; i++)
     if (!us[i]->list_initialized) uninit = true;
   if (uninit) {
@@ -353,10 +361,26 @@ static int any_expired(Unit **us, int n, int *expired) {
       force_timer_resolve(us[i]);
       MDB_TRY(check_device_error(us[i]));
       ex |= us[i]->ctrl_host->expired;
+      vbits = std::max(vbits, us[i]->ctrl_host->last_vmax2_bits);
     }
   }
-  MDB_TRY(comm_allreduce_or(us, n, &ex));  // Communicator::AllReduceBoolean, mdmanager.cc:375
+  // Communicator::AllReduceBoolean (mdmanager.cc:375); the global max |p|^2 rides along
+  MDB_TRY(comm_allreduce_flag_bits(us, n, &ex, &vbits));
   *expired = ex;
+  // every particle (also the neighbours' that we see as ghosts) moves at most vmax dt per step, a pair
+  // distance changes by at most twice that
+  double v2;
+  memcpy(&v2, &vbits, sizeof(double));
+  const double per_step = 2.0 * sqrt(v2) * us[0]->c.dt;
+  if (uninit || !(per_step == per_step)) {
+    us[0]->inner_left = -1.0;
+    us[0]->inner_delta = 0.0;
+  } else {
+    us[0]->inner_left -= per_step;
+    // next derivation: a delta that lasts INNER_STEPS steps, at most half the skin; not worth it below 6 steps
+    const double want = INNER_STEPS * per_step, cap = 0.5 * us[0]->c.BL;
+    us[0]->inner_delta = (6.0 * per_step > cap || getenv("MDB200_NO_PRUNE")) ? 0.0 : std::min(want, cap);
+  }
   return MDB200_OK;
 }
 
@@ -382,6 +406,16 @@ static int calculate(Unit **us, int n) {
   if (expired || ct)
     for (int i = 0; i < n; i++) MDB_TRY(materialize(us[i]));
   if (expired) MDB_TRY(make_pairlist(us, n));
+  // which list the fused NVE launch walks: the inner one while its budget lasts and every unit has one,
+  // otherwise the outer one -- deriving a fresh inner list on the side when pruning is worthwhile
+  bool all_inner = true;
+  for (int i = 0; i < n; i++) all_inner = all_inner && us[i]->inner_valid;
+  int inner = 0;
+  double keep_len = 0.0;
+  if (!ct && all_inner && us[0]->inner_left >= 0.0) inner = 1;
+  else if (!ct && us[0]->inner_delta > 0.0) { inner = 2; keep_len = us[0]->prm.cutoff + us[0]->inner_delta; }
+  if (inner == 2) us[0]->inner_left = us[0]->inner_delta;
+  for (int i = 0; i < n; i++) us[i]->inner_valid = (inner != 0);
   for (int i = 0; i < n; i++) {
     DeviceGuard g(us[i]->device);
     PhaseTimer t(us[i], PH_INTEG);
@@ -455,9 +489,9 @@ static int calculate(Unit **us, int n) {
     Unit *u = us[0];
     DeviceGuard g(u->device);
     force_timer_begin(u);
-    MDB_TRY(force_kick_drift(u, predrift, 1));
+    MDB_TRY(force_kick_drift(u, predrift, 1, inner, keep_len));
     MDB_CUDA(cudaStreamWaitEvent(u->stream, u->ev_ghost, 0));
-    MDB_TRY(force_kick_drift(u, predrift, 2));
+    MDB_TRY(force_kick_drift(u, predrift, 2, inner, keep_len));
     force_timer_end(u);
     u->predrifted = predrift;
   } else {
@@ -469,10 +503,10 @@ static int calculate(Unit **us, int n) {
         PhaseTimer t(us[i], PH_FORCE);
         force_timer_begin(us[i]);
         if (split_test) {  // test hook: the interior / boundary launches of the overlapped path, back to back
-          MDB_TRY(force_kick_drift(us[i], predrift, 1));
-          MDB_TRY(force_kick_drift(us[i], predrift, 2));
+          MDB_TRY(force_kick_drift(us[i], predrift, 1, inner, keep_len));
+          MDB_TRY(force_kick_drift(us[i], predrift, 2, inner, keep_len));
         } else {
-          MDB_TRY(force_kick_drift(us[i], predrift, 0));
+          MDB_TRY(force_kick_drift(us[i], predrift, 0, inner, keep_len));
         }
         force_timer_end(us[i]);
         us[i]->predrifted = predrift;
@@ -573,7 +607,7 @@ int mdb200_destroy(mdb200_unit *h) {
   for (int d = 0; d < 6; d++) u->border[d].release();
   u->send_buf.release(); u->mig_send_q.release(); u->mig_send_p.release(); u->mig_recv_q.release();
   u->mig_recv_p.release(); u->mig_send_t.release(); u->mig_recv_t.release();
-  u->row_count.release(); u->row_cls.release(); u->force_queue.release(); u->sm_rank.release(); u->warp_flag.release(); u->warp_order.release();
+  u->row_count.release(); u->row_cls.release(); u->list_in.release(); u->warp_len_in.release(); u->warp_flag.release(); u->warp_order.release();
   if (u->cstream) { cudaStreamDestroy(u->cstream); cudaEventDestroy(u->ev_drift); cudaEventDestroy(u->ev_ghost); }
   u->warp_len.release(); u->warp_off.release(); u->list.release();
   u->disp.release(); u->cand.release(); u->partial.release();
@@ -629,6 +663,7 @@ int mdb200_upload(mdb200_unit *h, const double (*q)[4], const double (*p)[4], co
   u->list_initialized = false;
   u->vmax_ready = false;
   u->predrifted = false;
+  u->inner_valid = false;
   u->max_row = 0;
   u->npairs = 0;
   u->list_entries = 0;
@@ -735,6 +770,7 @@ int mdb200_update_position_half(mdb200_unit *h) {
   if (!h) return MDB200_EINVAL;
   DeviceGuard g(h->u.device);
   MDB_TRY(materialize(&h->u));
+  h->u.inner_valid = false;  // positions change outside the budgeted step
   return drift_half(&h->u);
 }
 

@@ -74,6 +74,7 @@ struct CommState {
   int nranks = 1, rank = 0;
   ncclComm_t comm = nullptr;
   int *d_cnt = nullptr;  // device scratch: [0] send count, [1] recv count
+  void *d_cnt64 = nullptr; // device scratch for the {flag, bits} all-reduce
   int users = 0;
 };
 static CommState g_comm;
@@ -139,6 +140,7 @@ int comm_init(Unit **us, int n, int nranks, int rank, const void *unique_id) {
       MDB_CUDA(cudaSetDevice(us[0]->device));
       MDB_NCCL(g_nccl.CommInitRank(&g_comm.comm, nranks, id, rank));
       MDB_CUDA(cudaMalloc(&g_comm.d_cnt, 8 * sizeof(int)));
+      MDB_CUDA(cudaMalloc(&g_comm.d_cnt64, 4 * sizeof(long long)));
       g_comm.nranks = nranks;
       g_comm.rank = rank;
     }
@@ -268,6 +270,23 @@ int comm_allreduce_or(Unit **us, int n, int *flag) {
   MDB_CUDA(cudaMemcpyAsync(&h, g_comm.d_cnt + 2, sizeof(int), cudaMemcpyDeviceToHost, u->stream));
   MDB_CUDA(cudaStreamSynchronize(u->stream));
   *flag = h;
+  return MDB200_OK;
+}
+
+int comm_allreduce_flag_bits(Unit **us, int n, int *flag, unsigned long long *bits) {
+  (void)n;
+  if (g_comm.nranks <= 1 || !g_comm.comm) return MDB200_OK;
+  Unit *u = us[0];
+  cudaSetDevice(u->device);
+  // bit patterns of non-negative doubles order like signed 64-bit integers
+  long long h[2] = {(long long)*flag, (long long)*bits};
+  long long *d = reinterpret_cast<long long *>(g_comm.d_cnt64);
+  MDB_CUDA(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, u->stream));
+  MDB_NCCL(g_nccl.AllReduce(d, d, 2, ncclInt64, ncclMax, g_comm.comm, u->stream));
+  MDB_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, u->stream));
+  MDB_CUDA(cudaStreamSynchronize(u->stream));
+  *flag = (int)h[0];
+  *bits = (unsigned long long)h[1];
   return MDB200_OK;
 }
 

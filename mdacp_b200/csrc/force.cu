@@ -41,14 +41,14 @@ namespace mdb {
 #ifndef FORCE_PF_CHUNK
 #define FORCE_PF_CHUNK 0
 #endif
-#ifndef FORCE_PERSIST
-#define FORCE_PERSIST 0
-#endif
 #ifndef FORCE_POS_EVICT_LAST
 #define FORCE_POS_EVICT_LAST 0
 #endif
 #ifndef FORCE_LIST_EVICT_FIRST
 #define FORCE_LIST_EVICT_FIRST 0
+#endif
+#ifndef FORCE_PRUNE_MINBLK
+#define FORCE_PRUNE_MINBLK 8
 #endif
 #ifndef FORCE_TPB
 #define FORCE_TPB 128
@@ -71,6 +71,7 @@ __device__ __forceinline__ double fast_rcp(double x) {
 }
 
 struct ForceConsts {
+  double keep2;   // PRUNE: (cutoff + delta)^2
   double dt2;     // dt / 2
   double CL2;
   double c24dt;   // 24 dt
@@ -121,18 +122,21 @@ __device__ __forceinline__ uint2 ld_list(const uint2 *p) {
 #endif
 }
 
+// returns the bit pattern of r2 (non-negative doubles order like their bit patterns)
 template <int VARIANT>
-__device__ __forceinline__ void pair_accumulate(double ax, double ay, double az, double jx, double jy, double jz,
-                                                long long cl2b, const ForceConsts &fc, double &fx, double &fy,
-                                                double &fz) {
+__device__ __forceinline__ long long pair_accumulate(double ax, double ay, double az, double jx, double jy,
+                                                     double jz, long long cl2b, const ForceConsts &fc, double &fx,
+                                                     double &fy, double &fz) {
   const double dx = jx - ax, dy = jy - ay, dz = jz - az;
   const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
   double df = pair_df<VARIANT>(r2, fc);
   // r2 > CL2: the pair contributes nothing (fcalculator.cc:209-211); also kills the sentinel padding
-  if (__double_as_longlong(r2) > cl2b) df = 0.0;
+  const long long r2b = __double_as_longlong(r2);
+  if (r2b > cl2b) df = 0.0;
   fx = fma(df, dx, fx);
   fy = fma(df, dy, fy);
   fz = fma(df, dz, fz);
+  return r2b;
 }
 
 // MODE 0: impulses to fout (parity probe).  MODE 1: kick, p += F dt (ForceCalculator::CalculateForce).
@@ -146,24 +150,37 @@ __device__ __forceinline__ void pair_accumulate(double ax, double ay, double az,
 //   k_drift_half passes.  The end-of-step positions q[a] + p_new dt/2 are not stored; whoever needs them
 //   (rebuild, observation, download, displacement test) recomputes them bit-identically from the untouched
 //   input buffer and p_new (api.cu:materialize, integrate.cu).
+// PRUNE (with MODE 2 / 3): the launch walks the full ("outer") list and, on the side, derives the INNER list:
+//   the entries with r2 <= keep2 = (cutoff + delta)^2, re-dealt in rainbow order into list_in at the same row
+//   offsets, with their own step counts in warp_len_in.  25 % of the listed pairs lie between the cutoff and
+//   the search length and contribute exactly zero; until some pair can have closed the distance delta
+//   (velocity budget kept by the host, api.cu) the following launches walk the inner list and give
+//   identical contributions (the dropped ones are exact zeros) at ~0.8x the gathers.
 enum { FORCE_IMPULSE = 0, FORCE_KICK = 1, FORCE_KICK_DRIFT = 2, FORCE_KICK_DRIFT2 = 3 };
 #define FORCE_PARAMS                                                                                              \
   const double4 *__restrict__ q, double4 *__restrict__ p, double *__restrict__ fout,                             \
       const unsigned *__restrict__ list, const long long *__restrict__ warp_off, const int *__restrict__ warp_len, \
-      const int *__restrict__ ref_of_slot, int pn, long long nwarps, double4 *__restrict__ q_out, Ctrl *ctrl
-#define FORCE_PASS q, p, fout, list, warp_off, warp_len, ref_of_slot, pn, nwarps, q_out, ctrl
+      const int *__restrict__ ref_of_slot, int pn, long long nwarps, double4 *__restrict__ q_out, Ctrl *ctrl,    \
+      unsigned *__restrict__ list_in, int *__restrict__ warp_len_in, int sentinel
+#define FORCE_PASS q, p, fout, list, warp_off, warp_len, ref_of_slot, pn, nwarps, q_out, ctrl, list_in, warp_len_in, sentinel
 
 // One force-warp: the kPW locals in slots [w kPW, (w+1) kPW), kG lanes each.
-template <int VARIANT, int MODE>
+template <int VARIANT, int MODE, bool PRUNE>
 __device__ __forceinline__ void force_warp(long long w, int lane, FORCE_PARAMS, const ForceConsts &fc) {
   const long long a = w * kPW + lane / kG;
   const bool act = a < pn;
   double ax, ay, az;
   ld_q256(q + (act ? a : (long long)pn - 1), ax, ay, az);
   const int len2 = warp_len[w] >> 1;
-  const uint2 *__restrict__ lp = reinterpret_cast<const uint2 *>(list + warp_off[w]) + lane;
+  const long long base = warp_off[w];
+  const uint2 *__restrict__ lp = reinterpret_cast<const uint2 *>(list + base) + lane;
   double fx = 0.0, fy = 0.0, fz = 0.0;
   const long long cl2b = __double_as_longlong(fc.CL2);
+  // PRUNE: which of this lane's entries stay (bit 2k: first entry of step-pair k, bit 2k+1: second) and how
+  // many per class (index mod 4), 4 x 8 bits
+  const long long keep2b = __double_as_longlong(fc.keep2);
+  unsigned long long keepmask = 0ull;
+  unsigned kcnt = 0u;
 
   constexpr int UNR = FORCE_UNROLL;
 #if FORCE_PF_CHUNK
@@ -185,14 +202,56 @@ __device__ __forceinline__ void force_warp(long long w, int lane, FORCE_PARAMS, 
     double j0x, j0y, j0z, j1x, j1y, j1z;
     ld_q256(q + e.x, j0x, j0y, j0z);
     ld_q256(q + e.y, j1x, j1y, j1z);
-    pair_accumulate<VARIANT>(ax, ay, az, j0x, j0y, j0z, cl2b, fc, fx, fy, fz);
-    pair_accumulate<VARIANT>(ax, ay, az, j1x, j1y, j1z, cl2b, fc, fx, fy, fz);
+    const long long r0 = pair_accumulate<VARIANT>(ax, ay, az, j0x, j0y, j0z, cl2b, fc, fx, fy, fz);
+    const long long r1 = pair_accumulate<VARIANT>(ax, ay, az, j1x, j1y, j1z, cl2b, fc, fx, fy, fz);
+    if (PRUNE) {
+      if (r0 <= keep2b) { keepmask |= 1ull << (2 * k); kcnt += 1u << (8 * (e.x & 3u)); }
+      if (r1 <= keep2b) { keepmask |= 2ull << (2 * k); kcnt += 1u << (8 * (e.y & 3u)); }
+    }
   }
 #pragma unroll
   for (int o = kG / 2; o > 0; o >>= 1) {
     fx += __shfl_xor_sync(0xffffffffu, fx, o);
     fy += __shfl_xor_sync(0xffffffffu, fy, o);
     fz += __shfl_xor_sync(0xffffffffu, fz, o);
+  }
+  if (PRUNE) {
+    // ---- deal the kept entries of each local out again in rainbow order (cells.cu) --------------------------
+    const int c = lane % kG;
+    unsigned incl = kcnt;  // inclusive scan of the packed class counts over the 4 lanes of the group
+    unsigned t = __shfl_up_sync(0xffffffffu, incl, 1, kG);
+    if (c >= 1) incl += t;
+    t = __shfl_up_sync(0xffffffffu, incl, 2, kG);
+    if (c >= 2) incl += t;
+    const unsigned tot = __shfl_sync(0xffffffffu, incl, kG - 1, kG);  // class totals of the local
+    unsigned run = incl - kcnt;                                        // first ordinals of this lane's entries
+    const int nk = (int)((tot & 0xFFu) + ((tot >> 8) & 0xFFu) + ((tot >> 16) & 0xFFu) + (tot >> 24));
+    int steps = (nk + kG - 1) / kG;
+#pragma unroll
+    for (int o = kG; o < 32; o <<= 1) steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, o));
+    steps = (steps + 1) & ~1;
+    if (lane == 0) warp_len_in[w] = steps;
+    const int m = rainbow_min(tot);
+    const int glane0 = lane - c;
+    for (int k = 0; k < len2; k++) {
+      if (((keepmask >> (2 * k)) & 3ull) == 0ull) continue;
+      const uint2 e = __ldg(lp + (long long)k * 32);  // the row was just read: L1 / L2 hit
+      if ((keepmask >> (2 * k)) & 1ull) {
+        const int cc = (int)(e.x & 3u);
+        const int tt = (int)((run >> (8 * cc)) & 0xFFu);
+        run += 1u << (8 * cc);
+        const int ee = rainbow_place(tot, m, cc, tt);
+        list_in[base + list_word(ee / kG, glane0 + ee % kG)] = e.x;
+      }
+      if ((keepmask >> (2 * k)) & 2ull) {
+        const int cc = (int)(e.y & 3u);
+        const int tt = (int)((run >> (8 * cc)) & 0xFFu);
+        run += 1u << (8 * cc);
+        const int ee = rainbow_place(tot, m, cc, tt);
+        list_in[base + list_word(ee / kG, glane0 + ee % kG)] = e.y;
+      }
+    }
+    for (int ee = nk + c; ee < steps * kG; ee += kG) list_in[base + list_word(ee / kG, glane0 + ee % kG)] = (unsigned)sentinel;
   }
   const bool writer = act && (lane % kG) == 0;
   if (MODE == FORCE_IMPULSE) {
@@ -228,7 +287,6 @@ __device__ __forceinline__ void force_warp(long long w, int lane, FORCE_PARAMS, 
   }
 }
 
-// Plain grid: one force-warp per warp.
 // worder (may be null): the launch covers force-warps worder[wbase .. wbase + wcount) -- the interior or
 // the boundary part of the unit (cells.cu:k_warp_order); null = force-warps [0, wcount).
 template <int VARIANT, int MODE>
@@ -237,82 +295,16 @@ k_force(FORCE_PARAMS, const int *__restrict__ worder, long long wbase, long long
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= wcount) return;
   const long long w = worder ? (long long)worder[wbase + i] : i;
-  force_warp<VARIANT, MODE>(w, threadIdx.x & 31, FORCE_PASS, fc);
+  force_warp<VARIANT, MODE, false>(w, threadIdx.x & 31, FORCE_PASS, fc);
 }
-
-// PERSISTENT grid with one work queue per SM (FORCE_PERSIST=1).  The force-warps are split into one
-// contiguous range per SM; every resident warp of SM s takes the next force-warp of range s (atomic ticket),
-// so at any moment the ~40 warps of an SM work on ~320 ADJACENT locals whose partners are the same few cell
-// rows and share L1 lines (a round-robin grid puts neighbouring blocks on different SMs).  A warp whose range
-// is exhausted steals from the following ranges, so the result does not depend on block placement.
-// queue[0..nsm) is this launch's tickets; queue_next[0..nsm) is zeroed for the next launch.
+// the same, deriving the inner list on the side (a few launches per rebuild interval)
 template <int VARIANT, int MODE>
-__global__ void __launch_bounds__(FORCE_TPB, FORCE_MINBLK)
-k_force_persist(FORCE_PARAMS, int nsm, const int *__restrict__ sm_rank, int *queue, int *queue_next,
-                ForceConsts fc) {
-  const int lane = threadIdx.x & 31;
-  if (blockIdx.x == 0)
-    for (int i = threadIdx.x; i < nsm; i += blockDim.x) queue_next[i] = 0;
-  unsigned smid;
-  asm("mov.u32 %0, %%smid;" : "=r"(smid));
-  const long long per = (nwarps + nsm - 1) / nsm;
-  int cur = sm_rank[smid & 1023];  // dense rank of this SM (hardware SM ids may have gaps)
-  int ticket = 0;
-  if (lane == 0) ticket = atomicAdd(&queue[cur], 1);
-  for (;;) {
-    const int t = __shfl_sync(0xffffffffu, ticket, 0);
-    const long long w = (long long)cur * per + t;
-    if (t >= per || w >= nwarps) {
-      // own range exhausted: look for a range that still has tickets, 32 queues per probe
-      int found = -1;
-      for (int off = 1; off < nsm && found < 0; off += 32) {
-        const int cand = (cur + off + lane) % nsm;
-        const bool has = (off + lane < nsm) && (*(volatile int *)&queue[cand] < per) &&
-                         ((long long)cand * per + *(volatile int *)&queue[cand] < nwarps);
-        const unsigned m = __ballot_sync(0xffffffffu, has);
-        if (m) found = (cur + off + (__ffs(m) - 1)) % nsm;
-      }
-      if (found < 0) break;
-      cur = found;
-      if (lane == 0) ticket = atomicAdd(&queue[cur], 1);
-      continue;
-    }
-    if (lane == 0) ticket = atomicAdd(&queue[cur], 1);  // next ticket, in flight while this one is processed
-    force_warp<VARIANT, MODE>(w, lane, FORCE_PASS, fc);
-  }
-}
-
-// Hardware SM ids (%smid) need not be dense: record which ids exist on this device and rank them.
-__global__ void k_probe_smid(int *seen) {
-  unsigned smid;
-  asm("mov.u32 %0, %%smid;" : "=r"(smid));
-  if (threadIdx.x == 0) seen[smid & 1023] = 1;
-  // stay resident for a moment so that the blocks of this probe spread over every SM
-  const long long t0 = clock64();
-  while (clock64() - t0 < 20000) {}
-}
-
-static int force_queue_init(Unit *u) {
-  int nsm = 0;
-  MDB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, u->device));
-  MDB_TRY(u->force_queue.ensure(2 * 1024));
-  MDB_TRY(u->sm_rank.ensure(1024));
-  MDB_CUDA(cudaMemsetAsync(u->force_queue.ptr, 0, sizeof(int) * 2 * 1024, u->stream));
-  MDB_CUDA(cudaMemsetAsync(u->sm_rank.ptr, 0, sizeof(int) * 1024, u->stream));
-  k_probe_smid<<<nsm * 16, 128, 0, u->stream>>>(u->sm_rank.ptr);
-  int seen[1024];
-  MDB_CUDA(cudaMemcpyAsync(seen, u->sm_rank.ptr, sizeof(seen), cudaMemcpyDeviceToHost, u->stream));
-  MDB_CUDA(cudaStreamSynchronize(u->stream));
-  int rank[1024], n = 0;
-  for (int i = 0; i < 1024; i++) rank[i] = seen[i] ? n++ : 0;
-  if (n == 0) { set_error("SM probe saw no SM"); return MDB200_ECUDA; }
-  for (int i = 0, k = 0; i < 1024; i++)
-    if (!seen[i]) rank[i] = (k++) % n;
-  MDB_CUDA(cudaMemcpyAsync(u->sm_rank.ptr, rank, sizeof(rank), cudaMemcpyHostToDevice, u->stream));
-  MDB_CUDA(cudaStreamSynchronize(u->stream));
-  u->nsm = n;
-  u->force_queue_parity = 0;
-  return MDB200_OK;
+__global__ void __launch_bounds__(FORCE_TPB, FORCE_PRUNE_MINBLK)
+k_force_prune(FORCE_PARAMS, const int *__restrict__ worder, long long wbase, long long wcount, ForceConsts fc) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= wcount) return;
+  const long long w = worder ? (long long)worder[wbase + i] : i;
+  force_warp<VARIANT, MODE, true>(w, threadIdx.x & 31, FORCE_PASS, fc);
 }
 
 static int force_variant() {
@@ -337,39 +329,32 @@ static ForceConsts make_fc(const Unit *u) {
   return fc;
 }
 
-#define FORCE_ARGS(F, QOUT) u->q.ptr, u->p.ptr, F, u->list.ptr, u->warp_off.ptr, u->warp_len.ptr, u->ref_of_slot.ptr, \
-                            (int)u->pn, u->nwarps, QOUT, u->ctrl
+#define FORCE_ARGS(F, QOUT, LIST, WLEN) u->q.ptr, u->p.ptr, F, LIST, u->warp_off.ptr, WLEN, u->ref_of_slot.ptr, \
+                                        (int)u->pn, u->nwarps, QOUT, u->ctrl, u->list_in.ptr, u->warp_len_in.ptr, sentinel_index(u)
 
 // part: 0 = every force-warp, 1 = interior warps only, 2 = boundary warps only
-static int force_launch(Unit *u, int mode, double *fout, int part = 0) {
+// inner: 0 = walk the outer list, 1 = walk the inner list, 2 = walk the outer list and derive the inner one
+static int force_launch(Unit *u, int mode, double *fout, int part = 0, int inner = 0, double keep_len = 0.0) {
   const int tpb = FORCE_TPB;
   const int *worder = part ? u->warp_order.ptr : nullptr;
   const long long wbase = (part == 2) ? u->n_interior : 0;
   const long long wcount = (part == 0) ? u->nwarps : (part == 1 ? u->n_interior : u->nwarps - u->n_interior);
   if (wcount <= 0) return MDB200_OK;
-  const long long want = (wcount * 32 + tpb - 1) / tpb;
+  const unsigned grid = (unsigned)((wcount * 32 + tpb - 1) / tpb);
   ForceConsts fc = make_fc(u);
-#if FORCE_PERSIST
-  if (part != 0) { set_error("FORCE_PERSIST build has no split launch"); return MDB200_EINVAL; }
-  if (!u->force_queue.ptr) MDB_TRY(force_queue_init(u));
-  const int nsm = u->nsm;
-  int *qcur = u->force_queue.ptr + 1024 * u->force_queue_parity;
-  int *qnext = u->force_queue.ptr + 1024 * (1 - u->force_queue_parity);
-  u->force_queue_parity ^= 1;
-  const long long resident = (long long)nsm * FORCE_MINBLK;
-  const unsigned grid = (unsigned)(want < resident ? want : resident);
-#define KLAUNCH(V, M, F, QOUT) \
-  k_force_persist<V, M><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(F, QOUT), nsm, u->sm_rank.ptr, qcur, qnext, fc)
-#else
-  (void)force_queue_init;
-  const unsigned grid = (unsigned)want;
-#define KLAUNCH(V, M, F, QOUT) k_force<V, M><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(F, QOUT), worder, wbase, wcount, fc)
-#endif
+  fc.keep2 = keep_len * keep_len;
+  const unsigned *lst = (inner == 1) ? u->list_in.ptr : u->list.ptr;
+  const int *wlen = (inner == 1) ? u->warp_len_in.ptr : u->warp_len.ptr;
+  if (inner == 2 && (mode == FORCE_IMPULSE || mode == FORCE_KICK)) { set_error("pruning launch needs a fused mode"); return MDB200_EINVAL; }
+#define KLAUNCH(V, M, F, QOUT) k_force<V, M><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(F, QOUT, lst, wlen), worder, wbase, wcount, fc)
+#define PLAUNCH(V, M) k_force_prune<V, M><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(nullptr, u->q_alt.ptr, lst, wlen), worder, wbase, wcount, fc)
 #define LAUNCH(V)                                                                  \
   do {                                                                             \
     if (mode == FORCE_IMPULSE) KLAUNCH(V, FORCE_IMPULSE, fout, nullptr);           \
     else if (mode == FORCE_KICK) KLAUNCH(V, FORCE_KICK, nullptr, nullptr);         \
+    else if (mode == FORCE_KICK_DRIFT && inner == 2) PLAUNCH(V, FORCE_KICK_DRIFT); \
     else if (mode == FORCE_KICK_DRIFT) KLAUNCH(V, FORCE_KICK_DRIFT, nullptr, u->q_alt.ptr); \
+    else if (inner == 2) PLAUNCH(V, FORCE_KICK_DRIFT2);                            \
     else KLAUNCH(V, FORCE_KICK_DRIFT2, nullptr, u->q_alt.ptr);                     \
   } while (0)
   switch (force_variant()) {
@@ -379,6 +364,7 @@ static int force_launch(Unit *u, int mode, double *fout, int part = 0) {
   }
 #undef LAUNCH
 #undef KLAUNCH
+#undef PLAUNCH
   u->launches++;
   MDB_CUDA(cudaGetLastError());
   return MDB200_OK;
@@ -393,11 +379,29 @@ int force_kick(Unit *u) {
 
 // CalculateForce + UpdatePositionHalf of MDManager::CalculateForce (mdmanager.cc:151-157) in one kernel;
 // predrift = also the first half drift of the next step (MODE 3; the caller sets u->predrifted).
+// inner: 0 = walk the outer list, 1 = walk the inner list, 2 = walk the outer list and derive the inner one
+// (entries within keep_len); the caller keeps u->inner_valid and the budget (api.cu).
 // part 0 = every force-warp; 1 = interior warps only (no ghost in any row: may run before the ghost
 // exchange has finished); 2 = boundary warps.  The buffers swap after part 0 or 2.
-int force_kick_drift(Unit *u, bool predrift, int part) {
+int force_kick_drift(Unit *u, bool predrift, int part, int inner, double keep_len) {
   if (u->pn == 0 || u->nwarps == 0) return MDB200_OK;
-  MDB_TRY(force_launch(u, predrift ? FORCE_KICK_DRIFT2 : FORCE_KICK_DRIFT, nullptr, part));
+  if (inner == 2) {
+    MDB_TRY(u->list_in.ensure(u->list.cap));  // same rows, same offsets
+    MDB_TRY(u->warp_len_in.ensure((size_t)u->nwarps + 2));
+  }
+  static const bool dbg = getenv("MDB200_DEBUG_FORCE") != nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (dbg) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, u->stream); }
+  MDB_TRY(force_launch(u, predrift ? FORCE_KICK_DRIFT2 : FORCE_KICK_DRIFT, nullptr, part, inner, keep_len));
+  if (dbg) {
+    cudaEventRecord(e1, u->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    fprintf(stderr, "[mdb200] force launch: part %d list %s keep %.4f  %.3f ms\n", part,
+            inner == 0 ? "outer" : (inner == 1 ? "inner" : "outer->inner"), keep_len, ms);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
   if (part != 1) {
     std::swap(u->q, u->q_alt);  // ghosts live in both buffers (exchange.cu)
     u->vmax_ready = true;

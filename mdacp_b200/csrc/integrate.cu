@@ -161,6 +161,7 @@ int langevin_kick(Unit *u) {
 // block to finish does the scalar bookkeeping.
 // scalar bookkeeping of PairList::UpdatePairListValidity (pairlist.cc:48-65) once max |p|^2 is known
 __device__ __forceinline__ void expiry_budget(Ctrl *ctrl, double dt, double BL) {
+  ctrl->last_vmax2_bits = atomicAdd(&ctrl->vmax2_bits, 0ull);
   double bl = ctrl->buffer_length;
   if (bl > 0.0) {
     double vmax = sqrt(bits_d(atomicAdd(&ctrl->vmax2_bits, 0ull)));
@@ -325,6 +326,8 @@ int expiry_check_launch(Unit *u) {
   MDB_CUDA(cudaGetLastError());
   MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->expired, &u->ctrl->expired, 2 * sizeof(int), cudaMemcpyDeviceToHost,
                            u->stream));  // expired + err (adjacent)
+  MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->last_vmax2_bits, &u->ctrl->last_vmax2_bits, sizeof(unsigned long long),
+                           cudaMemcpyDeviceToHost, u->stream));
   return MDB200_OK;
 }
 

@@ -98,6 +98,7 @@ struct Ctrl {
   double obs[4];                 // K,U,W scratch
   double zeta;                   // Variables::Zeta (variables.h:19)
   int scratch[8];
+  unsigned long long last_vmax2_bits;  // max |p|^2 the last expiry test saw (host: inner-list budget)
 };
 
 struct Unit {
@@ -164,10 +165,13 @@ struct Unit {
   // interior force run while the ghost exchange is still in flight (api.cu, multi-process runs)
   DevBuf<int> warp_flag, warp_order;   // order: interior warps first, then boundary warps
   long long n_interior = 0;
-  DevBuf<int> force_queue;        // per-SM work tickets of the persistent force kernel (2 x 1024, ping-pong)
-  int force_queue_parity = 0;
-  DevBuf<int> sm_rank;            // dense rank of each hardware SM id
-  int nsm = 0;                    // SMs seen on the device
+  // INNER list (force.cu, PRUNE): the entries of `list` that were within cutoff + inner_delta when it was last
+  // derived, same row offsets (warp_off), own step counts.  The fused NVE step walks it instead of `list`
+  // until the velocity budget inner_budget (host side, global max |p|) is used up; see api.cu.
+  DevBuf<unsigned> list_in;
+  DevBuf<int> warp_len_in;
+  bool inner_valid = false;
+  double inner_left = -1.0, inner_delta = 0.0;  // budget of the unit GROUP, kept in its first unit (api.cu)
   long long list_entries = 0;     // padded entries
   long long npairs = 0;           // reference-style count of listed pairs (meshlist.cc:309)
   int max_row = 0;
@@ -211,6 +215,25 @@ constexpr int kPW = 32 / kG;  // locals per force-warp
 // list word of (step k, lane l) relative to the warp's first word
 __host__ __device__ inline long long list_word(int k, int lane) { return 64LL * (k >> 1) + 2 * lane + (k & 1); }
 
+#ifdef __CUDACC__
+// "Rainbow" row order (cells.cu): tot = partners per class (index mod 4), 4 x 8 bits; m = smallest class count.
+// Entry index (step * 4 + lane-in-group) of the t-th partner of class c: steps < m hold one partner of every
+// class, what is left over is dealt out in (ordinal, class) order.
+__device__ __forceinline__ int rainbow_min(unsigned tot) {
+  return (int)min(min(tot & 0xFFu, (tot >> 8) & 0xFFu), min((tot >> 16) & 0xFFu, (tot >> 24) & 0xFFu));
+}
+__device__ __forceinline__ int rainbow_place(unsigned tot, int m, int c, int t) {
+  if (t < m) return 4 * t + c;
+  int r = 0;
+#pragma unroll
+  for (int cc = 0; cc < 4; cc++) {
+    const int left = (int)((tot >> (8 * cc)) & 0xFFu) - m;
+    r += min(left, (t - m) + (cc < c ? 1 : 0));
+  }
+  return 4 * m + r;
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // kernels / phases (host launchers; all asynchronous on u->stream unless stated)
 // ---------------------------------------------------------------------------------------------
@@ -247,7 +270,7 @@ int expiry_check_local(Unit *u, int *expired);                           // sync
 
 // force.cu
 int force_kick(Unit *u);
-int force_kick_drift(Unit *u, bool predrift, int part);                  // fused kick + drift(s); swaps q / q_alt                                           // kick + second half drift, swaps q / q_alt
+int force_kick_drift(Unit *u, bool predrift, int part, int inner, double keep_len);  // inner: 0 outer list, 1 walk the inner list, 2 walk the outer list and derive the inner one (pairs within keep_len)                  // fused kick + drift(s); swaps q / q_alt                                           // kick + second half drift, swaps q / q_alt
 int force_impulse(Unit *u, double *f3_host, long long cap_rows);         // sync
 
 // observe.cu
