@@ -32,3 +32,12 @@ def test_plain_path_without_predrift(monkeypatch):
     monkeypatch.setenv("MDB200_NO_PREDRIFT", "1")
     rec, cfg, steps, init_build = load_golden("bench1")
     check_cuda_against_records(rec, steps, init_build, None, observe_every=25)
+
+
+# The fused NVE launch normally walks the INNER list (entries within cutoff + delta, re-derived every ~16 steps,
+# force.cu PRUNE); MDB200_NO_PRUNE keeps it on the full list.  Both must meet the same parity.
+@pytest.mark.parametrize("name", ["bench1", "bench8"])
+def test_outer_list_only_matches_reference_golden(name, monkeypatch):
+    monkeypatch.setenv("MDB200_NO_PRUNE", "1")
+    rec, cfg, steps, init_build = load_golden(name)
+    check_cuda_against_records(rec, steps, init_build, None, observe_every=25)
