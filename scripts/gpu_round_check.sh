@@ -5,7 +5,7 @@ timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&
 tail -5 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 600 gpurun_out/bench_n1.err
 cat gpurun_out/bench_n1.json | cut -c1-1500
-MDB200_NO_PRUNE=1 timeout 600 python bench.py > gpurun_out/bench_n1_noprune.json 2> gpurun_out/bench_n1_noprune.err
+MDB200_NO_PRUNE=1 timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_n1_noprune.json 2> gpurun_out/bench_n1_noprune.err
 cut -c1-200 gpurun_out/bench_n1_noprune.json
 MDB200_DEBUG_FORCE=1 timeout 300 python scripts/perf_probe.py 200 > gpurun_out/probe200.log 2>&1
 grep -v "force launch" gpurun_out/probe200.log | tail -8
