@@ -408,12 +408,16 @@ static int calculate(Unit **us, int n) {
   if (expired) MDB_TRY(make_pairlist(us, n));
   // which list the fused NVE launch walks: the inner one while its budget lasts and every unit has one,
   // otherwise the outer one -- deriving a fresh inner list on the side when pruning is worthwhile
-  bool all_inner = true;
-  for (int i = 0; i < n; i++) all_inner = all_inner && us[i]->inner_valid;
+  bool all_inner = true, can_prune = true;
+  for (int i = 0; i < n; i++) {
+    all_inner = all_inner && us[i]->inner_valid;
+    // the deriving launch keeps a 64-bit keep mask per lane: 2 bits per step pair, i.e. rows of <= 256 entries
+    can_prune = can_prune && us[i]->max_row <= 248;
+  }
   int inner = 0;
   double keep_len = 0.0;
   if (!ct && all_inner && us[0]->inner_left >= 0.0) inner = 1;
-  else if (!ct && us[0]->inner_delta > 0.0) { inner = 2; keep_len = us[0]->prm.cutoff + us[0]->inner_delta; }
+  else if (!ct && can_prune && us[0]->inner_delta > 0.0) { inner = 2; keep_len = us[0]->prm.cutoff + us[0]->inner_delta; }
   if (inner == 2) us[0]->inner_left = us[0]->inner_delta;
   for (int i = 0; i < n; i++) us[i]->inner_valid = (inner != 0);
   for (int i = 0; i < n; i++) {
@@ -786,6 +790,7 @@ int mdb200_calculate_force(mdb200_unit *h) {
   if (!h->u.list_initialized) { set_error("pair list not built"); return MDB200_EINVAL; }
   DeviceGuard g(h->u.device);
   MDB_TRY(materialize(&h->u));
+  h->u.inner_valid = false;  // momenta change outside the budgeted step
   return force_kick(&h->u);
 }
 
@@ -800,12 +805,14 @@ int mdb200_heatbath_momenta(mdb200_unit *h) {
   if (!h) return MDB200_EINVAL;
   DeviceGuard g(h->u.device);
   MDB_TRY(materialize(&h->u));
+  h->u.inner_valid = false;
   return heatbath_momenta(&h->u);
 }
 int mdb200_langevin(mdb200_unit *h) {
   if (!h) return MDB200_EINVAL;
   DeviceGuard g(h->u.device);
   MDB_TRY(materialize(&h->u));
+  h->u.inner_valid = false;
   return langevin_kick(&h->u);
 }
 int mdb200_set_seed(mdb200_unit *h, int seed) {
