@@ -98,6 +98,17 @@ int mdb200_download(mdb200_unit *u, double (*q)[4], double (*p)[4], int *type, l
                     long long *pn, long long *tn);
 int mdb200_get_counts(mdb200_unit *u, long long *pn, long long *tn, long long *npairs,
                       long long *nbuilds);
+/* Dump path.  The reference's writers -- MDUnit::SaveAsCdview (mdunit.cc:52-67), FileDumper
+ * (mdmanager.cc:475-505), Variables::SaveToStream (variables.cc:111-118) -- read q, p, type of the
+ * locals from the host Variables in index order.  mdb200_snapshot_begin queues a copy of exactly
+ * those arrays (reference index order, end-of-step positions) to library-owned pinned host memory on
+ * a second stream and returns at once; steps issued afterwards overlap the transfer and do not
+ * change what was captured.  mdb200_snapshot_wait blocks until the copy has landed and hands out
+ * read-only views (rows of 4 doubles / ints, pn rows) that stay valid until the next
+ * mdb200_snapshot_begin or mdb200_destroy on the unit. */
+int mdb200_snapshot_begin(mdb200_unit *u);
+int mdb200_snapshot_wait(mdb200_unit *u, const double (**q)[4], const double (**p)[4],
+                         const int **type, long long *pn);
 
 /* Join the units of this process (and, if nranks > 1, of the other processes through NCCL)
  * into one simulation.  Replaces MPI_Init + ParaInfo wiring (mdmanager.cc:11-47).

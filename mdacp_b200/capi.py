@@ -25,6 +25,7 @@ SYMBOLS = [
     "mdb200_set_zeta", "mdb200_set_control_temperature", "mdb200_set_aimed_temperature", "mdb200_observe",
     "mdb200_observe_unit", "mdb200_get_pairs", "mdb200_get_impulse", "mdb200_timers", "mdb200_set_profiling",
     "mdb200_synchronize", "mdb200_event_record", "mdb200_event_elapsed_ms", "mdb200_list_stats",
+    "mdb200_snapshot_begin", "mdb200_snapshot_wait",
 ]
 
 
@@ -89,6 +90,8 @@ def lib():
         L.mdb200_event_record.argtypes = [vp, C.c_int]
         L.mdb200_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, dp]
         L.mdb200_list_stats.argtypes = [vp, dp]
+        L.mdb200_snapshot_begin.argtypes = [vp]
+        L.mdb200_snapshot_wait.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), llp]
         _lib = L
     return _lib
 
@@ -171,6 +174,23 @@ class Unit:
         check(lib().mdb200_download(self.handle, _ptr(q), _ptr(p), _ptr(t), rows, C.byref(a), C.byref(b)))
         return {"pn": pn, "tn": tn, "q": None if q is None else q[:tn, :3], "p": None if p is None else p[:pn, :3],
                 "type": None if t is None else t[:pn]}
+
+    def snapshot_begin(self):
+        """Queue an asynchronous copy of q, p, type (locals, reference order) to pinned host memory."""
+        check(lib().mdb200_snapshot_begin(self.handle))
+
+    def snapshot_wait(self):
+        """-> {"pn", "q4", "p4", "type"}: read-only views of the library's pinned buffers (rows of 4 doubles),
+        valid until the next snapshot_begin / close on this unit."""
+        q, p, t, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_longlong()
+        check(lib().mdb200_snapshot_wait(self.handle, C.byref(q), C.byref(p), C.byref(t), C.byref(n)))
+        pn = n.value
+        if pn == 0:
+            return {"pn": 0, "q4": np.zeros((0, 4)), "p4": np.zeros((0, 4)), "type": np.zeros(0, dtype=np.int32)}
+        q4 = np.ctypeslib.as_array(C.cast(q, C.POINTER(C.c_double)), shape=(pn, 4))
+        p4 = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(pn, 4))
+        ty = np.ctypeslib.as_array(C.cast(t, C.POINTER(C.c_int)), shape=(pn,))
+        return {"pn": pn, "q4": q4, "p4": p4, "type": ty}
 
     def pairs(self):
         n = C.c_longlong()

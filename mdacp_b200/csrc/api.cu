@@ -615,6 +615,12 @@ int mdb200_destroy(mdb200_unit *h) {
   if (u->cstream) { cudaStreamDestroy(u->cstream); cudaEventDestroy(u->ev_drift); cudaEventDestroy(u->ev_ghost); }
   u->warp_len.release(); u->warp_off.release(); u->list.release();
   u->disp.release(); u->cand.release(); u->partial.release();
+  u->snap_q.release(); u->snap_p.release(); u->snap_t.release();
+  if (u->snap_stream) {
+    cudaStreamSynchronize(u->snap_stream);
+    cudaStreamDestroy(u->snap_stream); cudaEventDestroy(u->snap_ready); cudaEventDestroy(u->snap_done);
+  }
+  if (u->snap_hq) { cudaFreeHost(u->snap_hq); cudaFreeHost(u->snap_hp); cudaFreeHost(u->snap_ht); }
   if (u->ctrl) cudaFree(u->ctrl);
   if (u->ctrl_host) cudaFreeHost(u->ctrl_host);
   if (u->own_stream) cudaStreamDestroy(u->stream);
@@ -710,6 +716,72 @@ int mdb200_download(mdb200_unit *h, double (*q)[4], double (*p)[4], int *type, l
   }
   MDB_CUDA(cudaGetLastError());
   MDB_CUDA(cudaStreamSynchronize(u->stream));
+  return MDB200_OK;
+}
+
+// Dump path (MDUnit::SaveAsCdview mdunit.cc:52-67, FileDumper mdmanager.cc:475-505 read Variables::q/p/type of
+// the locals): the reference-ordered copy is gathered on the unit's stream into staging buffers nothing else
+// uses, and travels to pinned host memory on a second stream, so the following steps overlap the transfer.
+int mdb200_snapshot_begin(mdb200_unit *h) {
+  if (!h) return MDB200_EINVAL;
+  Unit *u = &h->u;
+  DeviceGuard g(u->device);
+  if (u->snap_pending) {  // a snapshot nobody waited for: finish it before its buffers are reused
+    MDB_CUDA(cudaEventSynchronize(u->snap_done));
+    u->snap_pending = false;
+  }
+  MDB_TRY(materialize(u));
+  if (!u->snap_stream) {
+    MDB_CUDA(cudaStreamCreateWithFlags(&u->snap_stream, cudaStreamNonBlocking));
+    MDB_CUDA(cudaEventCreateWithFlags(&u->snap_ready, cudaEventDisableTiming));
+    MDB_CUDA(cudaEventCreateWithFlags(&u->snap_done, cudaEventDisableTiming));
+  }
+  const long long pn = u->pn;
+  u->snap_pn = pn;
+  if (pn > u->snap_hcap) {
+    if (u->snap_hq) { cudaFreeHost(u->snap_hq); cudaFreeHost(u->snap_hp); cudaFreeHost(u->snap_ht); }
+    u->snap_hq = u->snap_hp = nullptr;
+    u->snap_ht = nullptr;
+    u->snap_hcap = 0;
+    const long long cap = pn + pn / 16 + 64;
+    MDB_CUDA(cudaMallocHost(&u->snap_hq, sizeof(double4) * (size_t)cap));
+    MDB_CUDA(cudaMallocHost(&u->snap_hp, sizeof(double4) * (size_t)cap));
+    MDB_CUDA(cudaMallocHost(&u->snap_ht, sizeof(int) * (size_t)cap));
+    u->snap_hcap = cap;
+  }
+  if (pn > 0) {
+    MDB_TRY(u->snap_q.ensure((size_t)pn));
+    MDB_TRY(u->snap_p.ensure((size_t)pn));
+    MDB_TRY(u->snap_t.ensure((size_t)pn));
+    const unsigned nb = (unsigned)((pn + 255) / 256);
+    k_gather_ref_order<<<nb, 256, 0, u->stream>>>(u->q.ptr, u->slot_of_ref.ptr, u->snap_q.ptr, (int)pn, (int)pn);
+    k_gather_ref_order<<<nb, 256, 0, u->stream>>>(u->p.ptr, u->slot_of_ref.ptr, u->snap_p.ptr, (int)pn, (int)pn);
+    k_gather_ref_order_i<<<nb, 256, 0, u->stream>>>(u->type.ptr, u->slot_of_ref.ptr, u->snap_t.ptr, (int)pn);
+    u->launches += 3;
+    MDB_CUDA(cudaGetLastError());
+    MDB_CUDA(cudaEventRecord(u->snap_ready, u->stream));
+    MDB_CUDA(cudaStreamWaitEvent(u->snap_stream, u->snap_ready, 0));
+    MDB_CUDA(cudaMemcpyAsync(u->snap_hq, u->snap_q.ptr, sizeof(double4) * (size_t)pn, cudaMemcpyDeviceToHost, u->snap_stream));
+    MDB_CUDA(cudaMemcpyAsync(u->snap_hp, u->snap_p.ptr, sizeof(double4) * (size_t)pn, cudaMemcpyDeviceToHost, u->snap_stream));
+    MDB_CUDA(cudaMemcpyAsync(u->snap_ht, u->snap_t.ptr, sizeof(int) * (size_t)pn, cudaMemcpyDeviceToHost, u->snap_stream));
+  }
+  MDB_CUDA(cudaEventRecord(u->snap_done, u->snap_stream));
+  u->snap_pending = true;
+  return MDB200_OK;
+}
+
+int mdb200_snapshot_wait(mdb200_unit *h, const double (**q)[4], const double (**p)[4], const int **type,
+                         long long *pn) {
+  if (!h) return MDB200_EINVAL;
+  Unit *u = &h->u;
+  if (!u->snap_done) { set_error("no snapshot was begun"); return MDB200_EINVAL; }
+  DeviceGuard g(u->device);
+  MDB_CUDA(cudaEventSynchronize(u->snap_done));
+  u->snap_pending = false;
+  if (q) *q = reinterpret_cast<const double (*)[4]>(u->snap_hq);
+  if (p) *p = reinterpret_cast<const double (*)[4]>(u->snap_hp);
+  if (type) *type = u->snap_ht;
+  if (pn) *pn = u->snap_pn;
   return MDB200_OK;
 }
 

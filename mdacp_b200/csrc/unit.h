@@ -193,6 +193,18 @@ struct Unit {
   cudaStream_t cstream = 0;       // second stream for the overlapped ghost exchange (created on demand)
   cudaEvent_t ev_drift = 0, ev_ghost = 0;
 
+  // asynchronous snapshot for the dump path (api.cu: mdb200_snapshot_begin / _wait): reference-ordered copies
+  // of q, p, type staged on the device, then copied to pinned host memory on a second stream while the step
+  // loop goes on
+  DevBuf<double4> snap_q, snap_p;
+  DevBuf<int> snap_t;
+  double4 *snap_hq = nullptr, *snap_hp = nullptr;   // pinned host
+  int *snap_ht = nullptr;
+  long long snap_hcap = 0, snap_pn = 0;
+  cudaStream_t snap_stream = 0;
+  cudaEvent_t snap_ready = 0, snap_done = 0;
+  bool snap_pending = false;
+
   // profiling
   int profiling = 0;               // 0 off, 1 force kernel only (no extra syncs), 2 every phase
   double t_ms[6] = {0, 0, 0, 0, 0, 0};

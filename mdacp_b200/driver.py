@@ -238,7 +238,7 @@ class MDManager:
     """
 
     def __init__(self, cfg, num_procs=1, rank=0, num_threads=1, devices=None, unique_id=None,
-                 cutoff=CUTOFF_LENGTH, pn_capacity=0, tn_capacity=0):
+                 cutoff=CUTOFF_LENGTH, pn_capacity=0, tn_capacity=0, barrier=None):
         self.param = cfg if isinstance(cfg, Parameter) else (
             Parameter.from_dict(cfg) if isinstance(cfg, dict) else Parameter(cfg))
         self.num_procs, self.rank, self.num_threads = num_procs, rank, num_threads
@@ -257,6 +257,10 @@ class MDManager:
             self.units.append(capi.Unit(P, devices[t % len(devices)]))
         self.group = capi.Group(self.units, num_procs, rank, unique_id)
         self.s_time = 0.0
+        self.barrier = barrier            # callable; Communicator::Barrier for the rank-serialised writers
+        self._cdview_index = 0            # static index of SaveAsCdviewSequential (mdmanager.cc:82)
+        self._dump_index = 0              # static index of SaveAsDumpFileSequential (mdmanager.cc:467)
+        self._snapshot_open = False
 
     # --- set-up -------------------------------------------------------------------------
     def GetTotalThreads(self):
@@ -343,6 +347,70 @@ class MDManager:
 
     def observables(self):
         return observables_from_raw(self.observe_raw(), self.sinfo.L)
+
+    # --- dump path (mdmanager.cc:80-113, 465-505) --------------------------------------------
+    def BeginSnapshot(self):
+        """Queue the device -> pinned-host copy of every unit's locals (reference order); the step loop
+        may go on, the Save* calls below pick the snapshot up (capi.Unit.snapshot_begin)."""
+        for u in self.units:
+            u.snapshot_begin()
+        self._snapshot_open = True
+
+    def _snapshots(self):
+        if not self._snapshot_open:
+            self.BeginSnapshot()
+        self._snapshot_open = False
+        return [u.snapshot_wait() for u in self.units]
+
+    def _serial_append(self, filename, write_unit):
+        """Rank 0 truncates, then the ranks append one after the other (mdmanager.cc:90-105 / ExecuteAllSerial
+        :454-463), each its units in order: the file is byte-identical to the reference's."""
+        from . import hostlib  # noqa: F401
+        snaps = self._snapshots()
+        if self.rank == 0:
+            open(filename, "w").close()
+        for r in range(self.num_procs):
+            if self.barrier is not None:
+                self.barrier()
+            if r == self.rank:
+                for sn in snaps:
+                    write_unit(filename, sn)
+        if self.barrier is not None:
+            self.barrier()
+
+    def SaveAsCdview(self, filename):
+        from . import hostlib
+        self._serial_append(filename, lambda fn, sn: hostlib.save_cdview(fn, sn["q4"], sn["p4"], sn["type"], append=True))
+
+    def SaveAsCdviewSequential(self):
+        filename = "conf%04d.cd" % self._cdview_index
+        self._cdview_index += 1
+        self.SaveAsCdview(filename)
+        return filename
+
+    def SaveAsDumpFile(self, filename):
+        from . import hostlib
+        self._serial_append(filename, lambda fn, sn: hostlib.save_dump(fn, sn["q4"], sn["p4"], append=True))
+
+    def SaveAsDumpFileSequential(self):
+        filename = "conf%04d.dump" % self._dump_index
+        self._dump_index += 1
+        self.SaveAsDumpFile(filename)
+        return filename
+
+    def SaveConfiguration(self):
+        """MDUnit::SaveConfiguration (mdunit.cc:69-75): conf%03d.cnf per unit, locals and ghosts; ghost momenta
+        (scratch in the reference) are written as zeros."""
+        from . import hostlib
+        names = []
+        for i, u in enumerate(self.units):
+            d = u.download()
+            p4 = np.zeros((d["tn"], 4))
+            p4[:d["pn"], :3] = d["p"]
+            name = "conf%03d.cnf" % (i + self.rank * self.num_threads)
+            hostlib.save_configuration(name, d["q"], p4)
+            names.append(name)
+        return names
 
     def close(self):
         for u in self.units:

@@ -8,12 +8,22 @@
 //   mdh_lattice_config     ConfigurationMaker::Execute          confmaker.cc:9-44
 //   mdh_collision_config   BallAdder (x2) in Collision::Run     collision.cc:8-61
 //   mdh_initial_velocity   Variables::SetInitialVelocity        variables.cc:82-108
+//   mdh_droplet_config     DropletMaker::Execute                burst.cc:10-64
+// and the file writers fed by mdb200_download / mdb200_snapshot_wait (byte-identical output: the
+// same iostream formatting, chunks formatted by several threads and written in order):
+//   mdh_save_cdview        MDUnit::SaveAsCdview                 mdunit.cc:52-67 (file handling mdmanager.cc:90-105)
+//   mdh_save_dump          FileDumper::Execute                  mdmanager.cc:475-505
+//   mdh_save_configuration Variables::SaveConfiguration         variables.cc:45-57
 //
 // All write rows of 4 doubles (the reference's `double q[N][4]`), lane 3 = 0, and return the
 // number of particles written, or -1 if `cap` rows are not enough.
 #include <math.h>
 #include <algorithm>
+#include <fstream>
 #include <random>
+#include <sstream>
+#include <string>
+#include <thread>
 #include <unordered_set>
 #include <vector>
 
@@ -37,6 +47,34 @@ struct Sink {
     n++;
   }
 };
+
+// Formats rows [0, n) with `row(os, i)` on several threads (one ostringstream per chunk, default iostream
+// state = what a fresh std::ofstream has) and writes the chunks in order.
+template <typename RowFn>
+int write_rows_text(const char *filename, bool append, long n, RowFn row) {
+  std::ofstream ofs(filename, append ? (std::ios::out | std::ios::app) : std::ios::out);
+  if (!ofs) return -1;
+  const long chunk = 1L << 16;
+  const long nchunks = (n + chunk - 1) / chunk;
+  unsigned hw = std::thread::hardware_concurrency();
+  const long nthreads = std::max<long>(1, std::min<long>(hw ? hw : 1, std::min<long>(nchunks, 32)));
+  for (long c0 = 0; c0 < nchunks; c0 += nthreads) {
+    const long nb = std::min<long>(nthreads, nchunks - c0);
+    std::vector<std::string> out((size_t)nb);
+    std::vector<std::thread> th;
+    for (long t = 0; t < nb; t++)
+      th.emplace_back([&, t]() {
+        std::ostringstream os;
+        const long b = (c0 + t) * chunk, e = std::min<long>(n, b + chunk);
+        for (long i = b; i < e; i++) row(os, i);
+        out[(size_t)t] = os.str();
+      });
+    for (auto &x : th) x.join();
+    for (long t = 0; t < nb; t++) ofs.write(out[(size_t)t].data(), (std::streamsize)out[(size_t)t].size());
+  }
+  ofs.close();
+  return ofs ? 0 : -1;
+}
 
 }  // namespace
 
@@ -178,6 +216,96 @@ void mdh_initial_velocity(double *p4, long n, double V0, int seed) {
     p4[4 * i + 1] -= avy;
     p4[4 * i + 2] -= avz;
   }
+}
+
+// DropletMaker::Execute (burst.cc:30-64) with AddSub (burst.cc:17-29): global FCC lattice, sites inside the
+// sphere of `radius` around the box centre (c = L[X]/2 on all three axes, as the reference has it).
+long mdh_droplet_config(const double L[3], double density, double radius, const double s[3], const double e[3],
+                        double *q4, long cap) {
+  const double sp = 1.0 / pow(density * 0.25, 1.0 / 3.0);
+  const double hs = sp * 0.5;
+  const int sx = static_cast<int>(L[0] / sp);
+  const int sy = static_cast<int>(L[1] / sp);
+  const int sz = static_cast<int>(L[2] / sp);
+  const double eps = 0.0000001;
+  const double c = L[0] * 0.5;
+  Sink sink{q4, nullptr, cap, 0, s, e, false};
+  auto add = [&](const double x[3]) {
+    const double dx = x[0] - c, dy = x[1] - c, dz = x[2] - c;
+    const double r2 = dx * dx + dy * dy + dz * dz;
+    if (r2 < radius * radius) sink.add(x, nullptr);
+  };
+  double x[3];
+  for (int iz = 0; iz < sz; iz++)
+    for (int iy = 0; iy < sy; iy++)
+      for (int ix = 0; ix < sx; ix++) {
+        x[0] = static_cast<double>(ix) * sp + eps;
+        x[1] = static_cast<double>(iy) * sp + eps;
+        x[2] = static_cast<double>(iz) * sp + eps;
+        add(x);
+        x[0] = static_cast<double>(ix) * sp + eps;
+        x[1] = static_cast<double>(iy) * sp + hs + eps;
+        x[2] = static_cast<double>(iz) * sp + hs + eps;
+        add(x);
+        x[0] = static_cast<double>(ix) * sp + hs + eps;
+        x[1] = static_cast<double>(iy) * sp + eps;
+        x[2] = static_cast<double>(iz) * sp + hs + eps;
+        add(x);
+        x[0] = static_cast<double>(ix) * sp + hs + eps;
+        x[1] = static_cast<double>(iy) * sp + hs + eps;
+        x[2] = static_cast<double>(iz) * sp + eps;
+        add(x);
+      }
+  return sink.overflow ? -1 : sink.n;
+}
+
+// MDUnit::SaveAsCdview (mdunit.cc:52-67): "0 type qx qy qz px py pz\n" per local particle.  append = 0 truncates
+// first, as rank 0 does in MDManager::SaveAsCdview (mdmanager.cc:90-94); the units are then appended in order.
+int mdh_save_cdview(const char *filename, int append, const double *q4, const double *p4, const int *type, long pn) {
+  return write_rows_text(filename, append != 0, pn, [=](std::ostream &os, long i) {
+    os << "0 ";
+    os << (type ? type[i] : 0) << " ";
+    os << q4[4 * i + 0] << " ";
+    os << q4[4 * i + 1] << " ";
+    os << q4[4 * i + 2] << " ";
+    os << p4[4 * i + 0] << " ";
+    os << p4[4 * i + 1] << " ";
+    os << p4[4 * i + 2] << "\n";
+  });
+}
+
+// Variables::SaveConfiguration (variables.cc:45-57): "qx qy qz px py pz\n" for rows [0, tn) -- the reference
+// writes the ghosts too (their momenta are scratch there; the caller passes whatever it wants written).
+int mdh_save_configuration(const char *filename, const double *q4, const double *p4, long tn) {
+  return write_rows_text(filename, false, tn, [=](std::ostream &os, long i) {
+    os << q4[4 * i + 0];
+    os << " " << q4[4 * i + 1];
+    os << " " << q4[4 * i + 2];
+    os << " " << p4[4 * i + 0];
+    os << " " << p4[4 * i + 1];
+    os << " " << p4[4 * i + 2];
+    os << "\n";
+  });
+}
+
+// FileDumper::Execute (mdmanager.cc:487-500): qx qy qz px py pz as raw doubles per local particle.
+int mdh_save_dump(const char *filename, int append, const double *q4, const double *p4, long pn) {
+  std::ofstream ofs(filename, append ? (std::ios::out | std::ios::binary | std::ios::app) : (std::ios::out | std::ios::binary));
+  if (!ofs) return -1;
+  std::vector<double> buf;
+  const long chunk = 1L << 16;
+  for (long b = 0; b < pn; b += chunk) {
+    const long e = std::min(pn, b + chunk);
+    buf.resize((size_t)(e - b) * 6);
+    for (long i = b; i < e; i++) {
+      double *o = &buf[(size_t)(i - b) * 6];
+      o[0] = q4[4 * i + 0]; o[1] = q4[4 * i + 1]; o[2] = q4[4 * i + 2];
+      o[3] = p4[4 * i + 0]; o[4] = p4[4 * i + 1]; o[5] = p4[4 * i + 2];
+    }
+    ofs.write((const char *)buf.data(), (std::streamsize)(buf.size() * sizeof(double)));
+  }
+  ofs.close();
+  return ofs ? 0 : -1;
 }
 
 }  // extern "C"

@@ -2,9 +2,10 @@
 //
 // Mirrors the reference's driver surface for the hot path -- main.cc:8-17, MDManager
 // (mdmanager.cc:11-47, 116-148, 262-280, 380-429), ParaInfo (parainfo.cc:18-150, 191-275, one
-// process), SimulationInfo (simulationinfo.cc:5-51), Parameter (parameter.cc:35-111) and the three
-// project loops Benchmark / Langevin / Collision (benchmark.cc:13-52, langevin.cc:11-32,
-// collision.cc:54-80) -- with the same cfg keys and the same printed lines, so a user of the
+// process), SimulationInfo (simulationinfo.cc:5-51), Parameter (parameter.cc:35-111) and the four
+// project loops Benchmark / Langevin / Collision / Burst (benchmark.cc:13-52, langevin.cc:11-32,
+// collision.cc:54-80, burst.cc:104-143), cdview output included (mdmanager.cc:80-105 through the
+// asynchronous snapshot of the C-ABI) -- with the same cfg keys and the same printed lines, so a user of the
 // reference can run `mdacp_b200 input.cfg` and read the output they are used to.
 // Units: MDB200_UNITS (default 1) units in this process, round-robin over the visible GPUs --
 // the role OMP_NUM_THREADS plays in the reference.  All numerics happen in libmdacp_b200.so.
@@ -26,6 +27,9 @@ long mdh_benchmark_config(const double s[3], const double e[3], double density, 
 long mdh_lattice_config(const double L[3], double density, const double s[3], const double e[3], double *q4, long cap);
 long mdh_collision_config(const double L[3], const double s[3], const double e[3], double *q4, double *p4, long cap);
 void mdh_initial_velocity(double *p4, long n, double V0, int seed);
+long mdh_droplet_config(const double L[3], double density, double radius, const double s[3], const double e[3],
+                        double *q4, long cap);
+int mdh_save_cdview(const char *filename, int append, const double *q4, const double *p4, const int *type, long pn);
 }
 
 static const double CUTOFF_LENGTH = 3.0;  // mdconfig.h:15
@@ -165,6 +169,25 @@ struct MDManager {
     ControlTemperature = b;
     for (auto *d : devs) check(mdb200_set_control_temperature(d, b ? 1 : 0));
   }
+  // MDManager::SaveAsCdviewSequential / SaveAsCdview (mdmanager.cc:80-105): the snapshot of every unit is queued
+  // first (device -> pinned host, asynchronous), then the units are appended in order
+  int cdview_index = 0;
+  void SaveAsCdviewSequential(void) {
+    char filename[256];
+    snprintf(filename, sizeof(filename), "conf%04d.cd", cdview_index++);
+    for (auto *d : devs) check(mdb200_snapshot_begin(d));
+    { std::ofstream ofs(filename); }
+    for (auto *d : devs) {
+      const double(*sq)[4] = NULL, (*sp)[4] = NULL;
+      const int *st = NULL;
+      long long n = 0;
+      check(mdb200_snapshot_wait(d, &sq, &sp, &st, &n));
+      if (mdh_save_cdview(filename, 1, (const double *)sq, (const double *)sp, st, (long)n) != 0) {
+        std::cout << "# Error: cannot write " << filename << std::endl;
+        exit(1);
+      }
+    }
+  }
   void MakePairList(void) { check(mdb200_make_pairlist(devs.data(), num_units)); }
   void Calculate(void) { check(mdb200_step(devs.data(), num_units, 1)); s_time += TimeStep; }
   void Observe(double o[4]) { check(mdb200_observe(devs.data(), num_units, o)); }
@@ -209,6 +232,9 @@ static void generate(MDManager &m, const std::string &mode) {
       n = mdh_benchmark_config(s, e, m.param.GetDoubleDef("Density", 0.7), id, m.q[id].data(), cap);
     } else if (mode == "Langevin") {
       n = mdh_lattice_config(m.L, m.param.GetDoubleDef("Density", 0.5), s, e, m.q[id].data(), cap);
+    } else if (mode == "Burst") {
+      n = mdh_droplet_config(m.L, m.param.GetDoubleDef("Density", 0.5), m.param.GetDoubleDef("Radius", 10), s, e,
+                             m.q[id].data(), cap);
     } else {
       m.p[id].assign((size_t)4 * cap, 0.0);
       n = mdh_collision_config(m.L, s, e, m.q[id].data(), m.p[id].data(), cap);
@@ -259,16 +285,52 @@ static void run_langevin(MDManager &m) {  // langevin.cc:11-32
   }
 }
 
-static void run_collision(MDManager &m) {  // collision.cc:54-80 (cdview output stays with the reference driver)
+static void run_collision(MDManager &m) {  // collision.cc:54-80
   generate(m, "Collision");
+  m.Upload();
+  m.SaveAsCdviewSequential();
   const int OBSERVE_LOOP = m.param.GetIntegerDef("ObserveLoop", 100);
   const int TOTAL_LOOP = m.param.GetIntegerDef("TotalLoop", 1000);
+  const bool save_cdview_file = m.param.GetBooleanDef("SaveCdviewFile", false);
   m.ShowSystemInformation();
-  m.Upload();
   for (int i = 0; i < TOTAL_LOOP; i++) {
     m.Calculate();  // the first call builds the pair list (pairlist.cc:27-29)
-    if (i % OBSERVE_LOOP == 0) std::cout << m.s_time << " " << m.Temperature() << "# observe" << std::endl;
+    if (i % OBSERVE_LOOP == 0) {
+      std::cout << m.s_time << " " << m.Temperature() << "# observe" << std::endl;
+      if (save_cdview_file) m.SaveAsCdviewSequential();
+    }
   }
+}
+
+static void run_burst(MDManager &m) {  // burst.cc:104-143
+  generate(m, "Burst");
+  m.SetInitialVelocity(m.param.GetDoubleDef("InitialVelocity", 1.0));
+  const int T_LOOP = m.param.GetIntegerDef("ThermalizeLoop", 150);
+  const int LOOP = m.param.GetIntegerDef("TotalLoop", 1000);
+  const int OBSERVE_LOOP = m.param.GetIntegerDef("ObserveLoop", 100);
+  m.ShowSystemInformation();
+  m.Upload();
+  m.MakePairList();
+  m.SetControlTemperature(true);
+  for (int i = 0; i < T_LOOP; i++) {
+    m.Calculate();
+    if (i % OBSERVE_LOOP == 0) m.SaveAsCdviewSequential();
+  }
+  m.SetControlTemperature(false);
+  const double start = now();
+  for (int i = 0; i < LOOP; i++) {
+    m.Calculate();
+    if (i % OBSERVE_LOOP == 0) {
+      std::cout << m.s_time << " " << m.Temperature() << " " << m.Pressure() << " " << m.TotalEnergy() << "# observe"
+                << std::endl;
+      m.SaveAsCdviewSequential();
+    }
+  }
+  for (auto *d : m.devs) mdb200_synchronize(d);
+  const double sec = now() - start;
+  const unsigned long n = m.GetTotalParticleNumber();
+  const double mups = (double)LOOP * (double)n / sec / 1.0e6;
+  std::cout << "# N = " << n << " " << sec << " [SEC] " << mups << " [MUPS]" << std::endl;
 }
 
 int main(int argc, char **argv) {
@@ -285,6 +347,7 @@ int main(int argc, char **argv) {
   if (mode == "Benchmark") run_benchmark(mdm);
   else if (mode == "Langevin") run_langevin(mdm);
   else if (mode == "Collision") run_collision(mdm);
+  else if (mode == "Burst") run_burst(mdm);
   else std::cout << "Mode " << mode << " is not found." << std::endl;
   return 0;
 }

@@ -25,6 +25,14 @@ def lib():
         L.mdh_collision_config.argtypes = [dp, dp, dp, vp, vp, C.c_long]
         L.mdh_initial_velocity.restype = None
         L.mdh_initial_velocity.argtypes = [vp, C.c_long, C.c_double, C.c_int]
+        L.mdh_droplet_config.restype = C.c_long
+        L.mdh_droplet_config.argtypes = [dp, C.c_double, C.c_double, dp, dp, vp, C.c_long]
+        L.mdh_save_cdview.restype = C.c_int
+        L.mdh_save_cdview.argtypes = [C.c_char_p, C.c_int, vp, vp, vp, C.c_long]
+        L.mdh_save_dump.restype = C.c_int
+        L.mdh_save_dump.argtypes = [C.c_char_p, C.c_int, vp, vp, C.c_long]
+        L.mdh_save_configuration.restype = C.c_int
+        L.mdh_save_configuration.argtypes = [C.c_char_p, vp, vp, C.c_long]
         _lib = L
     return _lib
 
@@ -74,3 +82,51 @@ def initial_velocity(n, V0, seed, out=None):
     p = np.zeros((n, 4)) if out is None else out
     lib().mdh_initial_velocity(_vp(p), int(n), float(V0), int(seed))
     return p[:n]
+
+
+def droplet_config(L, s, e, density=0.5, radius=10.0):
+    """DropletMaker (burst.cc:10-64): global FCC lattice sites inside the sphere around the box centre."""
+    vol = (e[0] - s[0]) * (e[1] - s[1]) * (e[2] - s[2])
+    cap = int(min(vol, 4.2 * radius ** 3 + 64) * density * 1.3) + 1024
+    q = np.zeros((cap, 4))
+    n = lib().mdh_droplet_config(_d3(L), float(density), float(radius), _d3(s), _d3(e), _vp(q), cap)
+    if n < 0:
+        raise MemoryError("droplet_config: output too small")
+    return q[:n]
+
+
+def _rows4(a):
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim != 2 or a.shape[1] != 4 or not a.flags["C_CONTIGUOUS"]:
+        b = np.zeros((a.shape[0], 4))
+        b[:, :a.shape[1]] = a
+        a = b
+    return a
+
+
+def save_cdview(filename, q, p, type_=None, append=False):
+    """MDUnit::SaveAsCdview (mdunit.cc:52-67) for one unit's locals; append=False truncates first
+    (mdmanager.cc:90-94).  q, p: (n,3) or (n,4) rows in reference index order."""
+    q4, p4 = _rows4(q), _rows4(p)
+    n = min(q4.shape[0], p4.shape[0])
+    t = None if type_ is None else np.ascontiguousarray(type_, dtype=np.int32)
+    rc = lib().mdh_save_cdview(os.fsencode(filename), 1 if append else 0, _vp(q4), _vp(p4),
+                               None if t is None else _vp(t), n)
+    if rc != 0:
+        raise IOError("cannot write " + str(filename))
+
+
+def save_dump(filename, q, p, append=False):
+    """FileDumper::Execute (mdmanager.cc:487-500): raw doubles qx qy qz px py pz per local."""
+    q4, p4 = _rows4(q), _rows4(p)
+    n = min(q4.shape[0], p4.shape[0])
+    if lib().mdh_save_dump(os.fsencode(filename), 1 if append else 0, _vp(q4), _vp(p4), n) != 0:
+        raise IOError("cannot write " + str(filename))
+
+
+def save_configuration(filename, q, p):
+    """Variables::SaveConfiguration (variables.cc:45-57): text rows "qx qy qz px py pz"."""
+    q4, p4 = _rows4(q), _rows4(p)
+    n = min(q4.shape[0], p4.shape[0])
+    if lib().mdh_save_configuration(os.fsencode(filename), _vp(q4), _vp(p4), n) != 0:
+        raise IOError("cannot write " + str(filename))

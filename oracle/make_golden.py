@@ -9,7 +9,9 @@ sha256 of the array in the reference's generation order); everything else at ful
 """
 import hashlib
 import os
+import shutil
 import sys
+import tempfile
 
 import numpy as np
 
@@ -37,6 +39,9 @@ CASES = {
     "nosehoover": ({"DumpInit": "Benchmark", "SystemSize": 14, "TimeStep": 0.002, "InitialVelocity": 1.5,
                     "ControlTemperature": "yes", "HeatbathType": "NoseHoover", "AimedTemperature": 1.0,
                     "HeatbathTau": 0.1}, 1, 100),
+    # the reference's own file writers on the final state (SaveAsCdview, SaveAsDumpFile, SaveConfiguration)
+    "files2": ({"DumpInit": "Benchmark", "UnitLength": 8, "TimeStep": 0.004, "InitialVelocity": 2.0,
+                "LocalGridX": 2, "LocalGridY": 1, "LocalGridZ": 1, "DumpSaveFiles": "yes"}, 2, 40),
 }
 
 
@@ -51,7 +56,13 @@ def make(name):
     first = 0 if init_build else 1
     kv.update({"DumpSteps": steps, "DumpStateAt": "0,%d" % steps, "DumpPairsAt": "",
                "DumpForceAt": "%d,%d" % (first, steps), "DumpPairsAtBuild": "yes"})
-    rec, out = refdump.run_reference(kv, nunits=nunits)
+    workdir = tempfile.mkdtemp(prefix="gold_")
+    rec, out = refdump.run_reference(kv, nunits=nunits, workdir=workdir)
+    files = {}
+    for fn in sorted(os.listdir(workdir)):
+        if fn.startswith("final.") or fn.endswith(".cnf"):
+            files["file." + fn] = np.frombuffer(open(os.path.join(workdir, fn), "rb").read(), dtype=np.uint8)
+    shutil.rmtree(workdir)
     keep = {}
     for k, v in rec.items():
         if k.startswith("pair_key."):
@@ -65,6 +76,7 @@ def make(name):
             continue
         else:
             keep[k] = v
+    keep.update(files)
     keep["cfg_keys"] = np.array(list(cfg.keys()))
     keep["cfg_vals"] = np.array([str(x) for x in cfg.values()])
     keep["steps"] = np.array([steps])
@@ -77,8 +89,47 @@ def make(name):
         os.path.getsize(path) / 1e3))
 
 
+
+
+# ---------------------------------------------------------------------------------------------
+# Whole-project runs of the unmodified reference (its own Mode= loops, its own printed lines and cdview
+# files): expected output for the stand-alone driver tests (tests/test_gpu_cxx_driver.py).
+# ---------------------------------------------------------------------------------------------
+PROJECT_RUNS = {
+    "burst": "Mode=Burst\nDensity=0.8\nThermalizeLoop=100\nAimedTemperature=1.5\nSystemSize=30\nRadius=6\n"
+             "TimeStep=0.005\nTotalLoop=201\nObserveLoop=100\nInitialVelocity=0.9\n",
+    "collision": "Mode=Collision\nSystemSizeX=40\nSystemSizeY=30\nSystemSizeZ=30\nTimeStep=0.004\nTotalLoop=101\n"
+                 "ObserveLoop=50\nSaveCdviewFile=yes\n",
+}
+
+
+def make_project_run(name):
+    import subprocess
+    out = os.path.join(GOLDEN, "projects", name)
+    os.makedirs(out, exist_ok=True)
+    work = tempfile.mkdtemp(prefix="proj_")
+    with open(os.path.join(work, "input.cfg"), "w") as f:
+        f.write(PROJECT_RUNS[name])
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    res = subprocess.run([refdump.REF_SCALAR, "input.cfg"], cwd=work, env=env, stdout=subprocess.PIPE,
+                         stderr=subprocess.STDOUT, text=True, timeout=3600, check=True)
+    with open(os.path.join(out, "input.cfg"), "w") as f:
+        f.write(PROJECT_RUNS[name])
+    with open(os.path.join(out, "stdout.txt"), "w") as f:
+        f.write(res.stdout)
+    files = sorted(fn for fn in os.listdir(work) if fn.endswith(".cd"))
+    keep = [files[0], files[-1]] if len(files) > 1 else files  # first and last snapshot
+    for fn in keep:
+        shutil.copy(os.path.join(work, fn), os.path.join(out, fn))
+    shutil.rmtree(work)
+    print("%-12s project run -> %s (%s)" % (name, os.path.relpath(out, ROOT), ", ".join(keep)))
+
+
 if __name__ == "__main__":
     if not refdump.have_ref():
         sys.exit("oracle/_ref/mdacp_scalar missing: run `make -C oracle ref` where /root/reference exists")
-    for n in (sys.argv[1:] or sorted(CASES)):
-        make(n)
+    for n in (sys.argv[1:] or sorted(CASES) + sorted(PROJECT_RUNS)):
+        if n in CASES:
+            make(n)
+        else:
+            make_project_run(n)

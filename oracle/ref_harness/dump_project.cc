@@ -14,6 +14,8 @@
 //   DumpPairsAt=a,b,c        steps at which the pair list (raw + CSR) is dumped
 //   DumpForceAt=a,b,c        steps at which the kick impulse of the current list/positions is dumped
 //   DumpPairsAtBuild=yes     additionally dump raw pairs after every rebuild
+//   DumpSaveFiles=yes        after the last step call the reference's own writers in the working directory:
+//                            MDManager::SaveAsCdview("final.cd"), SaveAsDumpFile("final.dump"), SaveConfiguration()
 //
 // Record format (little endian): char name[48]; int32 dtype (0=f64,1=i32,2=i64);
 // int32 ndim; int64 shape[4]; payload.
@@ -293,6 +295,11 @@ void OracleDump::Run(MDManager *mdm) {
     put_record("builds", 1, 2, sh2, builds.data());
     put_record("pn", 1, 2, sh2, pnv.data());
     put_record("tn", 1, 2, sh2, tnv.data());
+  }
+  if (param->GetBooleanDef("DumpSaveFiles", false)) {
+    mdm->SaveAsCdview("final.cd");
+    mdm->SaveAsDumpFile("final.dump");
+    mdm->SaveConfiguration();
   }
   // the reference's own printed observables at the end, for a human cross-check
   mout << mdm->GetSimulationTime() << " " << mdm->Temperature() << " " << mdm->Pressure() << " "

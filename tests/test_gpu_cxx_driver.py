@@ -45,3 +45,42 @@ def test_benchmark_cfg_as_shipped(tmp_path):
     assert got == EXPECTED, res.stdout
     assert any(l.startswith("# N = 87500 ") and l.endswith("[MUPS]") for l in lines)
     print(lines[-1])
+
+
+GOLDEN_PROJECTS = os.path.join(ROOT, "tests", "golden", "projects")
+
+
+def _cd_rows(path):
+    import numpy as np
+    return np.array([l.split() for l in open(path).read().splitlines()], dtype=float)
+
+
+@pytest.mark.parametrize("name", ["burst", "collision"])
+def test_project_run_matches_the_reference(name, tmp_path):
+    """Mode=Burst (droplet, Nose-Hoover thermalisation switched off mid-run, burst.cc:104-143) and Mode=Collision
+    with SaveCdviewFile=yes (collision.cc:54-80): the driver prints the unmodified reference's observe lines and
+    writes its cdview files -- conf0000.cd of Collision byte for byte (written before the first step), later files to
+    the 6 digits the format carries.  Expected output: tests/golden/projects/ (oracle/make_golden.py)."""
+    import numpy as np
+    if not os.path.exists(EXE):
+        pytest.skip("C++ driver not built")
+    gold = os.path.join(GOLDEN_PROJECTS, name)
+    (tmp_path / "input.cfg").write_text(open(os.path.join(gold, "input.cfg")).read())
+    res = subprocess.run([EXE, "input.cfg"], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                         text=True, timeout=600)
+    assert res.returncode == 0, res.stdout
+    ref_out = open(os.path.join(gold, "stdout.txt")).read().splitlines()
+    want = [l.strip() for l in ref_out if l.endswith("# observe")]
+    got = [l.strip() for l in res.stdout.splitlines() if l.endswith("# observe")]
+    assert got == want, res.stdout
+    for key in ("# Number of Particles", "# System Size", "# Density", "# TimeStep", "# ControlTemperature"):
+        assert [l for l in ref_out if l.startswith(key)] == [l for l in res.stdout.splitlines() if l.startswith(key)]
+    for fn in sorted(f for f in os.listdir(gold) if f.endswith(".cd")):
+        assert (tmp_path / fn).exists(), fn
+        if name == "collision" and fn == "conf0000.cd":
+            assert (tmp_path / fn).read_bytes() == open(os.path.join(gold, fn), "rb").read()
+            continue
+        ref, mine = _cd_rows(os.path.join(gold, fn)), _cd_rows(str(tmp_path / fn))
+        assert mine.shape == ref.shape, fn
+        assert np.array_equal(mine[:, :2], ref[:, :2])
+        assert np.abs(mine[:, 2:] - ref[:, 2:]).max() <= 2e-5 * max(1.0, np.abs(ref[:, 2:]).max()), fn
