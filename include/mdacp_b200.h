@@ -130,6 +130,12 @@ int mdb200_make_pairlist(mdb200_unit **units, int n);
  * Nose-Hoover (:160-175) or Langevin (:186-192). */
 int mdb200_step(mdb200_unit **units, int n, int nsteps);
 
+/* MDManager::ChangeScale (mdmanager.cc:432-443): MakePairList, scale the global box, every unit's rect
+ * (MDRect::ChangeScale, mdrect.cc:55-60), the locals' positions (Variables::ChangeScale,
+ * variables.cc:133-139) and the cell grid (MeshList::ChangeScale, meshlist.cc:31-55) by alpha,
+ * MakePairList again.  mdb200_get_rect returns the scaled rect afterwards. */
+int mdb200_change_scale(mdb200_unit **units, int n, double alpha);
+
 /* The pieces of one step, exposed for parity tests against the matching reference functions. */
 int mdb200_is_pairlist_expired(mdb200_unit **units, int n, int *expired); /* mdmanager.cc:369-377 */
 int mdb200_update_position_half(mdb200_unit *u);  /* ForceCalculator::UpdatePositionHalf, fcalculator.cc:22-32 */

@@ -25,7 +25,7 @@ SYMBOLS = [
     "mdb200_set_zeta", "mdb200_set_control_temperature", "mdb200_set_aimed_temperature", "mdb200_observe",
     "mdb200_observe_unit", "mdb200_get_pairs", "mdb200_get_impulse", "mdb200_timers", "mdb200_set_profiling",
     "mdb200_synchronize", "mdb200_event_record", "mdb200_event_elapsed_ms", "mdb200_list_stats",
-    "mdb200_snapshot_begin", "mdb200_snapshot_wait",
+    "mdb200_snapshot_begin", "mdb200_snapshot_wait", "mdb200_change_scale",
 ]
 
 
@@ -91,6 +91,7 @@ def lib():
         L.mdb200_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, dp]
         L.mdb200_list_stats.argtypes = [vp, dp]
         L.mdb200_snapshot_begin.argtypes = [vp]
+        L.mdb200_change_scale.argtypes = [C.POINTER(vp), C.c_int, C.c_double]
         L.mdb200_snapshot_wait.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), llp]
         _lib = L
     return _lib
@@ -287,6 +288,9 @@ class Group:
 
     def step(self, nsteps=1):
         check(lib().mdb200_step(self._arr, self.n, int(nsteps)))
+
+    def change_scale(self, alpha):
+        check(lib().mdb200_change_scale(self._arr, self.n, float(alpha)))
 
     def is_pairlist_expired(self):
         e = C.c_int()

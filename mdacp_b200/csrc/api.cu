@@ -151,6 +151,31 @@ static int materialize(Unit *u) {
   return MDB200_OK;
 }
 
+// cell grid and periodic shifts from the current box c.L / c.s / c.e (MeshList::ChangeScale, meshlist.cc:31-55)
+static void setup_cells(Unit *u) {
+  const mdb200_params &p = u->prm;
+  Consts &c = u->c;
+  c.ncell = 1;
+  for (int d = 0; d < 3; d++) {
+    // meshlist.cc:31-55: ms = int(w / SL) interior cells of edge w/ms >= SL, one halo layer
+    const double w = c.e[d] - c.s[d];
+    int ms = static_cast<int>(w / c.SL);
+    if (ms < 1) ms = 1;
+    c.ms[d] = ms;
+    c.m[d] = ms + 2;
+    c.inv_edge[d] = 1.0 / (w / static_cast<double>(ms));
+    c.ncell *= c.m[d];
+  }
+  // periodic shifts applied when a ghost crosses the global box (mdunit.cc:141-163)
+  for (int dir = 0; dir < 6; dir++) {
+    for (int d = 0; d < 3; d++) u->shift[dir][d] = 0.0;
+    const int axis = dir / 2;
+    const bool low = (dir % 2 == 0);
+    const bool over = low ? (p.grid_pos[axis] == 0) : (p.grid_pos[axis] == p.grid_size[axis] - 1);
+    if (over) u->shift[dir][axis] = low ? c.L[axis] : -c.L[axis];  // ParaInfo::IsOverBoundary, parainfo.cc:256-275
+  }
+}
+
 static void setup_consts(Unit *u) {
   const mdb200_params &p = u->prm;
   Consts &c = u->c;
@@ -177,25 +202,7 @@ static void setup_consts(Unit *u) {
     c.C2 = 6.0 * s14 - 3.0 * s8;
     c.C0 = -s12 + s6 - c.C2 / s2;
   }
-  c.ncell = 1;
-  for (int d = 0; d < 3; d++) {
-    // meshlist.cc:31-55: ms = int(w / SL) interior cells of edge w/ms >= SL, one halo layer
-    const double w = c.e[d] - c.s[d];
-    int ms = static_cast<int>(w / c.SL);
-    if (ms < 1) ms = 1;
-    c.ms[d] = ms;
-    c.m[d] = ms + 2;
-    c.inv_edge[d] = 1.0 / (w / static_cast<double>(ms));
-    c.ncell *= c.m[d];
-  }
-  // periodic shifts applied when a ghost crosses the global box (mdunit.cc:141-163)
-  for (int dir = 0; dir < 6; dir++) {
-    for (int d = 0; d < 3; d++) u->shift[dir][d] = 0.0;
-    const int axis = dir / 2;
-    const bool low = (dir % 2 == 0);
-    const bool over = low ? (p.grid_pos[axis] == 0) : (p.grid_pos[axis] == p.grid_size[axis] - 1);
-    if (over) u->shift[dir][axis] = low ? p.L[axis] : -p.L[axis];  // ParaInfo::IsOverBoundary, parainfo.cc:256-275
-  }
+  setup_cells(u);
 }
 
 static int reset_ctrl(Unit *u, bool keep_zeta) {
@@ -826,6 +833,48 @@ int mdb200_make_pairlist(mdb200_unit **units, int n) {
   std::vector<Unit *> us;
   MDB_TRY(unpack_units(units, n, us));
   for (int i = 0; i < n; i++) MDB_TRY(materialize(us[i]));
+  return make_pairlist(us.data(), n);
+}
+
+__global__ void k_scale_positions(double4 *__restrict__ q, int pn, double alpha) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pn) return;
+  double4 v = q[i];
+  v.x *= alpha; v.y *= alpha; v.z *= alpha;  // Variables::ChangeScale (variables.cc:133-139)
+  q[i] = v;
+}
+
+// MDManager::ChangeScale (mdmanager.cc:432-443): rebuild, scale the box (SimulationInfo::L, every unit's rect
+// by MDRect::ChangeScale mdrect.cc:55-60, i.e. s *= alpha, e *= alpha), the locals' positions and the cell grid
+// (MeshList::ChangeScale), rebuild again.
+int mdb200_change_scale(mdb200_unit **units, int n, double alpha) {
+  std::vector<Unit *> us;
+  MDB_TRY(unpack_units(units, n, us));
+  if (!(alpha > 0.0)) { set_error("scale factor must be positive"); return MDB200_EINVAL; }
+  for (int i = 0; i < n; i++) MDB_TRY(materialize(us[i]));
+  MDB_TRY(make_pairlist(us.data(), n));
+  for (int i = 0; i < n; i++) {
+    Unit *u = us[i];
+    DeviceGuard g(u->device);
+    for (int d = 0; d < 3; d++) {
+      u->prm.L[d] = u->prm.L[d] * alpha;
+      u->c.L[d] = u->prm.L[d];
+      u->c.s[d] *= alpha;
+      u->c.e[d] *= alpha;
+      const double w = u->c.e[d] - u->c.s[d];
+      if (static_cast<int>(w / u->c.SL) < 1) {
+        set_error("sub-box narrower than the search length along axis %d after scaling", d);
+        return MDB200_EINVAL;
+      }
+    }
+    setup_cells(u);
+    if (u->pn > 0) {
+      k_scale_positions<<<(unsigned)((u->pn + 255) / 256), 256, 0, u->stream>>>(u->q.ptr, (int)u->pn, alpha);
+      u->launches++;
+      MDB_CUDA(cudaGetLastError());
+    }
+    u->inner_valid = false;
+  }
   return make_pairlist(us.data(), n);
 }
 

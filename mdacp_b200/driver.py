@@ -315,6 +315,11 @@ class MDManager:
     def SendBorderParticles(self):
         self.group.send_border_particles()
 
+    def ChangeScale(self, alpha):
+        """mdmanager.cc:432-443"""
+        self.group.change_scale(alpha)
+        self.sinfo.L = [x * alpha for x in self.sinfo.L]
+
     # --- observation (mdmanager.cc:359-429) -----------------------------------------------
     def GetSimulationTime(self):
         return self.s_time

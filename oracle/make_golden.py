@@ -39,6 +39,21 @@ CASES = {
     "nosehoover": ({"DumpInit": "Benchmark", "SystemSize": 14, "TimeStep": 0.002, "InitialVelocity": 1.5,
                     "ControlTemperature": "yes", "HeatbathType": "NoseHoover", "AimedTemperature": 1.0,
                     "HeatbathTau": 0.1}, 1, 100),
+    # multi-unit versions of the thermostat / droplet cases (global temperature reduction, migration between
+    # eight sub-boxes, empty and nearly empty units)
+    "langevinT0_8": ({"DumpInit": "Langevin", "UnitLength": 8, "TimeStep": 0.005, "InitialVelocity": 1.8,
+                      "Density": 0.7, "AimedTemperature": 0.0, "HeatbathGamma": 0.1, "HeatbathType": "Langevin",
+                      "Seed": 12345}, 8, 100),
+    "nosehoover8": ({"DumpInit": "Benchmark", "SystemSize": 16, "TimeStep": 0.002, "InitialVelocity": 1.5,
+                     "ControlTemperature": "yes", "HeatbathType": "NoseHoover", "AimedTemperature": 1.0,
+                     "HeatbathTau": 0.1}, 8, 100),
+    "collision8": ({"DumpInit": "Collision", "SystemSizeX": 40, "SystemSizeY": 30, "SystemSizeZ": 30,
+                    "TimeStep": 0.004}, 8, 300),
+    # MDManager::ChangeScale (no caller in the shipped projects): compress by 2 % after step 40, expand after ... once
+    "scale8": ({"DumpInit": "Benchmark", "SystemSize": 16, "TimeStep": 0.004, "InitialVelocity": 2.0,
+                "DumpChangeScaleAt": 40, "DumpChangeScaleAlpha": 0.98}, 8, 80),
+    "scale1": ({"DumpInit": "Benchmark", "SystemSize": 14, "TimeStep": 0.004, "InitialVelocity": 2.0,
+                "DumpChangeScaleAt": 30, "DumpChangeScaleAlpha": 1.03}, 1, 80),
     # the reference's own file writers on the final state (SaveAsCdview, SaveAsDumpFile, SaveConfiguration)
     "files2": ({"DumpInit": "Benchmark", "UnitLength": 8, "TimeStep": 0.004, "InitialVelocity": 2.0,
                 "LocalGridX": 2, "LocalGridY": 1, "LocalGridZ": 1, "DumpSaveFiles": "yes"}, 2, 40),

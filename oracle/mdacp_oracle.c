@@ -768,6 +768,29 @@ static double temperature(orc_system *S) { /* mdmanager.cc:390-407 */
 }
 
 /* ---- MDManager::Calculate (mdmanager.cc:116-192) -------------------------------------------- */
+/* MDManager::ChangeScale (mdmanager.cc:432-443) with MDUnit::ChangeScale (mdunit.cc:200-205):
+ * MDRect::ChangeScale (mdrect.cc:55-60), Variables::ChangeScale (variables.cc:133-139, locals only),
+ * MeshList::ChangeScale (meshlist.cc:31-55) */
+void orc_change_scale(orc_system *S, double alpha) {
+  orc_make_pair_list(S);
+  for (int d = 0; d < 3; d++) S->prm.L[d] = S->prm.L[d] * alpha;
+  for (int id = 0; id < S->nunits; id++) {
+    unit_t *u = &S->u[id];
+    for (int d = 0; d < 3; d++) {
+      u->s[d] *= alpha;
+      u->e[d] *= alpha;
+    }
+    for (int i = 0; i < u->pn; i++) {
+      u->q[i][0] *= alpha;
+      u->q[i][1] *= alpha;
+      u->q[i][2] *= alpha;
+    }
+    free(u->mesh_index); free(u->mesh_index2); free(u->mesh_particle_number);
+    mesh_change_scale(S, u);
+  }
+  orc_make_pair_list(S);
+}
+
 int orc_is_pairlist_expired(orc_system *S) {
   int expired = 0;
   for (int i = 0; i < S->nunits; i++) expired |= is_pairlist_expired_unit(S, &S->u[i]);

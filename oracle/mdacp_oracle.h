@@ -44,6 +44,7 @@ int orc_add_particle(orc_system *s, const double x[3], const double v[3], int ty
 void orc_set_seed(orc_system *s, int seed);                  /* MDManager::SetSeed */
 void orc_set_control_temperature(orc_system *s, int on);
 void orc_make_pair_list(orc_system *s);                      /* MDManager::MakePairList */
+void orc_change_scale(orc_system *s, double alpha);          /* MDManager::ChangeScale */
 int orc_calculate(orc_system *s, int nsteps);                /* MDManager::Calculate; returns 0 or error code */
 void orc_update_position_half(orc_system *s);
 void orc_send_border_particles(orc_system *s);

@@ -46,6 +46,7 @@ def lib():
         L.orc_set_control_temperature.argtypes = [vp, C.c_int]
         L.orc_make_pair_list.argtypes = [vp]
         L.orc_calculate.argtypes = [vp, C.c_int]
+        L.orc_change_scale.argtypes = [vp, C.c_double]
         L.orc_update_position_half.argtypes = [vp]
         L.orc_send_border_particles.argtypes = [vp]
         L.orc_calculate_force.argtypes = [vp]
@@ -135,6 +136,9 @@ class System:
         rc = lib().orc_calculate(self.h, int(nsteps))
         if rc:
             raise RuntimeError("oracle error %d: %s" % (rc, lib().orc_last_error().decode()))
+
+    def change_scale(self, alpha):
+        lib().orc_change_scale(self.h, float(alpha))
 
     def update_position_half(self):
         lib().orc_update_position_half(self.h)

@@ -14,6 +14,7 @@
 //   DumpPairsAt=a,b,c        steps at which the pair list (raw + CSR) is dumped
 //   DumpForceAt=a,b,c        steps at which the kick impulse of the current list/positions is dumped
 //   DumpPairsAtBuild=yes     additionally dump raw pairs after every rebuild
+//   DumpChangeScaleAt=<k>, DumpChangeScaleAlpha=<a>   after the records of step k: MDManager::ChangeScale(a)
 //   DumpSaveFiles=yes        after the last step call the reference's own writers in the working directory:
 //                            MDManager::SaveAsCdview("final.cd"), SaveAsDumpFile("final.dump"), SaveConfiguration()
 //
@@ -199,6 +200,8 @@ void OracleDump::Run(MDManager *mdm) {
   const std::set<int> pairs_at = parse_list(param->GetStringDef("DumpPairsAt", "0"));
   const std::set<int> force_at = parse_list(param->GetStringDef("DumpForceAt", ""));
   const bool pairs_at_build = param->GetBooleanDef("DumpPairsAtBuild", false);
+  const int cs_at = param->GetIntegerDef("DumpChangeScaleAt", -1);
+  const double cs_alpha = param->GetDoubleDef("DumpChangeScaleAlpha", 1.0);
   const int nu = mdm->GetTotalThreads();
 
   g_fp = fopen(fname.c_str(), "wb");
@@ -287,6 +290,11 @@ void OracleDump::Run(MDManager *mdm) {
       }
     }
     if (s > 0 && state_at.count(s)) dump_state(mdm, s);
+    if (s == cs_at) {
+      mdm->ChangeScale(cs_alpha);
+      double cs[2] = {(double)cs_at, cs_alpha};
+      put_f64("change_scale", cs, 2);
+    }
   }
   {
     int64_t shape[4] = {steps + 1, nu, 3, 1};

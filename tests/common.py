@@ -144,6 +144,8 @@ def check_oracle_against_records(rec, steps, init_build, seed=None):
                     assert np.array_equal(st["p"], rec["p." + tag])
                     assert np.array_equal(st["type"], rec["type." + tag])
                     assert osys.zeta(u) == rec["zeta." + tag][0]
+            if "change_scale" in rec and s == int(rec["change_scale"][0]):
+                osys.change_scale(float(rec["change_scale"][1]))  # MDManager::ChangeScale after step s
     finally:
         osys.close()
 
@@ -197,14 +199,19 @@ def check_cuda_against_records(rec, steps, init_build, seed=None, observe_every=
                         worst[name] = max(worst[name], abs(o[idx] - r[idx]) / den)
                         assert worst[name] <= TOL_OBS, "%s differs by %.3e (relative) at step %d" % (
                             name, worst[name], s)
+            if "change_scale" in rec and s == int(rec["change_scale"][0]):
+                mdm.ChangeScale(float(rec["change_scale"][1]))  # MDManager::ChangeScale after step s
         # printed observables, combined exactly as mdmanager.cc:390-429
         tot = obs_ref[steps].sum(axis=0)
         N = float(pn_ref[steps].sum())
-        ref_o = driver.observables_from_raw([tot[0], tot[1], tot[2], N], meta["L"])
+        Lref = list(meta["L"])
+        if "change_scale" in rec and steps > int(rec["change_scale"][0]):
+            Lref = [x * float(rec["change_scale"][1]) for x in Lref]
+        ref_o = driver.observables_from_raw([tot[0], tot[1], tot[2], N], Lref)
         my_o = mdm.observables()
         for k in ("T", "E"):
             assert abs(my_o[k] - ref_o[k]) <= TOL_OBS * abs(ref_o[k]), (k, my_o[k], ref_o[k])
-        pscale = max(abs(ref_o["P"]), ref_o["T"] * N / (meta["L"][0] * meta["L"][1] * meta["L"][2]))
+        pscale = max(abs(ref_o["P"]), ref_o["T"] * N / (Lref[0] * Lref[1] * Lref[2]))
         assert abs(my_o["P"] - ref_o["P"]) <= TOL_OBS * pscale, ("P", my_o["P"], ref_o["P"])
         for u in range(nunits):
             tag = "s%d.u%d" % (steps, u)
@@ -214,7 +221,7 @@ def check_cuda_against_records(rec, steps, init_build, seed=None, observe_every=
             qr, pr, tr = rec["q." + tag], rec["p." + tag], rec["type." + tag]
             assert np.array_equal(d["type"], tr), "reference index order differs (unit %d)" % u
             assert d["q"].shape == qr.shape
-            assert np.max(np.abs(d["q"] - qr)) <= TOL_STATE * max(meta["L"]), "q differs (unit %d)" % u
+            assert np.max(np.abs(d["q"] - qr)) <= TOL_STATE * max(Lref), "q differs (unit %d)" % u
             assert np.max(np.abs(d["p"] - pr)) <= TOL_STATE * max(1.0, float(np.abs(pr).max())), "p differs"
         return worst
     finally:
