@@ -615,7 +615,6 @@ int mdb200_destroy(mdb200_unit *h) {
   u->cell_of.release(); u->cell_count.release(); u->cell_start.release(); u->cell_cursor.release();
   u->cell_items.release(); u->gcell_count.release(); u->gcell_start.release(); u->gcell_cursor.release();
   u->gcell_items.release();
-  u->tile_off.release(); u->tile_first.release();
   for (int d = 0; d < 6; d++) u->border[d].release();
   u->send_buf.release(); u->mig_send_q.release(); u->mig_send_p.release(); u->mig_recv_q.release();
   u->mig_recv_p.release(); u->mig_send_t.release(); u->mig_recv_t.release();

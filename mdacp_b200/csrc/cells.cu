@@ -706,195 +706,6 @@ k_pair_search_onepass(const double4 *__restrict__ q, const int *__restrict__ cel
     for (int e = n; e < wl * kG; e++) list[base + list_word(e / kG, flane0 + e % kG)] = (unsigned)sentinel;
 }
 
-// TILED one-pass search.  The plain kernels above are bound by the candidate loads: every test needs its own
-// 32-byte position per lane (8 clk of L1 -> register bandwidth per warp-wide load even when the address is uniform)
-// and waits for it (ncu: issue 41 %, FP64 pipe 22 %, the stall samples sit on the first DADD behind each load).
-// Here a thread owns a TILE of up to kTile = 4 locals OF ONE CELL (cells are split into ceil(n / 4) tiles by
-// k_tile_count / k_tile_table, so all tiles walk exactly one 27-cell neighbourhood), loads candidates four at a
-// time and tests each against all its locals; hits are collected as bit masks over chunks of 32 candidates (no
-// divergent code in the test loop) and appended in ascending order to per-local buffers in local memory.  Rows
-// keep k_pair_search_onepass's fixed capacity and rainbow deal-out; the per-force-warp step count is gathered with
-// atomicMax and the sentinel padding is written by k_pad_rows afterwards; on overflow the host falls back to
-// scan + fill exactly as before.
-constexpr int kTile = 4;
-__global__ void k_tile_count(const int *__restrict__ cell_start, int *__restrict__ tile_cnt, int ncell) {
-  const int ci = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ci >= ncell) return;
-  tile_cnt[ci] = (cell_start[ci + 1] - cell_start[ci] + kTile - 1) / kTile;
-}
-__global__ void k_tile_table(const int *__restrict__ cell_start, const int *__restrict__ tile_off,
-                             int *__restrict__ tile_first, int ncell) {
-  const int ci = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ci >= ncell) return;
-  const int b = cell_start[ci], e = cell_start[ci + 1];
-  int o = tile_off[ci];
-  for (int f = b; f < e; f += kTile) tile_first[o++] = f;
-}
-
-__global__ void __launch_bounds__(128, 4)
-k_pair_search_tile(const double4 *__restrict__ q, const int *__restrict__ cell_start,
-                   const int *__restrict__ gcell_start, const int *__restrict__ gcell_items,
-                   const int *__restrict__ tile_first, const int *__restrict__ tile_total,
-                   int *__restrict__ row_count, unsigned *__restrict__ row_cls, int *__restrict__ warp_len,
-                   unsigned *__restrict__ list, int *__restrict__ warp_flag, int pn, int S, Consts c, Ctrl *ctrl) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;  // tile
-  const int lane = threadIdx.x & 31;
-  const bool live = t < *tile_total;
-  const int cap = min(ONEPASS_HCAP, S * kG);
-  unsigned hits[kTile][ONEPASS_HCAP];
-  int n[kTile], nloc[kTile];
-  unsigned cls[kTile];
-#pragma unroll
-  for (int k = 0; k < kTile; k++) { n[k] = 0; nloc[k] = 0; cls[k] = 0u; }
-  int a0 = 0, cnt = 0;
-  if (live) {
-    a0 = tile_first[t];
-    double ax[kTile], ay[kTile], az[kTile];
-    const double4 q0 = q[a0];
-    const int cell = cell_index(q0, c, 0);
-    cnt = min(kTile, cell_start[cell + 1] - a0);
-#pragma unroll
-    for (int k = 0; k < kTile; k++) {
-      const double4 v = q[a0 + min(k, cnt - 1)];  // unused lanes repeat the last local; their hits are dropped
-      ax[k] = v.x; ay[k] = v.y; az[k] = v.z;
-    }
-    const int cx = cell % c.m[0];
-    const int cy = (cell / c.m[0]) % c.m[1];
-    const int cz = cell / (c.m[0] * c.m[1]);
-    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, c.m[0] - 1);
-    const double SL2 = c.SL2;
-#pragma unroll 1
-    for (int ghosts = 0; ghosts < 2; ghosts++) {  // ghosts after all locals
-      const int *__restrict__ start = ghosts ? gcell_start : cell_start;
-#pragma unroll 1
-      for (int dz = -1; dz <= 1; dz++) {
-        const int z = cz + dz;
-        if (z < 0 || z >= c.m[2]) continue;
-#pragma unroll 1
-        for (int dy = -1; dy <= 1; dy++) {
-          const int y = cy + dy;
-          if (y < 0 || y >= c.m[1]) continue;
-          const int rowc = c.m[0] * (y + c.m[1] * z);
-          // the three x-neighbours are contiguous in cell order: one range per (y,z)
-          const int jb = start[rowc + x0], je = start[rowc + x1 + 1];
-#pragma unroll 1
-          for (int j0 = jb; j0 < je; j0 += 32) {
-            const int c32 = min(32, je - j0);
-            unsigned m[kTile];
-#pragma unroll
-            for (int k = 0; k < kTile; k++) m[k] = 0u;
-#pragma unroll 1
-            for (int b = 0; b < c32; b += 4) {
-              // four candidates per trip, their loads issued together; indices past the range repeat its last
-              // candidate and are masked off below
-              int jj[4];
-#pragma unroll
-              for (int i = 0; i < 4; i++) {
-                const int idx = min(j0 + b + i, je - 1);
-                jj[i] = ghosts ? gcell_items[idx] : idx;
-              }
-              double4 qj[4];
-#pragma unroll
-              for (int i = 0; i < 4; i++) qj[i] = q[jj[i]];
-#pragma unroll
-              for (int i = 0; i < 4; i++) {
-#pragma unroll
-                for (int k = 0; k < kTile; k++) {
-                  const double dx = ax[k] - qj[i].x, dy2 = ay[k] - qj[i].y, dz2 = az[k] - qj[i].z;
-                  const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy2, dy2)), __dmul_rn(dz2, dz2));
-                  m[k] |= (!(r2 > SL2) ? 1u : 0u) << (b + i);
-                }
-              }
-            }
-            const unsigned valid = (c32 == 32) ? 0xffffffffu : ((1u << c32) - 1u);
-#pragma unroll
-            for (int k = 0; k < kTile; k++) {
-              unsigned mm = (k < cnt) ? (m[k] & valid) : 0u;
-              while (mm) {
-                const int b = __ffs(mm) - 1;
-                mm &= mm - 1u;
-                const int j = ghosts ? gcell_items[j0 + b] : j0 + b;
-                if (j == a0 + k) continue;
-                if (n[k] < cap) hits[k][n[k]] = (unsigned)j;
-                cls[k] += 1u << (8 * (j & 3));
-                n[k]++;
-              }
-            }
-          }
-        }
-      }
-      if (!ghosts) {
-#pragma unroll
-        for (int k = 0; k < kTile; k++) nloc[k] = n[k];
-      }
-    }
-  }
-  int over = 0, mrow = 0;
-  unsigned long long nref = 0ull;  // reference-style pair count in half-pairs (see k_pair_search)
-#pragma unroll
-  for (int k = 0; k < kTile; k++) {
-    if (k < cnt) {
-      const int a = a0 + k;
-      const int steps = (n[k] + kG - 1) / kG;
-      over |= (n[k] > cap || ((steps + 1) & ~1) > S) ? 1 : 0;
-      mrow = max(mrow, n[k]);
-      nref += (unsigned long long)(nloc[k] + 2 * (n[k] - nloc[k]));
-      row_count[a] = n[k];
-      row_cls[a] = cls[k];
-      if (((cls[k] & 0xFFu) + ((cls[k] >> 8) & 0xFFu) + ((cls[k] >> 16) & 0xFFu) + (cls[k] >> 24)) != (unsigned)n[k])
-        atomicOr(&ctrl->err, (int)DE_CAPACITY);  // a class count wrapped its 8 bits
-      // per force-warp: longest row in steps (k_pad_rows rounds it up to even), ghost flag
-      const int fw = a / kPW;
-      if (steps > *(volatile int *)&warp_len[fw]) atomicMax(&warp_len[fw], steps);
-      if (n[k] > nloc[k] && *(volatile int *)&warp_flag[fw] == 0) atomicOr(&warp_flag[fw], 1);
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    mrow = max(mrow, __shfl_xor_sync(0xffffffffu, mrow, o));
-    nref += __shfl_xor_sync(0xffffffffu, nref, o);
-    over |= __shfl_xor_sync(0xffffffffu, over, o);
-  }
-  if (lane == 0) {
-    if (nref) atomicAdd(&ctrl->npairs, nref);
-    if (mrow > *(volatile int *)&ctrl->max_row) atomicMax(&ctrl->max_row, mrow);
-    if (over) ctrl->scratch[6] = 1;
-  }
-#pragma unroll
-  for (int k = 0; k < kTile; k++) {
-    if (k < cnt && n[k] <= cap) {  // entries stay inside the row's S steps; an overflowing build is redone anyway
-      const int a = a0 + k;
-      const long long base = (long long)(a / kPW) * S * 32;
-      const int flane0 = (a % kPW) * kG;  // first lane of the local's group
-      RowOrder ro;
-      ro.init(cls[k]);
-      for (int e = 0; e < n[k]; e++) {
-        const unsigned j = hits[k][e];
-        const int w = ro.place((int)j);
-        list[base + list_word(w / kG, flane0 + w % kG)] = j;
-      }
-    }
-  }
-}
-
-// after k_pair_search_tile: rounds the force-warps' step counts up to even, writes the row offsets and pads every
-// row with the sentinel up to its force-warp's step count
-__global__ void k_pad_rows(const int *__restrict__ row_count, int *warp_len, long long *__restrict__ warp_off,
-                           unsigned *__restrict__ list, int pn, long long nslots, int sentinel, int S, const Ctrl *ctrl) {
-  const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // local slot (tail slots included)
-  if (a >= nslots) return;
-  const long long fw = a / kPW;
-  // every thread of the force-warp derives the same even count whether it reads the raw or the rounded value
-  const int wl = (*(volatile int *)&warp_len[fw] + 1) & ~1;
-  if ((a % kPW) == 0) warp_len[fw] = wl;  // also when a row overflowed: the scan + fill fallback needs the counts
-  if (ctrl->scratch[6]) return;
-  const long long base = fw * S * 32;
-  const int flane0 = (int)(a % kPW) * kG;
-  const int n = (a < pn) ? row_count[a] : 0;
-  for (int e = n; e < wl * kG; e++) list[base + list_word(e / kG, flane0 + e % kG)] = (unsigned)sentinel;
-  if ((a % kPW) == 0) warp_off[fw] = base;
-}
-
 __global__ void k_warp_order(const int *__restrict__ flag, const int *__restrict__ scanv, int *__restrict__ order,
                              int nw, int n_interior) {
   int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -936,30 +747,9 @@ int build_pair_list(Unit *u) {
         MDB_TRY(u->list.ensure((size_t)entries + (size_t)entries / 8 + 64));
       }
       MDB_CUDA(cudaMemsetAsync(&u->ctrl->scratch[6], 0, sizeof(int), u->stream));
-      static const bool tiled = getenv("MDB200_SEARCH_TILE") ? atoi(getenv("MDB200_SEARCH_TILE")) != 0 : true;
-      if (tiled) {
-        // tiles of <= kTile locals of one cell: counts per cell, offsets, table; the tile count stays on the device
-        const int nc = u->c.ncell;
-        const long long max_tiles = pn / kTile + std::min<long long>(nc, pn) + 1;
-        MDB_TRY(u->tile_off.ensure((size_t)nc + 2));
-        MDB_TRY(u->tile_first.ensure((size_t)max_tiles));
-        MDB_TRY(u->scan_ws.ensure(2 * scan_workspace_ints(nc + 2)));
-        k_tile_count<<<nblk(nc), TPB, 0, u->stream>>>(u->cell_start.ptr, u->cell_cursor.ptr, nc);
-        MDB_TRY(exclusive_scan_i32(u->cell_cursor.ptr, u->tile_off.ptr, nc, u->scan_ws.ptr, u->stream, &u->launches));
-        k_tile_table<<<nblk(nc), TPB, 0, u->stream>>>(u->cell_start.ptr, u->tile_off.ptr, u->tile_first.ptr, nc);
-        MDB_CUDA(cudaMemsetAsync(u->warp_len.ptr, 0, sizeof(int) * (size_t)nw, u->stream));
-        MDB_CUDA(cudaMemsetAsync(u->warp_flag.ptr, 0, sizeof(int) * (size_t)nw, u->stream));
-        k_pair_search_tile<<<nblk(max_tiles, tpb), tpb, 0, u->stream>>>(
-            u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr, u->gcell_items.ptr, u->tile_first.ptr, u->tile_off.ptr + nc,
-            u->row_count.ptr, u->row_cls.ptr, u->warp_len.ptr, u->list.ptr, u->warp_flag.ptr, (int)pn, S, u->c, u->ctrl);
-        k_pad_rows<<<nblk(nthr), TPB, 0, u->stream>>>(u->row_count.ptr, u->warp_len.ptr, u->warp_off.ptr, u->list.ptr,
-                                                      (int)pn, nthr, sentinel_index(u), S, u->ctrl);
-        u->launches += 3;
-      } else {
-        k_pair_search_onepass<<<nblk(nthr, tpb), tpb, 0, u->stream>>>(
-            u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr, u->gcell_items.ptr, u->row_count.ptr, u->row_cls.ptr,
-            u->warp_off.ptr, u->warp_len.ptr, u->list.ptr, u->warp_flag.ptr, (int)pn, sentinel_index(u), S, u->c, u->ctrl);
-      }
+      k_pair_search_onepass<<<nblk(nthr, tpb), tpb, 0, u->stream>>>(
+          u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr, u->gcell_items.ptr, u->row_count.ptr, u->row_cls.ptr,
+          u->warp_off.ptr, u->warp_len.ptr, u->list.ptr, u->warp_flag.ptr, (int)pn, sentinel_index(u), S, u->c, u->ctrl);
       u->launches++;
       MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->scratch[6], &u->ctrl->scratch[6], sizeof(int), cudaMemcpyDeviceToHost, u->stream));
       MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->npairs, &u->ctrl->npairs, sizeof(unsigned long long), cudaMemcpyDeviceToHost,

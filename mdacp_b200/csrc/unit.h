@@ -139,7 +139,6 @@ struct Unit {
   DevBuf<int> cell_of;            // per item
   DevBuf<int> cell_count, cell_start, cell_cursor, cell_items;     // locals (items = ref idx)
   DevBuf<int> gcell_count, gcell_start, gcell_cursor, gcell_items; // ghosts (items = slot)
-  DevBuf<int> tile_off, tile_first; // search tiles (cells.cu:k_pair_search_tile): first tile of a cell, first local of a tile
 
   // ghosts: per direction send list (slots) and receive window
   DevBuf<int> border[6];
