@@ -638,10 +638,34 @@ k_pair_search_onepass(const double4 *__restrict__ q, const int *__restrict__ cel
           const int rowc = c.m[0] * (y + c.m[1] * z);
           // the three x-neighbours are contiguous in cell order: one range per (y,z)
           const int jb = start[rowc + x0], je = start[rowc + x1 + 1];
-          for (int k = jb; k < je; k++) {
-            const int j = ghosts ? gcell_items[k] : k;
-            if (j == a) continue;
-            if (within_search(qa, q[j], c.SL2)) {
+          // Chunks of 32 candidates: the test loop is branch-free (hits go into a bit mask) and takes four
+          // candidates per trip so that their loads are in flight together -- with one load per test followed by
+          // a branch, every test waited for its own load (ncu: issue 41 %, the stall samples on the first DADD).
+          // Indices past the range repeat its last candidate and are masked off.
+#pragma unroll 1
+          for (int j0 = jb; j0 < je; j0 += 32) {
+            const int c32 = min(32, je - j0);
+            unsigned m = 0u;
+#pragma unroll 1
+            for (int b = 0; b < c32; b += 4) {
+              int jj[4];
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                const int idx = min(j0 + b + i, je - 1);
+                jj[i] = ghosts ? gcell_items[idx] : idx;
+              }
+              double4 qj[4];
+#pragma unroll
+              for (int i = 0; i < 4; i++) qj[i] = q[jj[i]];
+#pragma unroll
+              for (int i = 0; i < 4; i++) m |= (within_search(qa, qj[i], c.SL2) ? 1u : 0u) << (b + i);
+            }
+            m &= (c32 == 32) ? 0xffffffffu : ((1u << c32) - 1u);
+            while (m) {
+              const int b = __ffs(m) - 1;
+              m &= m - 1u;
+              const int j = ghosts ? gcell_items[j0 + b] : j0 + b;
+              if (j == a) continue;
               if (n < cap) hits[n] = (unsigned)j;
               cls += 1u << (8 * (j & 3));
               n++;
