@@ -346,7 +346,10 @@ static int send_border_particles(Unit **us, int n) {
 // have closed since the inner list was derived.  us[0]->inner_left < 0 = derive again at the next force launch.
 // (kept in the group's first unit: inner_left = remaining distance budget, inner_delta = the delta the next
 // derivation will use, 0 = pruning off)
-static const int INNER_STEPS = 16;   // steps one derivation should last
+static int inner_steps() {           // steps one derivation should last (MDB200_INNER_STEPS overrides)
+  static const int v = getenv("MDB200_INNER_STEPS") ? std::max(6, atoi(getenv("MDB200_INNER_STEPS"))) : 32;
+  return v;
+}
 
 static int any_expired(Unit **us, int n, int *expired) {
   int ex = 0;
@@ -385,7 +388,7 @@ static int any_expired(Unit **us, int n, int *expired) {
   } else {
     us[0]->inner_left -= per_step;
     // next derivation: a delta that lasts INNER_STEPS steps, at most half the skin; not worth it below 6 steps
-    const double want = INNER_STEPS * per_step, cap = 0.5 * us[0]->c.BL;
+    const double want = inner_steps() * per_step, cap = 0.5 * us[0]->c.BL;
     us[0]->inner_delta = (6.0 * per_step > cap || getenv("MDB200_NO_PRUNE")) ? 0.0 : std::min(want, cap);
   }
   return MDB200_OK;
