@@ -9,12 +9,12 @@
 //    fcalculator.cc:273-275 / SURVEY.md Q8).  RED.ADD.F64 for the reaction term of a half list would cost
 //    ~3 P atomics per particle at ~1.3 clk/lane/SM -- several times this whole kernel.
 //  * kG = 4 LANES PER LOCAL (unit.h): a warp owns 8 consecutive cell-sorted locals; the 4 lanes of a group
-//    take 4 consecutive entries of that local's ascending row per step and a 2-stage shuffle reduction
-//    combines them at the end.  Why: ncu shows the thread-per-local version bound by the L1 data pipe on the
-//    scattered gather of partner positions (~20 distinct 128-byte lines = ~20 wavefronts per warp-gather,
-//    FP64 pipe ~30 %; profiles/r01_force_v*_ncu.txt).  Consecutive entries of one row sit in the same or
-//    adjacent lines and 8 neighbouring locals share most of their partner lines, which cuts the distinct
-//    lines per warp-gather to ~13 (scripts/gather_model.py) at identical FP64 work.
+//    take one entry each of that local's row per step and a 2-stage shuffle reduction combines them at the
+//    end.  Why: ncu shows the kernel bound by the L1 data pipe on the scattered gather of partner positions
+//    (FP64 pipe below 50 %; profiles/r01_force_*_ncu.txt, r01c_force_ncu.txt), and the cost of a warp-wide
+//    gather of 32-byte records is set by conflicts between the four 32-byte sector slots of a line
+//    (profiles/r01_ubench_gather.txt).  Rows are therefore stored in "rainbow" order (cells.cu: RowOrder):
+//    at every step the 4 lanes of a local take partners of 4 different slots (index mod 4).
 //  * one 256-bit load per partner (LDG.E.256); list words for two steps come from one 8-byte load per lane
 //    (a contiguous 256-byte run per warp); locals cell-sorted.
 //  * the cutoff test runs on the integer pipe (bit-pattern compare of the non-negative r2), keeping the
@@ -37,15 +37,6 @@ namespace mdb {
 #endif
 #ifndef FORCE_PF_L1
 #define FORCE_PF_L1 2
-#endif
-#ifndef FORCE_PF_CHUNK
-#define FORCE_PF_CHUNK 0
-#endif
-#ifndef FORCE_POS_EVICT_LAST
-#define FORCE_POS_EVICT_LAST 0
-#endif
-#ifndef FORCE_LIST_EVICT_FIRST
-#define FORCE_LIST_EVICT_FIRST 0
 #endif
 #ifndef FORCE_PRUNE_MINBLK
 #define FORCE_PRUNE_MINBLK 8
@@ -101,26 +92,14 @@ __device__ __forceinline__ double pair_df(double r2, const ForceConsts &fc) {
 
 __device__ __forceinline__ void ld_q256(const double4 *p, double &x, double &y, double &z) {
   double w;
-#if FORCE_POS_EVICT_LAST
-  asm("ld.global.nc.L1::evict_last.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(p));
-#else
   asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(p));
-#endif
   (void)w;
 }
 
 
-// list words are streamed once: FORCE_LIST_EVICT_FIRST marks their L1 lines as first to go, so that they
-// displace fewer position lines
-__device__ __forceinline__ uint2 ld_list(const uint2 *p) {
-#if FORCE_LIST_EVICT_FIRST
-  uint2 v;
-  asm("ld.global.nc.L1::evict_first.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-  return v;
-#else
-  return __ldg(p);
-#endif
-}
+// list words are streamed once (L1 eviction hints on them or on the positions made no difference, see
+// profiles/r01_force_experiments.md)
+__device__ __forceinline__ uint2 ld_list(const uint2 *p) { return __ldg(p); }
 
 // returns the bit pattern of r2 (non-negative doubles order like their bit patterns)
 template <int VARIANT>
@@ -183,11 +162,6 @@ __device__ __forceinline__ void force_warp(long long w, int lane, FORCE_PARAMS, 
   unsigned kcnt = 0u;
 
   constexpr int UNR = FORCE_UNROLL;
-#if FORCE_PF_CHUNK
-  // one instruction: lane l pulls 128-byte line l of this warp's list chunk (len2 x 256 B) towards the SM
-  if (lane * 128 < len2 * 256)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(lp - lane) + lane * 128));
-#endif
   uint2 en = (len2 > 0) ? ld_list(lp) : make_uint2(0u, 0u);
 #pragma unroll UNR
   for (int k = 0; k < len2; k++) {

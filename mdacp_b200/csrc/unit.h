@@ -282,7 +282,10 @@ int expiry_check_local(Unit *u, int *expired);                           // sync
 
 // force.cu
 int force_kick(Unit *u);
-int force_kick_drift(Unit *u, bool predrift, int part, int inner, double keep_len);  // inner: 0 outer list, 1 walk the inner list, 2 walk the outer list and derive the inner one (pairs within keep_len)                  // fused kick + drift(s); swaps q / q_alt                                           // kick + second half drift, swaps q / q_alt
+// fused kick + second half drift (+ the next step's first half drift if predrift); swaps q / q_alt.
+// part: 0 every force-warp, 1 interior, 2 boundary; inner: 0 walk the outer list, 1 walk the inner list,
+// 2 walk the outer list and derive the inner one (pairs within keep_len)
+int force_kick_drift(Unit *u, bool predrift, int part, int inner, double keep_len);
 int force_impulse(Unit *u, double *f3_host, long long cap_rows);         // sync
 
 // observe.cu
