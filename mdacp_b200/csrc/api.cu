@@ -39,6 +39,10 @@ static int check_device_error(Unit *u) {
     set_error("Invalid index (unit %d)", u->prm.unit_id);
     return MDB200_ECELL;
   }
+  if (e & DE_COMM) {
+    set_error("ghost exchange timed out waiting for a neighbour process (unit %d)", u->prm.unit_id);
+    return MDB200_ECOMM;
+  }
   set_error("capacity exceeded (unit %d)", u->prm.unit_id);
   return MDB200_ECAPACITY;
 }
@@ -304,6 +308,7 @@ static int make_pairlist(Unit **us, int n) {
   }
   dbg.lap("wrap + cell sort");
   // --- border lists + first ghost exchange (mdmanager.cc:269-275)
+  comm_p2p_invalidate();
   for (int dir = 0; dir < 6; dir++) {
     for (int i = 0; i < n; i++) {
       DeviceGuard g(us[i]->device);
@@ -313,6 +318,7 @@ static int make_pairlist(Unit **us, int n) {
     MDB_TRY(comm_border_setup(us, n, dir));
     MDB_TRY(stage_barrier(us, n));
   }
+  MDB_TRY(comm_p2p_update(us, n));  // ghost windows of the neighbour processes for the per-step peer-to-peer refresh
   dbg.lap("border lists + ghosts");
   // --- per unit MDUnit::MakePairList (mdunit.cc:194-198)
   for (int i = 0; i < n; i++) {
@@ -335,6 +341,7 @@ static int make_pairlist(Unit **us, int n) {
 
 // MDManager::SendBorderParticles (mdmanager.cc:283-292)
 static int send_border_particles(Unit **us, int n) {
+  MDB_TRY(comm_refresh_begin(us, n, false));
   for (int dir = 0; dir < 6; dir++) {
     MDB_TRY(comm_border_refresh(us, n, dir));
     if (dir % 2 == 1) MDB_TRY(stage_barrier(us, n));
@@ -460,6 +467,7 @@ static int calculate(Unit **us, int n) {
     }
     MDB_CUDA(cudaEventRecord(u->ev_drift, u->stream));
     MDB_CUDA(cudaStreamWaitEvent(u->cstream, u->ev_drift, 0));
+    MDB_TRY(comm_refresh_begin(us, n, true));
     for (int dir = 0; dir < 6; dir++) MDB_TRY(comm_border_refresh(us, n, dir, true));
     MDB_CUDA(cudaEventRecord(u->ev_ghost, u->cstream));
   } else {

@@ -5,13 +5,24 @@
 //   2. neighbour lives in another process: pack kernel -> ncclSend / ncclRecv directly into the
 //      ghost window (one group per direction), NCCL resolved at run time so the library has no
 //      link-time dependency on a particular libnccl (torch ships its own);
+//      -- that is the path of the rebuild (migration, first ghost transfer).  The PER-STEP ghost refresh
+//      between processes does not go through NCCL: after every rebuild the processes exchange CUDA IPC handles
+//      of their position buffers, and the same gather/put kernel then stores over NVLink straight into the
+//      neighbour process's ghost window (both position buffers), as in case 1.  Ordering is kept by two epoch
+//      counters per direction in a small IPC-shared mailbox: the sender's last block publishes "arrived" after a
+//      system-scope fence, a one-thread kernel on the receiver's stream waits for it, and the receiver
+//      acknowledges a round at the start of the next one so that the sender never overwrites ghosts still in use;
 //   3. scalar reductions: MPI_Allreduce(LOR/SUM) -> ncclAllReduce on a few words.
 // The order of operations per direction is the reference's (mdmanager.cc:195-248, 295-349):
 // all units pack, then all units receive.
 #include <dlfcn.h>
 #include <nccl.h>
 #include <string.h>
+#include <algorithm>
 #include <map>
+#include <set>
+#include <string>
+#include <vector>
 #include "comm.h"
 
 namespace mdb {
@@ -29,6 +40,7 @@ struct NcclApi {
   decltype(&ncclGroupStart) GroupStart = nullptr;
   decltype(&ncclGroupEnd) GroupEnd = nullptr;
   decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
   decltype(&ncclGetErrorString) GetErrorString = nullptr;
 };
 static NcclApi g_nccl;
@@ -55,6 +67,7 @@ static int load_nccl() {
   LOADSYM(GroupStart)
   LOADSYM(GroupEnd)
   LOADSYM(AllReduce)
+  LOADSYM(AllGather)
   LOADSYM(GetErrorString)
 #undef LOADSYM
   g_nccl.loaded = true;
@@ -79,6 +92,98 @@ struct CommState {
 };
 static CommState g_comm;
 
+// ---------------------------------------------------------------------------------------------
+// peer-to-peer ghost refresh between processes (one unit per process)
+// ---------------------------------------------------------------------------------------------
+struct Mailbox {
+  unsigned long long arrive[6];  // written by the sender of direction d: last refresh round whose ghosts have landed
+  unsigned long long ack[6];     // written by the receiver of direction d: last round it has finished reading
+  unsigned int ticket[6];        // last-block tickets of this unit's put kernels
+  unsigned int pad[2];
+};
+struct Window {                  // what a receiver tells its sender after a rebuild
+  cudaIpcMemHandle_t hq, hq2;    // the two position buffers
+  long long off, cnt;            // ghost window of the direction
+};
+struct P2P {
+  bool enabled = false, windows_valid = false;
+  Mailbox *mine = nullptr;
+  Mailbox *nbr_mail[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // unit we send to in dir
+  Mailbox *src_mail[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // unit we receive from in dir
+  double4 *dst_q[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double4 *dst_q2[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  unsigned long long epoch = 0;  // refresh rounds so far (identical on every process)
+  std::map<std::string, void *> opened;  // imported allocations by handle bytes
+  std::set<std::string> mail_keys;
+  Window *d_win = nullptr;       // device scratch: [0] send, [1] recv
+};
+static P2P g_p2p;
+
+static int p2p_open(const cudaIpcMemHandle_t &h, void **out, std::string *key_out = nullptr) {
+  std::string key(reinterpret_cast<const char *>(&h), sizeof(h));
+  if (key_out) *key_out = key;
+  auto it = g_p2p.opened.find(key);
+  if (it != g_p2p.opened.end()) { *out = it->second; return MDB200_OK; }
+  void *p = nullptr;
+  MDB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  g_p2p.opened[key] = p;
+  *out = p;
+  return MDB200_OK;
+}
+
+// ~10 s at 2 GHz: a neighbour that never shows up raises DE_COMM instead of hanging the device (and once the
+// flag is up nobody waits any more)
+__device__ __forceinline__ bool spin_until(const unsigned long long *flag, unsigned long long want, const Ctrl *ctrl) {
+  const long long t0 = clock64();
+  while (*(const volatile unsigned long long *)flag < want) {
+    if ((*(const volatile int *)&ctrl->err & (int)DE_COMM) || clock64() - t0 > 20000000000LL) return false;
+    __nanosleep(64);
+  }
+  return true;
+}
+
+struct MailPtrs { Mailbox *m[6]; };
+// start of refresh round `epoch`: everything up to round epoch - 1 has been read here (stream order)
+__global__ void k_p2p_ack(MailPtrs src, unsigned long long done_epoch) {
+  for (int d = 0; d < 6; d++)
+    if (src.m[d]) *(volatile unsigned long long *)&src.m[d]->ack[d] = done_epoch;
+  __threadfence_system();
+}
+
+// k_ghost_put (exchange.cu) into the neighbour PROCESS's ghost window
+__global__ void k_ghost_put_p2p(const double4 *__restrict__ sq, const int *__restrict__ border,
+                                double4 *__restrict__ dq, double4 *__restrict__ dq2, int n, double sx, double sy,
+                                double sz, Mailbox *mine, Mailbox *peer, int dir, unsigned long long epoch, Ctrl *ctrl) {
+  __shared__ int ok;
+  if (threadIdx.x == 0) ok = spin_until(&mine->ack[dir], epoch - 1, ctrl) ? 1 : 0;  // the window is free again
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ok && i < n) {
+    double4 v = sq[border[i]];
+    v = make_double4(v.x + sx, v.y + sy, v.z + sz, 0.0);  // mdunit.cc:167
+    dq[i] = v;
+    dq2[i] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (!ok) atomicOr(&ctrl->err, (int)DE_COMM);
+    const unsigned t = atomicAdd(&mine->ticket[dir], 1u);
+    if (t == gridDim.x - 1) {  // last block: every block's stores are fenced
+      mine->ticket[dir] = 0u;
+      __threadfence_system();
+      *(volatile unsigned long long *)&peer->arrive[dir] = epoch;
+    }
+  }
+}
+
+__global__ void k_p2p_wait(Mailbox *mine, int dir, unsigned long long epoch, Ctrl *ctrl) {
+  if (!spin_until(&mine->arrive[dir], epoch, ctrl)) atomicOr(&ctrl->err, (int)DE_COMM);
+}
+
+bool comm_p2p_enabled() { return g_p2p.enabled; }
+void comm_p2p_invalidate() { g_p2p.windows_valid = false; }
+
 int comm_unique_id(void *out128) {
   if (!out128) return MDB200_EINVAL;
   MDB_TRY(load_nccl());
@@ -92,6 +197,127 @@ int comm_unique_id(void *out128) {
 static bool is_remote(const Unit *u, int dir) { return u->nbr[dir] == nullptr; }
 static bool src_remote(const Unit *u, int dir) { return u->src[dir] == nullptr; }
 static const int OPP[6] = {1, 0, 3, 2, 5, 4};
+
+// mailboxes: one per process, exported once; all-gathered handles, the neighbours' mailboxes mapped here.
+// MDB200_P2P=0 keeps every refresh on NCCL; a process that cannot map a neighbour switches it off everywhere.
+static int p2p_init(Unit *u) {
+  const char *env = getenv("MDB200_P2P");
+  int ok = (env && env[0] == '0') ? 0 : 1;
+  cudaStream_t st = u->stream;
+  const int nr = g_comm.nranks;
+  MDB_CUDA(cudaMalloc(&g_p2p.mine, sizeof(Mailbox)));
+  MDB_CUDA(cudaMemsetAsync(g_p2p.mine, 0, sizeof(Mailbox), st));
+  MDB_CUDA(cudaMalloc(&g_p2p.d_win, 2 * sizeof(Window)));
+  cudaIpcMemHandle_t mh;
+  memset(&mh, 0, sizeof(mh));
+  if (cudaIpcGetMemHandle(&mh, g_p2p.mine) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+  cudaIpcMemHandle_t *d_all = nullptr;
+  MDB_CUDA(cudaMalloc(&d_all, sizeof(cudaIpcMemHandle_t) * (size_t)nr));
+  MDB_CUDA(cudaMemcpyAsync(d_all + g_comm.rank, &mh, sizeof(mh), cudaMemcpyHostToDevice, st));
+  MDB_NCCL(g_nccl.AllGather(d_all + g_comm.rank, d_all, sizeof(mh), ncclChar, g_comm.comm, st));
+  std::vector<cudaIpcMemHandle_t> all((size_t)nr);
+  MDB_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(mh) * (size_t)nr, cudaMemcpyDeviceToHost, st));
+  MDB_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_all);
+  if (ok) {
+    for (int dir = 0; dir < 6 && ok; dir++) {
+      if (!is_remote(u, dir)) continue;
+      void *a = nullptr, *b = nullptr;
+      std::string ka, kb;
+      if (p2p_open(all[(size_t)u->prm.neighbor_rank[dir]], &a, &ka) != MDB200_OK ||
+          p2p_open(all[(size_t)u->prm.neighbor_rank[OPP[dir]]], &b, &kb) != MDB200_OK) {
+        ok = 0;
+        cudaGetLastError();
+        break;
+      }
+      g_p2p.nbr_mail[dir] = static_cast<Mailbox *>(a);
+      g_p2p.src_mail[dir] = static_cast<Mailbox *>(b);
+      g_p2p.mail_keys.insert(ka);
+      g_p2p.mail_keys.insert(kb);
+    }
+  }
+  // everybody or nobody
+  MDB_CUDA(cudaMemcpyAsync(g_comm.d_cnt + 4, &ok, sizeof(int), cudaMemcpyHostToDevice, st));
+  MDB_NCCL(g_nccl.AllReduce(g_comm.d_cnt + 4, g_comm.d_cnt + 4, 1, ncclInt32, ncclMin, g_comm.comm, st));
+  MDB_CUDA(cudaMemcpyAsync(&ok, g_comm.d_cnt + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MDB_CUDA(cudaStreamSynchronize(st));
+  g_p2p.enabled = ok != 0;
+  if (g_p2p.enabled) {
+    u->q.graveyard = &u->deferred_free;
+    u->q_alt.graveyard = &u->deferred_free;
+  }
+  if (getenv("MDB200_DEBUG")) fprintf(stderr, "[mdb200] rank %d: peer-to-peer ghost refresh %s\n", g_comm.rank, ok ? "on" : "off");
+  return MDB200_OK;
+}
+
+// After the border set-up of a rebuild: every receiver tells its sender where its ghost window is now.
+int comm_p2p_update(Unit **us, int n) {
+  if (!g_p2p.enabled || n != 1) return MDB200_OK;
+  Unit *u = us[0];
+  cudaSetDevice(u->device);
+  cudaStream_t st = u->stream;
+  cudaIpcMemHandle_t hq, hq2;
+  MDB_CUDA(cudaIpcGetMemHandle(&hq, u->q.ptr));
+  MDB_CUDA(cudaIpcGetMemHandle(&hq2, u->q_alt.ptr));
+  std::set<std::string> used = g_p2p.mail_keys;
+  for (int dir = 0; dir < 6; dir++) {
+    g_p2p.dst_q[dir] = g_p2p.dst_q2[dir] = nullptr;
+    if (!is_remote(u, dir)) continue;
+    Window w[2];
+    memset(w, 0, sizeof(w));
+    w[0].hq = hq; w[0].hq2 = hq2; w[0].off = u->recv_off[dir]; w[0].cnt = u->recv_cnt[dir];
+    MDB_CUDA(cudaMemcpyAsync(g_p2p.d_win, &w[0], sizeof(Window), cudaMemcpyHostToDevice, st));
+    MDB_NCCL(g_nccl.GroupStart());
+    // my window for direction dir is filled by the unit in the opposite direction; I fill the window of nbr[dir]
+    MDB_NCCL(g_nccl.Send(g_p2p.d_win, sizeof(Window), ncclChar, u->prm.neighbor_rank[OPP[dir]], g_comm.comm, st));
+    MDB_NCCL(g_nccl.Recv(g_p2p.d_win + 1, sizeof(Window), ncclChar, u->prm.neighbor_rank[dir], g_comm.comm, st));
+    MDB_NCCL(g_nccl.GroupEnd());
+    MDB_CUDA(cudaMemcpyAsync(&w[1], g_p2p.d_win + 1, sizeof(Window), cudaMemcpyDeviceToHost, st));
+    MDB_CUDA(cudaStreamSynchronize(st));
+    if (w[1].cnt != u->n_border[dir]) {
+      set_error("ghost window of direction %d holds %lld rows, %lld are sent", dir, w[1].cnt, u->n_border[dir]);
+      return MDB200_ECOMM;
+    }
+    void *a = nullptr, *b = nullptr;
+    std::string ka, kb;
+    MDB_TRY(p2p_open(w[1].hq, &a, &ka));
+    MDB_TRY(p2p_open(w[1].hq2, &b, &kb));
+    used.insert(ka);
+    used.insert(kb);
+    g_p2p.dst_q[dir] = static_cast<double4 *>(a) + w[1].off;
+    g_p2p.dst_q2[dir] = static_cast<double4 *>(b) + w[1].off;
+  }
+  // unmap what the neighbours have replaced, then -- once every process has done so -- free what was replaced here
+  if (u->cstream) MDB_CUDA(cudaStreamSynchronize(u->cstream));
+  for (auto it = g_p2p.opened.begin(); it != g_p2p.opened.end();) {
+    if (used.count(it->first)) { ++it; continue; }
+    cudaIpcCloseMemHandle(it->second);
+    it = g_p2p.opened.erase(it);
+  }
+  int one = 1;
+  MDB_CUDA(cudaMemcpyAsync(g_comm.d_cnt + 4, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+  MDB_NCCL(g_nccl.AllReduce(g_comm.d_cnt + 4, g_comm.d_cnt + 4, 1, ncclInt32, ncclMin, g_comm.comm, st));
+  MDB_CUDA(cudaStreamSynchronize(st));
+  for (void *p : u->deferred_free) cudaFree(p);
+  u->deferred_free.clear();
+  g_p2p.windows_valid = true;
+  return MDB200_OK;
+}
+
+// Opens one refresh round: tells every sender that the ghosts of the previous round are no longer needed.
+int comm_refresh_begin(Unit **us, int n, bool on_comm_stream) {
+  if (!g_p2p.enabled || !g_p2p.windows_valid || n != 1) return MDB200_OK;
+  Unit *u = us[0];
+  cudaSetDevice(u->device);
+  cudaStream_t st = (on_comm_stream && u->cstream) ? u->cstream : u->stream;
+  g_p2p.epoch++;
+  MailPtrs mp;
+  for (int d = 0; d < 6; d++) mp.m[d] = is_remote(u, d) ? g_p2p.src_mail[d] : nullptr;
+  k_p2p_ack<<<1, 1, 0, st>>>(mp, g_p2p.epoch - 1);
+  u->launches++;
+  MDB_CUDA(cudaGetLastError());
+  return MDB200_OK;
+}
 
 int comm_init(Unit **us, int n, int nranks, int rank, const void *unique_id) {
   std::map<int, Unit *> by_id;
@@ -144,6 +370,7 @@ int comm_init(Unit **us, int n, int nranks, int rank, const void *unique_id) {
       g_comm.nranks = nranks;
       g_comm.rank = rank;
     }
+    if (any_remote && !g_p2p.mine) MDB_TRY(p2p_init(us[0]));
   }
   for (int i = 0; i < n; i++) us[i]->comm_ready = true;
   return MDB200_OK;
@@ -239,6 +466,18 @@ int comm_border_refresh(Unit **us, int n, int dir, bool on_comm_stream) {
     if (!is_remote(u, dir)) {
       Unit *d = u->nbr[dir];
       MDB_TRY(ghost_put_to(u, dir, d->q.ptr + d->recv_off[dir], d->q_alt.ptr + d->recv_off[dir], st));
+      continue;
+    }
+    if (g_p2p.enabled && g_p2p.windows_valid && n == 1) {
+      // straight into the neighbour process's ghost window; then wait for our own window of this direction
+      const long long nb = u->n_border[dir];
+      const unsigned grid = (unsigned)std::max<long long>(1, (nb + 255) / 256);
+      k_ghost_put_p2p<<<grid, 256, 0, st>>>(u->q.ptr, u->border[dir].ptr, g_p2p.dst_q[dir], g_p2p.dst_q2[dir], (int)nb,
+                                            u->shift[dir][0], u->shift[dir][1], u->shift[dir][2], g_p2p.mine,
+                                            g_p2p.nbr_mail[dir], dir, g_p2p.epoch, u->ctrl);
+      k_p2p_wait<<<1, 1, 0, st>>>(g_p2p.mine, dir, g_p2p.epoch, u->ctrl);
+      u->launches += 2;
+      MDB_CUDA(cudaGetLastError());
       continue;
     }
     MDB_TRY(u->send_buf.ensure((size_t)u->n_border[dir] + 1));

@@ -15,6 +15,13 @@ int comm_migrate(Unit **us, int n, int dir, const long long *n_leave);
 int comm_border_setup(Unit **us, int n, int dir);
 // per-step ghost refresh in direction dir (fixed windows)
 int comm_border_refresh(Unit **us, int n, int dir, bool on_comm_stream = false);
+// Peer-to-peer ghost refresh between processes (comm.cu): comm_p2p_update exchanges the ghost windows after the
+// border set-up of a rebuild, comm_refresh_begin opens one refresh round (acknowledges the previous one to the
+// senders), comm_p2p_invalidate sends the next refreshes through NCCL until the windows have been exchanged again.
+int comm_p2p_update(Unit **us, int n);
+int comm_refresh_begin(Unit **us, int n, bool on_comm_stream);
+void comm_p2p_invalidate();
+bool comm_p2p_enabled();
 bool comm_multi_process();
 int comm_remote_directions(const Unit *u);  // how many of the 6 neighbours live in another process
 int comm_allreduce_or(Unit **us, int n, int *flag);

@@ -31,7 +31,7 @@ void set_error(const char *fmt, ...);
   } while (0)
 
 // device-side error word (bit set by kernels, read back at sync points)
-enum DevErr : int { DE_TOOFAST = 1, DE_POSITION = 2, DE_CELL = 4, DE_CAPACITY = 8 };
+enum DevErr : int { DE_TOOFAST = 1, DE_POSITION = 2, DE_CELL = 4, DE_CAPACITY = 8, DE_COMM = 16 };
 
 // ---------------------------------------------------------------------------------------------
 // growable device buffer
@@ -40,6 +40,9 @@ template <typename T>
 struct DevBuf {
   T *ptr = nullptr;
   size_t cap = 0;
+  // set for buffers other processes have mapped (comm.cu, peer-to-peer ghost exchange): a replaced allocation
+  // is parked here and freed once the importers have closed it
+  std::vector<void *> *graveyard = nullptr;
   __attribute__((noinline)) int ensure(size_t n, bool keep = false, cudaStream_t st = 0) {
     if (n <= cap) return MDB200_OK;
     // generous head-room: re-allocation (cudaMalloc + cudaFree, both device-synchronising) inside the step
@@ -54,7 +57,10 @@ struct DevBuf {
       MDB_CUDA(cudaMemcpyAsync(np, ptr, cap * sizeof(T), cudaMemcpyDeviceToDevice, st));
       MDB_CUDA(cudaStreamSynchronize(st));
     }
-    if (ptr) cudaFree(ptr);
+    if (ptr) {
+      if (graveyard) graveyard->push_back(ptr);
+      else cudaFree(ptr);
+    }
     ptr = np;
     cap = ncap;
     return MDB200_OK;
@@ -190,6 +196,7 @@ struct Unit {
   Unit *nbr[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // destination when sending in dir
   Unit *src[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // source when receiving in dir (neighbour in opposite dir)
   bool comm_ready = false;
+  std::vector<void *> deferred_free;  // replaced q / q_alt allocations still mapped by neighbour processes
   cudaStream_t cstream = 0;       // second stream for the overlapped ghost exchange (created on demand)
   cudaEvent_t ev_drift = 0, ev_ghost = 0;
 
