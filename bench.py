@@ -83,17 +83,26 @@ class ClockSampler:
                 pass
             time.sleep(0.05)
 
-    def start(self):
+    def prepare(self):
+        """NVML initialisation (can take ~100 ms on a fresh box): done BEFORE the barrier that opens the timed
+        region, so that the other ranks do not spend it waiting for rank 0 inside their timed region."""
         try:
             import pynvml as nv
             nv.nvmlInit()
             self.nv = nv
             self.h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
             self.sm_max = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
-            self.thread = threading.Thread(target=self._loop, daemon=True)
-            self.thread.start()
         except Exception:
+            self.nv = None
+
+    def start(self):
+        if self.nv is None and self.h is None:
+            self.prepare()
+        if self.nv is None:
             self.thread = None
+            return
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -312,6 +321,8 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     unit.set_profiling(1)  # force kernel timed with CUDA events on the unit's stream, no extra syncs
     unit.timers(reset=True)
+    if rank == 0:
+        sampler.prepare()
     barrier()
     if rank == 0:
         sampler.start()
@@ -394,7 +405,10 @@ def run_ours(args):
                        "n_particles": n_total, "rebuilds_in_window": rebuilds, "observations_in_window": n_obs,
                        "l2": "inputs (%.1f GB of positions, momenta and pair list per GPU) far exceed the 126 MB L2; "
                              "no flush needed" % ((n_local * 64 + (2 * npairs * 4.4)) / 1e9),
-                       "parallelism": "domain decomposition, one unit per GPU, NCCL halo" if world > 1 else "single unit",
+                       "parallelism": ("domain decomposition, one unit per GPU; per-step ghost refresh by %s, migration and "
+                                       "reductions over NCCL" % ("NCCL send/recv" if os.environ.get("MDB200_P2P", "1")[:1] == "0"
+                                                                 else "peer-to-peer stores over NVLink (CUDA IPC windows)"))
+                       if world > 1 else "single unit",
                        "timing": "CUDA events on the unit's stream, max over ranks; host wall %.3f s" % (tw1 - tw0)},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
