@@ -83,3 +83,63 @@ def test_reference_arm_nonzero_ranks_exit_quietly():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
     assert res.returncode == 0 and res.stdout.strip() == ""
+
+
+class _FakeUnit:
+    """stands in for capi.Unit: hands out a fixed snapshot (the device side is covered by tests/test_dump_files.py)"""
+
+    def __init__(self, q4, p4, t):
+        self.snap = {"pn": len(t), "q4": q4, "p4": p4, "type": t}
+
+    def snapshot_begin(self):
+        pass
+
+    def snapshot_wait(self):
+        return self.snap
+
+
+def _state(seed, n):
+    rng = np.random.default_rng(seed)
+    q4, p4 = np.zeros((n, 4)), np.zeros((n, 4))
+    q4[:, :3] = rng.uniform(0, 20, (n, 3))
+    p4[:, :3] = rng.normal(size=(n, 3))
+    return q4, p4, np.arange(n, dtype=np.int32) + 1000 * seed
+
+
+def _writer_worker(rank, world, port, outdir):
+    sys.path.insert(0, ROOT)
+    os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port)})
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mdacp_b200 import driver
+        mdm = object.__new__(driver.MDManager)  # host logic only: no device behind it
+        mdm.rank, mdm.num_procs, mdm.num_threads = rank, world, 2
+        mdm.units = [_FakeUnit(*_state(2 * rank + k, 300 + 7 * rank + k)) for k in range(2)]
+        mdm.barrier = dist.barrier
+        mdm._snapshot_open, mdm._cdview_index, mdm._dump_index = False, 0, 0
+        os.chdir(outdir)
+        assert mdm.SaveAsCdviewSequential() == "conf0000.cd"   # mdmanager.cc:80-105
+        assert mdm.SaveAsDumpFileSequential() == "conf0000.dump"  # mdmanager.cc:465-505
+        assert mdm.SaveAsCdviewSequential() == "conf0001.cd"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_rank_serialised_writers(tmp_path):
+    """SaveAsCdview / SaveAsDumpFile: rank 0 truncates, then the ranks append in rank order, each its units in
+    order -- the file equals what one process holding all four units would have written."""
+    sys.path.insert(0, ROOT)
+    from mdacp_b200 import hostlib
+    world = 2
+    mp.spawn(_writer_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    cd, dump = str(tmp_path / "expect.cd"), str(tmp_path / "expect.dump")
+    first = True
+    for rank in range(world):
+        for k in range(2):
+            q4, p4, t = _state(2 * rank + k, 300 + 7 * rank + k)
+            hostlib.save_cdview(cd, q4, p4, t, append=not first)
+            hostlib.save_dump(dump, q4, p4, append=not first)
+            first = False
+    assert (tmp_path / "conf0000.cd").read_bytes() == open(cd, "rb").read()
+    assert (tmp_path / "conf0001.cd").read_bytes() == open(cd, "rb").read()
+    assert (tmp_path / "conf0000.dump").read_bytes() == open(dump, "rb").read()
