@@ -370,7 +370,14 @@ int comm_init(Unit **us, int n, int nranks, int rank, const void *unique_id) {
       g_comm.nranks = nranks;
       g_comm.rank = rank;
     }
-    if (any_remote && !g_p2p.mine) MDB_TRY(p2p_init(us[0]));
+    if (any_remote && !g_p2p.mine) {
+      MDB_TRY(p2p_init(us[0]));
+    } else if (any_remote && g_p2p.enabled) {
+      // a later unit of the same process (the mailboxes and the neighbours stay): its buffers will be mapped too
+      us[0]->q.graveyard = &us[0]->deferred_free;
+      us[0]->q_alt.graveyard = &us[0]->deferred_free;
+      g_p2p.windows_valid = false;
+    }
   }
   for (int i = 0; i < n; i++) us[i]->comm_ready = true;
   return MDB200_OK;
@@ -378,6 +385,10 @@ int comm_init(Unit **us, int n, int nranks, int rank, const void *unique_id) {
 
 int comm_release(Unit *u) {
   u->comm_ready = false;
+  for (void *p : u->deferred_free) cudaFree(p);
+  u->deferred_free.clear();
+  u->q.graveyard = u->q_alt.graveyard = nullptr;
+  if (g_p2p.enabled && g_comm.nranks > 1) g_p2p.windows_valid = false;  // the windows pointed into this unit's peers
   return MDB200_OK;
 }
 
