@@ -24,6 +24,11 @@ CASES = {
     "nosehoover": ({"DumpInit": "Benchmark", "SystemSize": 20, "TimeStep": 0.002, "InitialVelocity": 1.5,
                     "ControlTemperature": "yes", "HeatbathType": "NoseHoover", "AimedTemperature": 1.0,
                     "HeatbathTau": 0.1}, 1, 60),
+    # MDManager::ChangeScale in the middle of the run (compression, 8 units; expansion, 1 unit)
+    "scale8": ({"DumpInit": "Benchmark", "SystemSize": 24, "TimeStep": 0.004, "InitialVelocity": 2.0,
+                "DumpChangeScaleAt": 30, "DumpChangeScaleAlpha": 0.97}, 8, 70),
+    "scale1": ({"DumpInit": "Benchmark", "SystemSize": 18, "TimeStep": 0.004, "InitialVelocity": 2.0,
+                "DumpChangeScaleAt": 25, "DumpChangeScaleAlpha": 1.04}, 1, 70),
 }
 
 
