@@ -8,6 +8,7 @@
 #include <time.h>
 #include <algorithm>
 #include <map>
+#include <mutex>
 #include <set>
 #include <utility>
 #include <vector>
@@ -596,6 +597,8 @@ int mdb200_create(const mdb200_params *params, int device, mdb200_unit **out) {
   // by the stream itself when they hand particles to each other
   {
     static std::map<int, cudaStream_t> dev_stream;
+    static std::mutex dev_stream_mutex;  // mdb200_create may be called from one host thread per unit
+    std::lock_guard<std::mutex> lock(dev_stream_mutex);
     auto it = dev_stream.find(device);
     if (it == dev_stream.end()) {
       cudaStream_t st;
