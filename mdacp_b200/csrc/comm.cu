@@ -256,9 +256,16 @@ int comm_p2p_update(Unit **us, int n) {
   Unit *u = us[0];
   cudaSetDevice(u->device);
   cudaStream_t st = u->stream;
+  // A process that cannot export or map a window does not fail the run: it keeps taking part in the exchanges
+  // below and reports ok = 0 through the closing all-reduce, after which EVERY process falls back to NCCL.
+  int ok = 1;
   cudaIpcMemHandle_t hq, hq2;
-  MDB_CUDA(cudaIpcGetMemHandle(&hq, u->q.ptr));
-  MDB_CUDA(cudaIpcGetMemHandle(&hq2, u->q_alt.ptr));
+  memset(&hq, 0, sizeof(hq));
+  memset(&hq2, 0, sizeof(hq2));
+  if (cudaIpcGetMemHandle(&hq, u->q.ptr) != cudaSuccess || cudaIpcGetMemHandle(&hq2, u->q_alt.ptr) != cudaSuccess) {
+    ok = 0;
+    cudaGetLastError();
+  }
   std::set<std::string> used = g_p2p.mail_keys;
   for (int dir = 0; dir < 6; dir++) {
     g_p2p.dst_q[dir] = g_p2p.dst_q2[dir] = nullptr;
@@ -274,14 +281,15 @@ int comm_p2p_update(Unit **us, int n) {
     MDB_NCCL(g_nccl.GroupEnd());
     MDB_CUDA(cudaMemcpyAsync(&w[1], g_p2p.d_win + 1, sizeof(Window), cudaMemcpyDeviceToHost, st));
     MDB_CUDA(cudaStreamSynchronize(st));
-    if (w[1].cnt != u->n_border[dir]) {
-      set_error("ghost window of direction %d holds %lld rows, %lld are sent", dir, w[1].cnt, u->n_border[dir]);
-      return MDB200_ECOMM;
-    }
+    if (!ok) continue;
     void *a = nullptr, *b = nullptr;
     std::string ka, kb;
-    MDB_TRY(p2p_open(w[1].hq, &a, &ka));
-    MDB_TRY(p2p_open(w[1].hq2, &b, &kb));
+    if (w[1].cnt != u->n_border[dir] || p2p_open(w[1].hq, &a, &ka) != MDB200_OK ||
+        p2p_open(w[1].hq2, &b, &kb) != MDB200_OK) {
+      ok = 0;
+      cudaGetLastError();
+      continue;
+    }
     used.insert(ka);
     used.insert(kb);
     g_p2p.dst_q[dir] = static_cast<double4 *>(a) + w[1].off;
@@ -294,13 +302,18 @@ int comm_p2p_update(Unit **us, int n) {
     cudaIpcCloseMemHandle(it->second);
     it = g_p2p.opened.erase(it);
   }
-  int one = 1;
-  MDB_CUDA(cudaMemcpyAsync(g_comm.d_cnt + 4, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+  MDB_CUDA(cudaMemcpyAsync(g_comm.d_cnt + 4, &ok, sizeof(int), cudaMemcpyHostToDevice, st));
   MDB_NCCL(g_nccl.AllReduce(g_comm.d_cnt + 4, g_comm.d_cnt + 4, 1, ncclInt32, ncclMin, g_comm.comm, st));
+  MDB_CUDA(cudaMemcpyAsync(&ok, g_comm.d_cnt + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
   MDB_CUDA(cudaStreamSynchronize(st));
   for (void *p : u->deferred_free) cudaFree(p);
   u->deferred_free.clear();
-  g_p2p.windows_valid = true;
+  g_p2p.windows_valid = ok != 0;
+  if (!ok) {  // some process could not set its windows up: every process refreshes through NCCL from here on
+    g_p2p.enabled = false;
+    u->q.graveyard = u->q_alt.graveyard = nullptr;
+    if (getenv("MDB200_DEBUG")) fprintf(stderr, "[mdb200] rank %d: peer-to-peer ghost refresh switched off\n", g_comm.rank);
+  }
   return MDB200_OK;
 }
 
