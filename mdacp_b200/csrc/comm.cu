@@ -312,6 +312,11 @@ int comm_p2p_update(Unit **us, int n) {
   if (!ok) {  // some process could not set its windows up: every process refreshes through NCCL from here on
     g_p2p.enabled = false;
     u->q.graveyard = u->q_alt.graveyard = nullptr;
+    for (auto it = g_p2p.opened.begin(); it != g_p2p.opened.end();) {  // nothing of the neighbours stays mapped
+      if (g_p2p.mail_keys.count(it->first)) { ++it; continue; }
+      cudaIpcCloseMemHandle(it->second);
+      it = g_p2p.opened.erase(it);
+    }
     if (getenv("MDB200_DEBUG")) fprintf(stderr, "[mdb200] rank %d: peer-to-peer ghost refresh switched off\n", g_comm.rank);
   }
   return MDB200_OK;
