@@ -155,6 +155,28 @@ def cubic_units(cores):
     return n ** 3
 
 
+def unit_grid_for(cores):
+    """Unit grid a x b x c (a <= b <= c <= 2a) with the most units <= cores: the sub-boxes stay cubes when the box is
+    a x b x c unit edges, so every host core gets a unit (16 cores -> 2x2x4, not only 2x2x2)."""
+    best = (1, 1, 1)
+    for a in range(1, 9):
+        for b in range(a, 2 * a + 1):
+            for c in range(b, 2 * a + 1):
+                if a * b * c <= cores and (a * b * c, -c) > (best[0] * best[1] * best[2], -best[2]):
+                    best = (a, b, c)
+    return best
+
+
+def mem_available_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return float(line.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
 def run_reference_cpu(unit_length, n_gpus_equiv, therm, loop, timeout=1500):
     """Times the reference's own CPU implementation (oracle/_ref, unmodified sources) on the host
     cores: Mode=Benchmark on the SAME system as the GPU arm (global box = the GPU run's box), with
@@ -162,23 +184,19 @@ def run_reference_cpu(unit_length, n_gpus_equiv, therm, loop, timeout=1500):
     from oracle import refdump
     from mdacp_b200 import driver
     cores = host_cores()
-    units = cubic_units(cores)
     # bounded sample: the CPU cannot hold the N-GPU weak-scaled system (N x 16 M particles), and its
-    # throughput does not grow with the box, so every N is compared with the one-GPU-sized box
-    g = [1, 1, 1]
-    L = [unit_length * g[0], unit_length * g[1], unit_length * g[2]]
-    cubic_box = (L[0] == L[1] == L[2])
-    if not cubic_box:
-        # the reference can only make cubic units: take the largest grid whose units are cubes
-        lg = [int(round(x / min(L))) for x in L]
-        k = 1
-        while (k + 1) ** 3 * lg[0] * lg[1] * lg[2] <= cores:
-            k += 1
-        lgrid = [k * x for x in lg]
-        units = lgrid[0] * lgrid[1] * lgrid[2]
-    else:
-        k = round(units ** (1.0 / 3.0))
-        lgrid = [k, k, k]
+    # throughput does not grow with the box, so every N is compared with a box of one-GPU size or a small multiple:
+    # CPU units of edge unit_length / 2 (what 2x2x2 units make of the one-GPU box), one per host core on the largest
+    # grid that keeps them cubes -- 8 cores: the one-GPU box itself; 16 cores: 2x2x4 units, i.e. twice that box.
+    lgrid = list(unit_grid_for(cores)) if cores >= 8 else [2, 2, 2]
+    units = lgrid[0] * lgrid[1] * lgrid[2]
+    # at most ~2.1 one-GPU systems in total (many-core hosts get smaller units rather than a bigger box)
+    n_cap = 2.1 * DENSITY * unit_length ** 3
+    edge = min(unit_length / 2.0, (n_cap / DENSITY / units) ** (1.0 / 3.0))
+    need_gb = 0.8e-6 * DENSITY * edge ** 3 * units  # measured: 12.2 GB for 16 M particles
+    if need_gb * 1.5 > mem_available_gb() > 0.0:
+        lgrid, units, edge = [2, 2, 2], 8, unit_length / 2.0
+    L = [edge * lgrid[0], edge * lgrid[1], edge * lgrid[2]]
     n_total = int(L[0] * L[1] * L[2] * DENSITY)
     per_unit = n_total / units * 1.35 + 50000  # locals + ghosts
     exe = refdump.REF_AVX2 if per_unit < 950000 else refdump.REF_AVX2_BIG
