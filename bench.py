@@ -465,9 +465,10 @@ def main():
             "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": (r["sec"] / r["steps"] * 1e3) if r.get("sec") else None, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "benchmark.cfg-shaped LJ FCC on the host CPU, same box as the %d-GPU run "
-                                   "(UnitLength=%g per GPU), cutoff 3.0; each run a bounded sample: %d thermalise + %d "
-                                   "timed steps" % (args.gpus, args.unit_length, therm, loop)},
+            "config": {"workload": "benchmark.cfg-shaped LJ FCC on the host CPU (reference arm of the %d-GPU run): one "
+                                   "cubic unit per host core, units of the 2x2x2 split of the one-GPU box (UnitLength=%g "
+                                   "per GPU), cutoff 3.0; each run a bounded sample: %d thermalise + %d timed steps" % (
+                                       args.gpus, args.unit_length, therm, loop)},
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": n_units, "kind": r["kind"],
                              "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
