@@ -94,6 +94,16 @@ struct PhaseTimer {
   }
 };
 
+static void derive_timer_resolve(Unit *u) {
+  if (!u->dev_pending) return;
+  float ms = 0.f;
+  if (cudaEventSynchronize(u->dev[1]) == cudaSuccess && cudaEventElapsedTime(&ms, u->dev[0], u->dev[1]) == cudaSuccess) {
+    u->derive_ms += ms;
+    u->derive_launches++;
+  }
+  u->dev_pending = false;
+}
+
 // level-1 profiling: two events around the force kernel, resolved at the next host sync
 static void force_timer_begin(Unit *u) {
   if (u->profiling != 1) return;
@@ -117,6 +127,23 @@ static void force_timer_resolve(Unit *u) {
     u->force_launches++;
   }
   u->fev_pending = false;
+}
+
+// the same around the inner-list derivation (reported by mdb200_list_stats)
+static void derive_timer_begin(Unit *u) {
+  if (u->profiling != 1) return;
+  if (!u->dev_ready) {
+    cudaEventCreate(&u->dev[0]);
+    cudaEventCreate(&u->dev[1]);
+    u->dev_ready = true;
+  }
+  derive_timer_resolve(u);
+  cudaEventRecord(u->dev[0], u->stream);
+}
+static void derive_timer_end(Unit *u) {
+  if (u->profiling != 1) { u->derive_launches++; return; }
+  cudaEventRecord(u->dev[1], u->stream);
+  u->dev_pending = true;
 }
 
 // make every stream of the group wait for everything queued so far on the others
@@ -355,7 +382,7 @@ static int send_border_particles(Unit **us, int n) {
 // (kept in the group's first unit: inner_left = remaining distance budget, inner_delta = the delta the next
 // derivation will use, 0 = pruning off)
 static int inner_steps() {           // steps one derivation should last (MDB200_INNER_STEPS overrides)
-  static const int v = getenv("MDB200_INNER_STEPS") ? std::max(6, atoi(getenv("MDB200_INNER_STEPS"))) : 32;
+  static const int v = getenv("MDB200_INNER_STEPS") ? std::max(4, atoi(getenv("MDB200_INNER_STEPS"))) : 16;
   return v;
 }
 
@@ -395,9 +422,10 @@ static int any_expired(Unit **us, int n, int *expired) {
     us[0]->inner_delta = 0.0;
   } else {
     us[0]->inner_left -= per_step;
-    // next derivation: a delta that lasts INNER_STEPS steps, at most half the skin; not worth it below 6 steps
+    // next derivation: a delta that lasts INNER_STEPS steps, at most half the skin; not worth it below 4 steps
+    static const bool no_prune = getenv("MDB200_NO_PRUNE") != nullptr;
     const double want = inner_steps() * per_step, cap = 0.5 * us[0]->c.BL;
-    us[0]->inner_delta = (6.0 * per_step > cap || getenv("MDB200_NO_PRUNE")) ? 0.0 : std::min(want, cap);
+    us[0]->inner_delta = (4.0 * per_step > cap || no_prune) ? 0.0 : std::min(want, cap);
   }
   return MDB200_OK;
 }
@@ -424,20 +452,17 @@ static int calculate(Unit **us, int n) {
   if (expired || ct)
     for (int i = 0; i < n; i++) MDB_TRY(materialize(us[i]));
   if (expired) MDB_TRY(make_pairlist(us, n));
-  // which list the fused NVE launch walks: the inner one while its budget lasts and every unit has one,
-  // otherwise the outer one -- deriving a fresh inner list on the side when pruning is worthwhile
-  bool all_inner = true, can_prune = true;
-  for (int i = 0; i < n; i++) {
-    all_inner = all_inner && us[i]->inner_valid;
-    // the deriving launch keeps a 64-bit keep mask per lane: 2 bits per step pair, i.e. rows of <= 256 entries
-    can_prune = can_prune && us[i]->max_row <= 248;
+  // The force kernel walks the INNER list (force.cu): the entries of the pair list within cutoff + delta when it
+  // was derived.  A new one is due when there is none (rebuild, momenta or positions changed outside the step) or
+  // when the velocity budget of a pruned one is used up; it is derived below, once the ghosts of this step are in.
+  bool derive = false;
+  for (int i = 0; i < n; i++) derive = derive || !us[i]->inner_valid;
+  if (!derive && us[0]->inner_keep < us[0]->c.SL && us[0]->inner_left < 0.0) derive = true;
+  double keep_len = us[0]->c.SL;
+  if (derive) {
+    if (us[0]->inner_delta > 0.0) keep_len = std::min(us[0]->prm.cutoff + us[0]->inner_delta, us[0]->c.SL);
+    us[0]->inner_left = us[0]->inner_delta;
   }
-  int inner = 0;
-  double keep_len = 0.0;
-  if (!ct && all_inner && us[0]->inner_left >= 0.0) inner = 1;
-  else if (!ct && can_prune && us[0]->inner_delta > 0.0) { inner = 2; keep_len = us[0]->prm.cutoff + us[0]->inner_delta; }
-  if (inner == 2) us[0]->inner_left = us[0]->inner_delta;
-  for (int i = 0; i < n; i++) us[i]->inner_valid = (inner != 0);
   for (int i = 0; i < n; i++) {
     DeviceGuard g(us[i]->device);
     PhaseTimer t(us[i], PH_INTEG);
@@ -453,7 +478,7 @@ static int calculate(Unit **us, int n) {
   // directions (2x1x1 units: no gain) and ~0.5 ms with 6 (2x2x2: 4.61 -> 4.34 ms/step), so overlap from 4 up.
   const char *ov_env = getenv("MDB200_OVERLAP");  // 0 / 1 forces it off / on
   const bool ov_want = ov_env ? (ov_env[0] == '1') : (n == 1 && comm_remote_directions(us[0]) >= 4);
-  const bool overlap = !ct && n == 1 && comm_multi_process() && us[0]->profiling < 2 && us[0]->nwarps > 0 && ov_want;
+  const bool overlap = !ct && n == 1 && comm_multi_process() && us[0]->profiling < 2 && us[0]->ntiles > 0 && ov_want;
   if (overlap) {
     Unit *u = us[0];
     DeviceGuard g(u->device);
@@ -477,6 +502,16 @@ static int calculate(Unit **us, int n) {
     int r = send_border_particles(us, n);
     for (auto *x : tm) delete x;
     MDB_TRY(r);
+  }
+  if (derive) {
+    for (int i = 0; i < n; i++) {
+      Unit *u = us[i];
+      DeviceGuard g(u->device);
+      if (overlap) MDB_CUDA(cudaStreamWaitEvent(u->stream, u->ev_ghost, 0));  // the derivation reads the ghosts
+      derive_timer_begin(u);
+      MDB_TRY(derive_inner(u, keep_len));
+      derive_timer_end(u);
+    }
   }
   if (ct && us[0]->prm.heatbath_type == MDB200_HT_NOSEHOOVER) {
     // MDManager::CalculateNoseHoover (mdmanager.cc:160-175)
@@ -512,9 +547,9 @@ static int calculate(Unit **us, int n) {
     Unit *u = us[0];
     DeviceGuard g(u->device);
     force_timer_begin(u);
-    MDB_TRY(force_kick_drift(u, predrift, 1, inner, keep_len));
+    MDB_TRY(force_kick_drift(u, predrift, 1));
     MDB_CUDA(cudaStreamWaitEvent(u->stream, u->ev_ghost, 0));
-    MDB_TRY(force_kick_drift(u, predrift, 2, inner, keep_len));
+    MDB_TRY(force_kick_drift(u, predrift, 2));
     force_timer_end(u);
     u->predrifted = predrift;
   } else {
@@ -526,10 +561,10 @@ static int calculate(Unit **us, int n) {
         PhaseTimer t(us[i], PH_FORCE);
         force_timer_begin(us[i]);
         if (split_test) {  // test hook: the interior / boundary launches of the overlapped path, back to back
-          MDB_TRY(force_kick_drift(us[i], predrift, 1, inner, keep_len));
-          MDB_TRY(force_kick_drift(us[i], predrift, 2, inner, keep_len));
+          MDB_TRY(force_kick_drift(us[i], predrift, 1));
+          MDB_TRY(force_kick_drift(us[i], predrift, 2));
         } else {
-          MDB_TRY(force_kick_drift(us[i], predrift, 0, inner, keep_len));
+          MDB_TRY(force_kick_drift(us[i], predrift, 0));
         }
         force_timer_end(us[i]);
         us[i]->predrifted = predrift;
@@ -632,9 +667,9 @@ int mdb200_destroy(mdb200_unit *h) {
   for (int d = 0; d < 6; d++) u->border[d].release();
   u->send_buf.release(); u->mig_send_q.release(); u->mig_send_p.release(); u->mig_recv_q.release();
   u->mig_recv_p.release(); u->mig_send_t.release(); u->mig_recv_t.release();
-  u->row_count.release(); u->row_cls.release(); u->list_in.release(); u->warp_len_in.release(); u->warp_flag.release(); u->warp_order.release();
+  u->row_count.release(); u->list_in.release(); u->fw_len_in.release(); u->tile_fw0.release(); u->tile_flag.release(); u->tile_order.release();
   if (u->cstream) { cudaStreamDestroy(u->cstream); cudaEventDestroy(u->ev_drift); cudaEventDestroy(u->ev_ghost); }
-  u->warp_len.release(); u->warp_off.release(); u->list.release();
+  u->fw_len.release(); u->fw_off.release(); u->list.release();
   u->disp.release(); u->cand.release(); u->partial.release();
   u->snap_q.release(); u->snap_p.release(); u->snap_t.release();
   if (u->snap_stream) {
@@ -1026,6 +1061,9 @@ int mdb200_timers(mdb200_unit *h, double out_ms[6], long long out_counts[2], int
     for (int k = 0; k < 6; k++) u->t_ms[k] = 0.0;
     u->launches = 0;
     u->force_launches = 0;
+    derive_timer_resolve(u);
+    u->derive_ms = 0.0;
+    u->derive_launches = 0;
   }
   return MDB200_OK;
 }
@@ -1039,23 +1077,27 @@ int mdb200_list_stats(mdb200_unit *h, double out[8]) {
   Unit *u = &h->u;
   DeviceGuard g(u->device);
   for (int k = 0; k < 8; k++) out[k] = 0.0;
-  out[0] = (double)u->nwarps;
-  out[1] = (double)u->list_entries;   // padded list words
+  out[0] = (double)u->nfw;            // force-warps
+  out[1] = (double)u->list_entries;   // stored 16-bit entries of the outer list (padded)
   out[2] = (double)u->max_row;
   out[4] = (double)kG;
+  derive_timer_resolve(u);
+  out[6] = u->derive_ms;              // inner-list derivations: device time (profiling level 1) and count
+  out[7] = (double)u->derive_launches;
   if (u->pn > 0 && u->list_initialized) {
     std::vector<int> rc((size_t)u->pn);
     MDB_CUDA(cudaMemcpyAsync(rc.data(), u->row_count.ptr, sizeof(int) * rc.size(), cudaMemcpyDeviceToHost, u->stream));
     MDB_CUDA(cudaStreamSynchronize(u->stream));
     double s = 0;
     for (size_t k = 0; k < rc.size(); k++) s += rc[k];
-    out[3] = s;                       // sum of row lengths (unpadded entries)
-    std::vector<int> wl((size_t)u->nwarps);
-    MDB_CUDA(cudaMemcpyAsync(wl.data(), u->warp_len.ptr, sizeof(int) * wl.size(), cudaMemcpyDeviceToHost, u->stream));
+    out[3] = s;                       // sum of outer row lengths (unpadded entries)
+    std::vector<int> wl((size_t)u->nfw);
+    const int *src = u->inner_valid ? u->fw_len_in.ptr : u->fw_len.ptr;
+    MDB_CUDA(cudaMemcpyAsync(wl.data(), src, sizeof(int) * wl.size(), cudaMemcpyDeviceToHost, u->stream));
     MDB_CUDA(cudaStreamSynchronize(u->stream));
     double w = 0;
     for (size_t k = 0; k < wl.size(); k++) w += wl[k];
-    out[5] = 32.0 * w;                // list words the force kernel walks (rows padded to their warp's steps)
+    out[5] = 32.0 * w;                // entries the force kernel walks (inner list if there is one; rows padded)
   }
   return MDB200_OK;
 }

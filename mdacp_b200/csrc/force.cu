@@ -3,125 +3,101 @@
 //   for each listed pair (i,j): d = q_j - q_i, r2 = |d|^2; if r2 > CL2 the pair contributes 0;
 //   r6 = r2^3; df = ((24 r6 - 48)/(r6 r6 r2) + 8 C2) dt; p_i += df d; p_j -= df d.
 //
-// B200 formulation.
-//  * FULL neighbour list, no atomics: every local's momentum is owned by one lane group, so the summation
-//    order is deterministic and ghost momenta are never written (they are scratch in the reference,
-//    fcalculator.cc:273-275 / SURVEY.md Q8).  RED.ADD.F64 for the reaction term of a half list would cost
-//    ~3 P atomics per particle at ~1.3 clk/lane/SM -- several times this whole kernel.
-//  * kG = 4 LANES PER LOCAL (unit.h): a warp owns 8 consecutive cell-sorted locals; the 4 lanes of a group
-//    take one entry each of that local's row per step and a 2-stage shuffle reduction combines them at the
-//    end.  Why: ncu shows the kernel bound by the L1 data pipe on the scattered gather of partner positions
-//    (FP64 pipe below 50 %; profiles/r01_force_*_ncu.txt, r01c_force_ncu.txt), and the cost of a warp-wide
-//    gather of 32-byte records is set by conflicts between the four 32-byte sector slots of a line
-//    (profiles/r01_ubench_gather.txt).  Rows are therefore stored in "rainbow" order (cells.cu: RowOrder):
-//    at every step the 4 lanes of a local take partners of 4 different slots (index mod 4).
-//  * one 256-bit load per partner (LDG.E.256); list words for two steps come from one 8-byte load per lane
-//    (a contiguous 256-byte run per warp); locals cell-sorted.
-//  * the cutoff test runs on the integer pipe (bit-pattern compare of the non-negative r2), keeping the
-//    FP64 pipe for arithmetic.
+// B200 formulation (round 2; tile.cuh has the why).
+//  * One block per TILE of up to 3 x 3 x 3 cells: the positions of the tile and of its one-cell halo are staged
+//    in shared memory once (32-byte records), partners are 16-bit indices into that staged array, and every
+//    gather is two shared-memory loads.  Round 1 gathered from global memory and was bound by the L1 data pipe
+//    at 20 wavefronts per warp-gather (profiles/r01c_force_ncu.txt); here a gather costs 8.
+//  * FULL neighbour list, no atomics: every local's momentum is owned by one lane group, the summation order is
+//    deterministic and ghost momenta are never written (they are scratch in the reference, fcalculator.cc:273-275).
+//    red.global.add.f64 for the reaction term of a half list was measured at 1.2-1.3 clk per reduction per SM
+//    (profiles/r02_ubench_red_f64.txt): ~180 clk per local against ~30 for this whole kernel.
+//  * kG = 4 lanes per local; a force-warp owns 8 consecutive staged interior locals.  A staged record is
+//    (x, y, z, y): EVEN lane groups read the low half (x, y) with one LDS.128 and z with one LDS.64, ODD groups
+//    read the high half (z, y) first and x second, and simply compute with x and z exchanged (r2 and the three
+//    accumulators do not care; the writer lane swaps them back).  The 8 lanes of a quarter-warp then touch 8
+//    different 16-byte bank groups as long as the 4 lanes of a group read records of 4 different classes
+//    (staged index mod 4) -- which is how k_tile_derive deals the rows out ("rainbow" order).
+//  * the cutoff test is one integer compare on the high word of r2 (exact when the low word of CL2 is zero, as
+//    for cutoff 3.0 and 2.5; a full 64-bit compare otherwise), and zeroes df with two integer selects.
+//  * list words for four steps come from one 8-byte load per lane (a contiguous 256-byte run per warp), loaded
+//    one chunk ahead and prefetched three ahead.
 //
 // Roofline: algorithmic HBM bytes per particle = 4 B x P (half-list indices) + 96 B
 // (q read, p read + write), 30 flop per listed unordered pair.
 #include <stdlib.h>
 #include <utility>
-#include "unit.h"
+#include "tile.cuh"
 
 namespace mdb {
 
-// tuning knobs (scripts/build_variants.sh)
-#ifndef FORCE_UNROLL
-#define FORCE_UNROLL 1
-#endif
-#ifndef FORCE_MINBLK
-#define FORCE_MINBLK 10
-#endif
-#ifndef FORCE_PF_L1
-#define FORCE_PF_L1 2
-#endif
-#ifndef FORCE_PRUNE_MINBLK
-#define FORCE_PRUNE_MINBLK 8
-#endif
-#ifndef FORCE_TPB
-#define FORCE_TPB 128
-#endif
+TileGrid tile_grid(const Unit *u);  // tile_search.cu
 
-// 1 / x: hardware seed (MUFU.RCP64H) + one cubic (Halley-type) refinement y (1 + e + e^2);
-// GUARD adds one linear Newton step (2 DFMA) that makes the result independent of the seed quality.
-template <bool GUARD>
-__device__ __forceinline__ double fast_rcp(double x) {
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-x, y, 1.0);
-  double t = fma(e, e, e);
-  y = fma(y, t, y);
-  if (GUARD) {
-    e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-  }
-  return y;
-}
+#ifndef FORCE_TPB
+#define FORCE_TPB 512
+#endif
+#ifndef DERIVE_TPB
+#define DERIVE_TPB 384
+#endif
 
 struct ForceConsts {
-  double keep2;   // PRUNE: (cutoff + delta)^2
   double dt2;     // dt / 2
   double CL2;
   double c24dt;   // 24 dt
   double c48dt;   // 48 dt
   double c2x8dt;  // 8 C2 dt
-  double dt;
-  double c2x8;
+  int cl2_hi;     // high word of CL2
+  int exact_cut;  // low word of CL2 != 0: compare all 64 bits
 };
 
-// VARIANT 0: reference expression with an IEEE division (validation baseline)
-// VARIANT 1: s = 1/r2 (seed + cubic + guard step), df = s^4 (24 - 48 s^3) dt + 8 C2 dt
-// VARIANT 2: same without the guard step
-template <int VARIANT>
-__device__ __forceinline__ double pair_df(double r2, const ForceConsts &fc) {
-  if (VARIANT == 0) {
-    double r6 = r2 * r2 * r2;
-    return ((24.0 * r6 - 48.0) / (r6 * r6 * r2) + fc.c2x8) * fc.dt;
-  } else {
-    double s = fast_rcp<VARIANT == 1>(r2);
-    double s2 = s * s;
-    double s3 = s2 * s;
-    double s4 = s2 * s2;
-    double t = fma(-fc.c48dt, s3, fc.c24dt);
-    return fma(s4, t, fc.c2x8dt);
-  }
+__device__ __forceinline__ void lds128(unsigned a, double &x, double &y) {
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
+}
+__device__ __forceinline__ double lds64(unsigned a) {
+  double x;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(a));
+  return x;
 }
 
-__device__ __forceinline__ void ld_q256(const double4 *p, double &x, double &y, double &z) {
-  double w;
-  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(p));
-  (void)w;
+// 1 / x: hardware seed (MUFU.RCP64H, ~2^-20) + one cubic (Halley-type) refinement y (1 + e + e^2): ~2^-60
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x, y, 1.0);
+  const double t = fma(e, e, e);
+  return fma(y, t, y);
 }
 
-
-// list words are streamed once (L1 eviction hints on them or on the positions made no difference, see
-// profiles/r01_force_experiments.md)
-__device__ __forceinline__ uint2 ld_list(const uint2 *p) { return __ldg(p); }
-
-// returns the bit pattern of r2 (non-negative doubles order like their bit patterns)
-template <int VARIANT>
-__device__ __forceinline__ long long pair_accumulate(double ax, double ay, double az, double jx, double jy,
-                                                     double jz, long long cl2b, const ForceConsts &fc, double &fx,
-                                                     double &fy, double &fz) {
-  const double dx = jx - ax, dy = jy - ay, dz = jz - az;
-  const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-  double df = pair_df<VARIANT>(r2, fc);
+// one listed entry: o0 / o1 = shared-memory addresses of the record's first / second half as this lane reads it
+template <bool EXACT>
+__device__ __forceinline__ void pair_kick(unsigned o0, unsigned o1, double a0, double a1, double a2, const ForceConsts &fc,
+                                          double &f0, double &f1, double &f2) {
+  double j0, j1;
+  lds128(o0, j0, j1);
+  const double j2 = lds64(o1);
+  const double d0 = j0 - a0, d1 = j1 - a1, d2 = j2 - a2;
+  const double r2 = fma(d2, d2, fma(d1, d1, d0 * d0));
+  // s = 1 / r2; df = s^4 (24 - 48 s^3) dt + 8 C2 dt  (= ((24 r6 - 48) / (r6 r6 r2) + 8 C2) dt)
+  const double s = fast_rcp(r2);
+  const double s2 = s * s;
+  const double s3 = s2 * s;
+  const double s4 = s2 * s2;
+  const double t = fma(-fc.c48dt, s3, fc.c24dt);
+  double df = fma(s4, t, fc.c2x8dt);
   // r2 > CL2: the pair contributes nothing (fcalculator.cc:209-211); also kills the sentinel padding
-  const long long r2b = __double_as_longlong(r2);
-  if (r2b > cl2b) df = 0.0;
-  fx = fma(df, dx, fx);
-  fy = fma(df, dy, fy);
-  fz = fma(df, dz, fz);
-  return r2b;
+  bool in;
+  if (EXACT) in = __double_as_longlong(r2) <= __double_as_longlong(fc.CL2);
+  else in = __double2hiint(r2) < fc.cl2_hi;
+  df = __hiloint2double(in ? __double2hiint(df) : 0, in ? __double2loint(df) : 0);
+  f0 = fma(df, d0, f0);
+  f1 = fma(df, d1, f1);
+  f2 = fma(df, d2, f2);
 }
 
 // MODE 0: impulses to fout (parity probe).  MODE 1: kick, p += F dt (ForceCalculator::CalculateForce).
 // MODE 2: kick fused with the second half drift of MDManager::CalculateForce (mdmanager.cc:151-157):
 //   q_out[a] = q[a] + p_new dt/2 with the same non-fused mul/add as k_drift_half (bit-identical), written to
-//   the OTHER position buffer because q is still being gathered by other warps; the caller swaps the
+//   the OTHER position buffer because q is still being staged by other blocks; the caller swaps the
 //   buffers.  It also leaves max |p_new|^2 in ctrl->vmax2_bits for the next step's velocity-budget test
 //   (pairlist.cc:48-65), so that test needs no pass of its own.
 // MODE 3: as MODE 2 plus the FIRST half drift of the NEXT step (mdmanager.cc:128-131), speculatively:
@@ -129,216 +105,291 @@ __device__ __forceinline__ long long pair_accumulate(double ax, double ay, doubl
 //   k_drift_half passes.  The end-of-step positions q[a] + p_new dt/2 are not stored; whoever needs them
 //   (rebuild, observation, download, displacement test) recomputes them bit-identically from the untouched
 //   input buffer and p_new (api.cu:materialize, integrate.cu).
-// PRUNE (with MODE 2 / 3): the launch walks the full ("outer") list and, on the side, derives the INNER list:
-//   the entries with r2 <= keep2 = (cutoff + delta)^2, re-dealt in rainbow order into list_in at the same row
-//   offsets, with their own step counts in warp_len_in.  25 % of the listed pairs lie between the cutoff and
-//   the search length and contribute exactly zero; until some pair can have closed the distance delta
-//   (velocity budget kept by the host, api.cu) the following launches walk the inner list and give
-//   identical contributions (the dropped ones are exact zeros) at ~0.8x the gathers.
 enum { FORCE_IMPULSE = 0, FORCE_KICK = 1, FORCE_KICK_DRIFT = 2, FORCE_KICK_DRIFT2 = 3 };
-#define FORCE_PARAMS                                                                                              \
-  const double4 *__restrict__ q, double4 *__restrict__ p, double *__restrict__ fout,                             \
-      const unsigned *__restrict__ list, const long long *__restrict__ warp_off, const int *__restrict__ warp_len, \
-      const int *__restrict__ ref_of_slot, int pn, long long nwarps, double4 *__restrict__ q_out, Ctrl *ctrl,    \
-      unsigned *__restrict__ list_in, int *__restrict__ warp_len_in, int sentinel
-#define FORCE_PASS q, p, fout, list, warp_off, warp_len, ref_of_slot, pn, nwarps, q_out, ctrl, list_in, warp_len_in, sentinel
 
-// One force-warp: the kPW locals in slots [w kPW, (w+1) kPW), kG lanes each.
-template <int VARIANT, int MODE, bool PRUNE>
-__device__ __forceinline__ void force_warp(long long w, int lane, FORCE_PARAMS, const ForceConsts &fc) {
-  const long long a = w * kPW + lane / kG;
-  const bool act = a < pn;
-  double ax, ay, az;
-  ld_q256(q + (act ? a : (long long)pn - 1), ax, ay, az);
-  const int len2 = warp_len[w] >> 1;
-  const long long base = warp_off[w];
-  const uint2 *__restrict__ lp = reinterpret_cast<const uint2 *>(list + base) + lane;
-  double fx = 0.0, fy = 0.0, fz = 0.0;
-  const long long cl2b = __double_as_longlong(fc.CL2);
-  // PRUNE: which of this lane's entries stay (bit 2k: first entry of step-pair k, bit 2k+1: second) and how
-  // many per class (index mod 4), 4 x 8 bits
-  const long long keep2b = __double_as_longlong(fc.keep2);
-  unsigned long long keepmask = 0ull;
-  unsigned kcnt = 0u;
+struct TileArgs {
+  TileGrid g;
+  const int *cell_start, *gcell_start, *gitems, *tile_fw0, *tile_order;
+  int tile_base;     // first entry of tile_order this launch covers
+  int cap;           // staged-record capacity the shared memory was sized for
+};
 
-  constexpr int UNR = FORCE_UNROLL;
-  uint2 en = (len2 > 0) ? ld_list(lp) : make_uint2(0u, 0u);
-#pragma unroll UNR
-  for (int k = 0; k < len2; k++) {
-    const uint2 e = en;
-#if FORCE_PF_L1
-    // fire-and-forget: the list words of step-pair k + FORCE_PF_L1 into L1, so that the (compiler-scheduled)
-    // load of the next words never waits on L2 / HBM -- ptxas otherwise sinks that load below the arithmetic,
-    // which serialises its latency behind the gather's (1.15 -> 1.42 ms at 5.5 M particles)
-    if (k + FORCE_PF_L1 < len2) asm volatile("prefetch.global.L1 [%0];" ::"l"(lp + (long long)(k + FORCE_PF_L1) * 32));
-#endif
-    if (k + 1 < len2) en = ld_list(lp + (long long)(k + 1) * 32);
-    double j0x, j0y, j0z, j1x, j1y, j1z;
-    ld_q256(q + e.x, j0x, j0y, j0z);
-    ld_q256(q + e.y, j1x, j1y, j1z);
-    const long long r0 = pair_accumulate<VARIANT>(ax, ay, az, j0x, j0y, j0z, cl2b, fc, fx, fy, fz);
-    const long long r1 = pair_accumulate<VARIANT>(ax, ay, az, j1x, j1y, j1z, cl2b, fc, fx, fy, fz);
-    if (PRUNE) {
-      if (r0 <= keep2b) { keepmask |= 1ull << (2 * k); kcnt += 1u << (8 * (e.x & 3u)); }
-      if (r1 <= keep2b) { keepmask |= 2ull << (2 * k); kcnt += 1u << (8 * (e.y & 3u)); }
-    }
-  }
-#pragma unroll
-  for (int o = kG / 2; o > 0; o >>= 1) {
-    fx += __shfl_xor_sync(0xffffffffu, fx, o);
-    fy += __shfl_xor_sync(0xffffffffu, fy, o);
-    fz += __shfl_xor_sync(0xffffffffu, fz, o);
-  }
-  if (PRUNE) {
-    // ---- deal the kept entries of each local out again in rainbow order (cells.cu) --------------------------
-    const int c = lane % kG;
-    unsigned incl = kcnt;  // inclusive scan of the packed class counts over the 4 lanes of the group
-    unsigned t = __shfl_up_sync(0xffffffffu, incl, 1, kG);
-    if (c >= 1) incl += t;
-    t = __shfl_up_sync(0xffffffffu, incl, 2, kG);
-    if (c >= 2) incl += t;
-    const unsigned tot = __shfl_sync(0xffffffffu, incl, kG - 1, kG);  // class totals of the local
-    unsigned run = incl - kcnt;                                        // first ordinals of this lane's entries
-    const int nk = (int)((tot & 0xFFu) + ((tot >> 8) & 0xFFu) + ((tot >> 16) & 0xFFu) + (tot >> 24));
-    int steps = (nk + kG - 1) / kG;
-#pragma unroll
-    for (int o = kG; o < 32; o <<= 1) steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, o));
-    steps = (steps + 1) & ~1;
-    if (lane == 0) warp_len_in[w] = steps;
-    const int m = rainbow_min(tot);
-    const int glane0 = lane - c;
-    for (int k = 0; k < len2; k++) {
-      if (((keepmask >> (2 * k)) & 3ull) == 0ull) continue;
-      const uint2 e = __ldg(lp + (long long)k * 32);  // the row was just read: L1 / L2 hit
-      if ((keepmask >> (2 * k)) & 1ull) {
-        const int cc = (int)(e.x & 3u);
-        const int tt = (int)((run >> (8 * cc)) & 0xFFu);
-        run += 1u << (8 * cc);
-        const int ee = rainbow_place(tot, m, cc, tt);
-        list_in[base + list_word(ee / kG, glane0 + ee % kG)] = e.x;
-      }
-      if ((keepmask >> (2 * k)) & 2ull) {
-        const int cc = (int)(e.y & 3u);
-        const int tt = (int)((run >> (8 * cc)) & 0xFFu);
-        run += 1u << (8 * cc);
-        const int ee = rainbow_place(tot, m, cc, tt);
-        list_in[base + list_word(ee / kG, glane0 + ee % kG)] = e.y;
+template <int MODE, bool EXACT>
+__global__ void __launch_bounds__(FORCE_TPB, 2)
+k_tile_force(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__restrict__ p, double *__restrict__ fout,
+             const uint2 *__restrict__ list, const long long *__restrict__ fw_off, const int *__restrict__ fw_len,
+             const int *__restrict__ ref_of_slot, double4 *__restrict__ q_out, Ctrl *ctrl, ForceConsts fc) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  TileShared &ts = *reinterpret_cast<TileShared *>(smem);
+  double4 *sq = reinterpret_cast<double4 *>(smem + tile_shared_offset());
+  const int tile = ta.tile_order ? ta.tile_order[ta.tile_base + blockIdx.x] : (int)blockIdx.x;
+  tile_setup(ts, tile, ta.g, c, ta.cell_start, ta.gcell_start);
+  tile_stage_f64(ts, q, ta.gitems, sq, nullptr);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(sq);
+  const unsigned gp = (lane >> 2) & 1u;                                // odd groups: x and z exchanged
+  const unsigned hx = sbase + (gp << 4), hx2 = sbase + ((gp ^ 1u) << 4);
+  const int n_int = ts.n_int;
+  const int nfw = (n_int + kPW - 1) / kPW;
+  const int gfw0 = ta.tile_fw0[tile];
+  double v2max = 0.0;
+  for (;;) {
+    int fw = 0;
+    if (lane == 0) fw = atomicAdd(&ts.next_row, 1);
+    fw = __shfl_sync(0xffffffffu, fw, 0);
+    if (fw >= nfw) break;
+    const int a = fw * kPW + (lane >> 2);
+    const bool act = a < n_int;
+    const unsigned ao = (unsigned)(act ? a : ts.n_all) << 5;
+    double a0, a1;
+    lds128(ao + hx, a0, a1);
+    const double a2 = lds64(ao + hx2);
+    const int steps = fw_len[gfw0 + fw];
+    const uint2 *__restrict__ lp = list + fw_off[gfw0 + fw] + lane;
+    double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+    // the list allocation is padded: loading one chunk and prefetching three chunks past a row is harmless
+    uint2 wn = __ldg(lp);
+#pragma unroll 1
+    for (int k = 0; k < steps; k += 4) {
+      const uint2 w = wn;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(lp + 96));
+      wn = __ldg(lp + 32);
+      lp += 32;
+      const unsigned e0 = (w.x & 0xffffu) << 5, e1 = (w.x >> 16) << 5;
+      pair_kick<EXACT>(e0 + hx, e0 + hx2, a0, a1, a2, fc, f0, f1, f2);
+      pair_kick<EXACT>(e1 + hx, e1 + hx2, a0, a1, a2, fc, f0, f1, f2);
+      if (k + 2 < steps) {
+        const unsigned e2 = (w.y & 0xffffu) << 5, e3 = (w.y >> 16) << 5;
+        pair_kick<EXACT>(e2 + hx, e2 + hx2, a0, a1, a2, fc, f0, f1, f2);
+        pair_kick<EXACT>(e3 + hx, e3 + hx2, a0, a1, a2, fc, f0, f1, f2);
       }
     }
-    for (int ee = nk + c; ee < steps * kG; ee += kG) list_in[base + list_word(ee / kG, glane0 + ee % kG)] = (unsigned)sentinel;
-  }
-  const bool writer = act && (lane % kG) == 0;
-  if (MODE == FORCE_IMPULSE) {
-    if (writer) {
-      const long long ra = ref_of_slot[a];
-      fout[3 * ra + 0] = fx; fout[3 * ra + 1] = fy; fout[3 * ra + 2] = fz;
+#pragma unroll
+    for (int o = kG / 2; o > 0; o >>= 1) {
+      f0 += __shfl_xor_sync(0xffffffffu, f0, o);
+      f1 += __shfl_xor_sync(0xffffffffu, f1, o);
+      f2 += __shfl_xor_sync(0xffffffffu, f2, o);
     }
-    return;
-  }
-  double v2 = 0.0;
-  if (writer) {
-    double4 pa = p[a];
-    pa.x += fx; pa.y += fy; pa.z += fz;
-    p[a] = pa;
-    if (MODE == FORCE_KICK_DRIFT || MODE == FORCE_KICK_DRIFT2) {
-      // fcalculator.cc:22-32, no FMA contraction: identical to k_drift_half
-      const double sx = __dmul_rn(pa.x, fc.dt2), sy = __dmul_rn(pa.y, fc.dt2), sz = __dmul_rn(pa.z, fc.dt2);
-      double nx = __dadd_rn(ax, sx), ny = __dadd_rn(ay, sy), nz = __dadd_rn(az, sz);
-      if (MODE == FORCE_KICK_DRIFT2) { nx = __dadd_rn(nx, sx); ny = __dadd_rn(ny, sy); nz = __dadd_rn(nz, sz); }
-      q_out[a] = make_double4(nx, ny, nz, 0.0);
-      v2 = __dadd_rn(__dadd_rn(__dmul_rn(pa.x, pa.x), __dmul_rn(pa.y, pa.y)), __dmul_rn(pa.z, pa.z));
+    if (act && (lane & 3) == 0) {
+      const double fx = gp ? f2 : f0, fy = f1, fz = gp ? f0 : f2;
+      const int slot = tile_interior_slot(ts, a);
+      if (MODE == FORCE_IMPULSE) {
+        const long long ra = ref_of_slot[slot];
+        fout[3 * ra + 0] = fx; fout[3 * ra + 1] = fy; fout[3 * ra + 2] = fz;
+      } else {
+        double4 pa = p[slot];
+        pa.x += fx; pa.y += fy; pa.z += fz;
+        p[slot] = pa;
+        if (MODE == FORCE_KICK_DRIFT || MODE == FORCE_KICK_DRIFT2) {
+          const double4 qa = sq[a];
+          // fcalculator.cc:22-32, no FMA contraction: identical to k_drift_half
+          const double sx = __dmul_rn(pa.x, fc.dt2), sy = __dmul_rn(pa.y, fc.dt2), sz = __dmul_rn(pa.z, fc.dt2);
+          double nx = __dadd_rn(qa.x, sx), ny = __dadd_rn(qa.y, sy), nz = __dadd_rn(qa.z, sz);
+          if (MODE == FORCE_KICK_DRIFT2) { nx = __dadd_rn(nx, sx); ny = __dadd_rn(ny, sy); nz = __dadd_rn(nz, sz); }
+          q_out[slot] = make_double4(nx, ny, nz, 0.0);
+          v2max = fmax(v2max, __dadd_rn(__dadd_rn(__dmul_rn(pa.x, pa.x), __dmul_rn(pa.y, pa.y)), __dmul_rn(pa.z, pa.z)));
+        }
+      }
     }
   }
   if (MODE == FORCE_KICK_DRIFT || MODE == FORCE_KICK_DRIFT2) {
 #pragma unroll
-    for (int o = 16; o >= kG; o >>= 1) v2 = fmax(v2, __shfl_xor_sync(0xffffffffu, v2, o));
+    for (int o = 16; o > 0; o >>= 1) v2max = fmax(v2max, __shfl_xor_sync(0xffffffffu, v2max, o));
     if (lane == 0) {
-      // non-negative doubles order like their bit patterns; the maximum settles after a few warps, so the
+      // non-negative doubles order like their bit patterns; the maximum settles after a few blocks, so the
       // plain read filters out almost every atomic
-      const unsigned long long b = (unsigned long long)__double_as_longlong(v2);
+      const unsigned long long b = (unsigned long long)__double_as_longlong(v2max);
       if (b > *(volatile unsigned long long *)&ctrl->vmax2_bits) atomicMax(&ctrl->vmax2_bits, b);
     }
   }
 }
 
-// worder (may be null): the launch covers force-warps worder[wbase .. wbase + wcount) -- the interior or
-// the boundary part of the unit (cells.cu:k_warp_order); null = force-warps [0, wcount).
-template <int VARIANT, int MODE>
-__global__ void __launch_bounds__(FORCE_TPB, FORCE_MINBLK)
-k_force(FORCE_PARAMS, const int *__restrict__ worder, long long wbase, long long wcount, ForceConsts fc) {
-  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (i >= wcount) return;
-  const long long w = worder ? (long long)worder[wbase + i] : i;
-  force_warp<VARIANT, MODE, false>(w, threadIdx.x & 31, FORCE_PASS, fc);
-}
-// the same, deriving the inner list on the side (a few launches per rebuild interval)
-template <int VARIANT, int MODE>
-__global__ void __launch_bounds__(FORCE_TPB, FORCE_PRUNE_MINBLK)
-k_force_prune(FORCE_PARAMS, const int *__restrict__ worder, long long wbase, long long wcount, ForceConsts fc) {
-  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (i >= wcount) return;
-  const long long w = worder ? (long long)worder[wbase + i] : i;
-  force_warp<VARIANT, MODE, true>(w, threadIdx.x & 31, FORCE_PASS, fc);
-}
-
-static int force_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("MDB200_FORCE_VARIANT");
-    v = e ? atoi(e) : 1;
-    if (v < 0 || v > 2) v = 1;
+// ---------------------------------------------------------------------------------------------------------
+// Inner list.  ~25 % of the listed pairs lie between the cutoff and the search length and contribute exactly
+// zero.  k_tile_derive copies the entries of the outer list with r2 <= keep2 = (cutoff + delta)^2 at the CURRENT
+// positions into list_in, re-dealt in rainbow order (tile.cuh) at the same row offsets, with their own step counts
+// in fw_len_in.  Until some pair can have closed the distance delta (velocity budget kept by the host, api.cu)
+// the force launches walk the inner list and give identical contributions: the dropped ones are exact zeros.
+// With keep = search length it is a plain re-deal of the whole outer list.
+//
+// A warp takes one force-warp row: pass A walks the outer row (arrival order) and marks what stays, a 4-lane
+// scan gives every kept entry its ordinal within its class, pass B scatters the kept entries into a row block
+// in shared memory, which is then written out as whole chunks.
+// ---------------------------------------------------------------------------------------------------------
+template <int DUMMY>
+__global__ void __launch_bounds__(DERIVE_TPB, 1)
+k_tile_derive(TileArgs ta, Consts c, const double4 *__restrict__ q, const uint2 *__restrict__ list,
+              const long long *__restrict__ fw_off, const int *__restrict__ fw_len, uint2 *__restrict__ list_in,
+              int *__restrict__ fw_len_in, double keep2, int max_chunks) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  TileShared &ts = *reinterpret_cast<TileShared *>(smem);
+  double4 *sq = reinterpret_cast<double4 *>(smem + tile_shared_offset());
+  const int tile = ta.tile_order ? ta.tile_order[ta.tile_base + blockIdx.x] : (int)blockIdx.x;
+  tile_setup(ts, tile, ta.g, c, ta.cell_start, ta.gcell_start);
+  tile_stage_f64(ts, q, ta.gitems, sq, nullptr);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // row block of this warp: max_chunks x 32 words
+  uint2 *rb = reinterpret_cast<uint2 *>(sq + ta.cap + 1) + (size_t)wid * max_chunks * 32;
+  unsigned short *rb16 = reinterpret_cast<unsigned short *>(rb);
+  const int n_int = ts.n_int;
+  const int nfw = (n_int + kPW - 1) / kPW;
+  const int gfw0 = ta.tile_fw0[tile];
+  const unsigned sent = (unsigned)ts.n_all;
+  const uint2 sent2 = make_uint2(sent | (sent << 16), sent | (sent << 16));
+  const int c4 = lane & 3, glane0 = lane & ~3;
+  for (;;) {
+    int fw = 0;
+    if (lane == 0) fw = atomicAdd(&ts.next_row, 1);
+    fw = __shfl_sync(0xffffffffu, fw, 0);
+    if (fw >= nfw) break;
+    const int a = fw * kPW + (lane >> 2);
+    const double4 qa = sq[a < n_int ? a : ts.n_all];
+    const int steps = fw_len[gfw0 + fw];
+    const uint2 *__restrict__ lp = list + fw_off[gfw0 + fw] + lane;
+    const int nchunk = (steps + 3) >> 2;
+    // ---- pass A: which of this lane's entries stay (bit 4 c + s of the mask: step 4 c + s), how many per class
+    unsigned long long keep = 0ull;   // rows of at most 16 chunks = 64 steps = 256 entries (derive_inner checks)
+    unsigned kcnt = 0u;
+    const bool act = a < n_int;       // the last force-warp of a tile may own fewer than 8 locals
+    for (int ch = 0; ch < nchunk; ch++) {
+      const uint2 w = __ldg(lp + 32 * ch);
+      unsigned m = 0u;
+#pragma unroll
+      for (int s = 0; s < 4; s++) {
+        const unsigned j = ((s < 2 ? w.x : w.y) >> (16 * (s & 1))) & 0xffffu;
+        const double4 qj = sq[j];
+        const double dx = qj.x - qa.x, dy = qj.y - qa.y, dz = qj.z - qa.z;
+        const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+        if (act && r2 <= keep2 && 4 * ch + s < steps) { m |= 1u << s; kcnt += 1u << (8 * (j & 3u)); }
+      }
+      keep |= (unsigned long long)m << (4 * ch);
+    }
+    // ---- ordinals: inclusive scan of the packed class counts over the 4 lanes of the group
+    unsigned incl = kcnt;
+    unsigned t = __shfl_up_sync(0xffffffffu, incl, 1, kG);
+    if (c4 >= 1) incl += t;
+    t = __shfl_up_sync(0xffffffffu, incl, 2, kG);
+    if (c4 >= 2) incl += t;
+    const unsigned tot = __shfl_sync(0xffffffffu, incl, kG - 1, kG);  // class totals of the local
+    unsigned run = incl - kcnt;                                        // first ordinals of this lane's entries
+    const int nk = (int)((tot & 0xFFu) + ((tot >> 8) & 0xFFu) + ((tot >> 16) & 0xFFu) + (tot >> 24));
+    int steps_in = (nk + kG - 1) / kG;
+#pragma unroll
+    for (int o = kG; o < 32; o <<= 1) steps_in = max(steps_in, __shfl_xor_sync(0xffffffffu, steps_in, o));
+    steps_in = (steps_in + 1) & ~1;
+    const int nchunk_in = (steps_in + 3) >> 2;
+    // ---- row block <- sentinel, then the kept entries at their rainbow positions
+    for (int i = lane; i < nchunk_in * 32; i += 32) rb[i] = sent2;
+    __syncwarp();
+    const int m = rainbow_min(tot);
+    for (int ch = 0; ch < nchunk; ch++) {
+      const unsigned km = (unsigned)((keep >> (4 * ch)) & 0xFull);
+      if (km == 0u) continue;
+      const uint2 w = __ldg(lp + 32 * ch);  // the row was just read: L1 / L2 hit
+#pragma unroll
+      for (int s = 0; s < 4; s++) {
+        if (km & (1u << s)) {
+          const unsigned j = ((s < 2 ? w.x : w.y) >> (16 * (s & 1))) & 0xffffu;
+          const int cc = (int)(j & 3u);
+          const int tt = (int)((run >> (8 * cc)) & 0xFFu);
+          run += 1u << (8 * cc);
+          const int ee = rainbow_place(tot, m, cc, tt);  // entry index of the local: lane ee & 3, step ee >> 2
+          const int st = ee >> 2;
+          rb16[((st >> 2) * 32 + glane0 + (ee & 3)) * 4 + (st & 3)] = (unsigned short)j;
+        }
+      }
+    }
+    __syncwarp();
+    uint2 *__restrict__ dst = list_in + fw_off[gfw0 + fw];
+    for (int i = lane; i < nchunk_in * 32; i += 32) dst[i] = rb[i];
+    if (lane == 0) fw_len_in[gfw0 + fw] = steps_in;
+    __syncwarp();
   }
-  return v;
 }
 
 static ForceConsts make_fc(const Unit *u) {
   ForceConsts fc;
   fc.CL2 = u->c.CL2;
-  fc.dt = u->c.dt;
   fc.dt2 = u->c.dt2;
   fc.c24dt = 24.0 * u->c.dt;
   fc.c48dt = 48.0 * u->c.dt;
-  fc.c2x8 = u->c.C2 * 8.0;
   fc.c2x8dt = u->c.C2 * 8.0 * u->c.dt;
+  long long b;
+  memcpy(&b, &fc.CL2, sizeof(b));
+  fc.cl2_hi = (int)(b >> 32);
+  fc.exact_cut = (unsigned)(b & 0xffffffffll) != 0u;
   return fc;
 }
 
-#define FORCE_ARGS(F, QOUT, LIST, WLEN) u->q.ptr, u->p.ptr, F, LIST, u->warp_off.ptr, WLEN, u->ref_of_slot.ptr, \
-                                        (int)u->pn, u->nwarps, QOUT, u->ctrl, u->list_in.ptr, u->warp_len_in.ptr, sentinel_index(u)
+static TileArgs make_ta(const Unit *u, int part) {
+  TileArgs ta;
+  ta.g = tile_grid(u);
+  ta.cell_start = u->cell_start.ptr;
+  ta.gcell_start = u->gcell_start.ptr;
+  ta.gitems = u->gcell_items.ptr;
+  ta.tile_fw0 = u->tile_fw0.ptr;
+  ta.tile_order = part ? u->tile_order.ptr : nullptr;
+  ta.tile_base = (part == 2) ? u->n_interior_tiles : 0;
+  ta.cap = u->tile_cap;
+  return ta;
+}
 
-// part: 0 = every force-warp, 1 = interior warps only, 2 = boundary warps only
-// inner: 0 = walk the outer list, 1 = walk the inner list, 2 = walk the outer list and derive the inner one
-static int force_launch(Unit *u, int mode, double *fout, int part = 0, int inner = 0, double keep_len = 0.0) {
-  const int tpb = FORCE_TPB;
-  const int *worder = part ? u->warp_order.ptr : nullptr;
-  const long long wbase = (part == 2) ? u->n_interior : 0;
-  const long long wcount = (part == 0) ? u->nwarps : (part == 1 ? u->n_interior : u->nwarps - u->n_interior);
-  if (wcount <= 0) return MDB200_OK;
-  const unsigned grid = (unsigned)((wcount * 32 + tpb - 1) / tpb);
-  ForceConsts fc = make_fc(u);
-  fc.keep2 = keep_len * keep_len;
-  const unsigned *lst = (inner == 1) ? u->list_in.ptr : u->list.ptr;
-  const int *wlen = (inner == 1) ? u->warp_len_in.ptr : u->warp_len.ptr;
-  if (inner == 2 && (mode == FORCE_IMPULSE || mode == FORCE_KICK)) { set_error("pruning launch needs a fused mode"); return MDB200_EINVAL; }
-#define KLAUNCH(V, M, F, QOUT) k_force<V, M><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(F, QOUT, lst, wlen), worder, wbase, wcount, fc)
-#define PLAUNCH(V, M) k_force_prune<V, M><<<grid, tpb, 0, u->stream>>>(FORCE_ARGS(nullptr, u->q_alt.ptr, lst, wlen), worder, wbase, wcount, fc)
-#define LAUNCH(V)                                                                  \
-  do {                                                                             \
-    if (mode == FORCE_IMPULSE) KLAUNCH(V, FORCE_IMPULSE, fout, nullptr);           \
-    else if (mode == FORCE_KICK) KLAUNCH(V, FORCE_KICK, nullptr, nullptr);         \
-    else if (mode == FORCE_KICK_DRIFT && inner == 2) PLAUNCH(V, FORCE_KICK_DRIFT); \
-    else if (mode == FORCE_KICK_DRIFT) KLAUNCH(V, FORCE_KICK_DRIFT, nullptr, u->q_alt.ptr); \
-    else if (inner == 2) PLAUNCH(V, FORCE_KICK_DRIFT2);                            \
-    else KLAUNCH(V, FORCE_KICK_DRIFT2, nullptr, u->q_alt.ptr);                     \
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+  MDB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return MDB200_OK;
+}
+
+int derive_inner(Unit *u, double keep_len) {
+  u->inner_valid = false;
+  if (u->pn == 0 || u->ntiles == 0) { u->inner_valid = true; u->inner_keep = keep_len; return MDB200_OK; }
+  const int max_steps = (((u->max_row + kG - 1) / kG) + 1) & ~1;
+  const int max_chunks = (max_steps + 3) >> 2;
+  if (max_chunks > 16) { set_error("rows of %d entries are too long for the inner-list derivation", u->max_row); return MDB200_ECAPACITY; }
+  // as many warps as the row blocks leave room for beside the staged tile (at least 4: tile_setup needs 125 threads)
+  const size_t base = tile_smem_bytes_f64(u->tile_cap), per_warp = (size_t)max_chunks * 256, limit = 227 * 1024;
+  int warps = DERIVE_TPB / 32;
+  while (warps > 4 && base + warps * per_warp > limit) warps--;
+  const size_t sm = base + warps * per_warp;
+  if (sm > limit) { set_error("tile of %d records leaves no shared memory for the inner-list derivation", u->tile_cap); return MDB200_ECAPACITY; }
+  MDB_TRY(set_smem(k_tile_derive<0>, sm));
+  MDB_TRY(u->list_in.ensure(u->list.cap));
+  k_tile_derive<0><<<u->ntiles, warps * 32, sm, u->stream>>>(make_ta(u, 0), u->c, u->q.ptr, u->list.ptr, u->fw_off.ptr, u->fw_len.ptr,
+                                                             u->list_in.ptr, u->fw_len_in.ptr, keep_len * keep_len, max_chunks);
+  u->launches++;
+  MDB_CUDA(cudaGetLastError());
+  u->inner_valid = true;
+  u->inner_keep = keep_len;
+  return MDB200_OK;
+}
+
+// part: 0 = every tile, 1 = interior tiles only, 2 = boundary tiles only
+static int force_launch(Unit *u, int mode, double *fout, int part = 0) {
+  const int ntl = (part == 0) ? u->ntiles : (part == 1 ? u->n_interior_tiles : u->ntiles - u->n_interior_tiles);
+  if (ntl <= 0) return MDB200_OK;
+  if (!u->inner_valid) MDB_TRY(derive_inner(u, u->c.SL));  // no budgeted inner list: a full one
+  const ForceConsts fc = make_fc(u);
+  const TileArgs ta = make_ta(u, part);
+  const size_t sm = tile_smem_bytes_f64(u->tile_cap);
+#define KLAUNCH(M, E)                                                                                               \
+  do {                                                                                                              \
+    MDB_TRY(set_smem(k_tile_force<M, E>, sm));                                                                      \
+    k_tile_force<M, E><<<ntl, FORCE_TPB, sm, u->stream>>>(ta, u->c, u->q.ptr, u->p.ptr, fout, u->list_in.ptr, u->fw_off.ptr, \
+                                                          u->fw_len_in.ptr, u->ref_of_slot.ptr, u->q_alt.ptr, u->ctrl, fc); \
   } while (0)
-  switch (force_variant()) {
-    case 0: LAUNCH(0); break;
-    case 2: LAUNCH(2); break;
-    default: LAUNCH(1); break;
-  }
+#define LAUNCH(E)                                          \
+  do {                                                     \
+    if (mode == FORCE_IMPULSE) KLAUNCH(FORCE_IMPULSE, E);  \
+    else if (mode == FORCE_KICK) KLAUNCH(FORCE_KICK, E);   \
+    else if (mode == FORCE_KICK_DRIFT) KLAUNCH(FORCE_KICK_DRIFT, E); \
+    else KLAUNCH(FORCE_KICK_DRIFT2, E);                    \
+  } while (0)
+  if (fc.exact_cut) LAUNCH(true);
+  else LAUNCH(false);
 #undef LAUNCH
 #undef KLAUNCH
-#undef PLAUNCH
   u->launches++;
   MDB_CUDA(cudaGetLastError());
   return MDB200_OK;
@@ -347,33 +398,26 @@ static int force_launch(Unit *u, int mode, double *fout, int part = 0, int inner
 // ForceCalculator::CalculateForce (fcalculator.cc:35-50)
 int force_kick(Unit *u) {
   u->vmax_ready = false;
-  if (u->pn == 0 || u->nwarps == 0) return MDB200_OK;
+  if (u->pn == 0 || u->ntiles == 0) return MDB200_OK;
   return force_launch(u, FORCE_KICK, nullptr);
 }
 
 // CalculateForce + UpdatePositionHalf of MDManager::CalculateForce (mdmanager.cc:151-157) in one kernel;
 // predrift = also the first half drift of the next step (MODE 3; the caller sets u->predrifted).
-// inner: 0 = walk the outer list, 1 = walk the inner list, 2 = walk the outer list and derive the inner one
-// (entries within keep_len); the caller keeps u->inner_valid and the budget (api.cu).
-// part 0 = every force-warp; 1 = interior warps only (no ghost in any row: may run before the ghost
-// exchange has finished); 2 = boundary warps.  The buffers swap after part 0 or 2.
-int force_kick_drift(Unit *u, bool predrift, int part, int inner, double keep_len) {
-  if (u->pn == 0 || u->nwarps == 0) return MDB200_OK;
-  if (inner == 2) {
-    MDB_TRY(u->list_in.ensure(u->list.cap));  // same rows, same offsets
-    MDB_TRY(u->warp_len_in.ensure((size_t)u->nwarps + 2));
-  }
+// part 0 = every tile; 1 = interior tiles only (no ghost staged: may run before the ghost exchange has
+// finished); 2 = boundary tiles.  The buffers swap after part 0 or 2.
+int force_kick_drift(Unit *u, bool predrift, int part) {
+  if (u->pn == 0 || u->ntiles == 0) return MDB200_OK;
   static const bool dbg = getenv("MDB200_DEBUG_FORCE") != nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (dbg) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, u->stream); }
-  MDB_TRY(force_launch(u, predrift ? FORCE_KICK_DRIFT2 : FORCE_KICK_DRIFT, nullptr, part, inner, keep_len));
+  MDB_TRY(force_launch(u, predrift ? FORCE_KICK_DRIFT2 : FORCE_KICK_DRIFT, nullptr, part));
   if (dbg) {
     cudaEventRecord(e1, u->stream);
     cudaEventSynchronize(e1);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
-    fprintf(stderr, "[mdb200] force launch: part %d list %s keep %.4f  %.3f ms\n", part,
-            inner == 0 ? "outer" : (inner == 1 ? "inner" : "outer->inner"), keep_len, ms);
+    fprintf(stderr, "[mdb200] force launch: part %d keep %.4f  %.3f ms\n", part, u->inner_keep, ms);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
   }
   if (part != 1) {
@@ -391,7 +435,11 @@ int force_impulse(Unit *u, double *f3_host, long long cap_rows) {
   if (u->pn == 0) return MDB200_OK;
   DevBuf<double> f;
   MDB_TRY(f.ensure((size_t)u->pn * 3));
+  // parity probe, called at arbitrary points between steps: walk a fresh copy of the WHOLE outer list rather than an
+  // inner list whose velocity budget the caller's momenta changes may not be covered by
+  MDB_TRY(derive_inner(u, u->c.SL));
   MDB_TRY(force_launch(u, FORCE_IMPULSE, f.ptr));
+  u->inner_valid = false;
   MDB_CUDA(cudaMemcpyAsync(f3_host, f.ptr, sizeof(double) * 3 * (size_t)u->pn, cudaMemcpyDeviceToHost, u->stream));
   MDB_CUDA(cudaStreamSynchronize(u->stream));
   f.release();

@@ -10,11 +10,13 @@
 // the time of the call: locals after the second half drift, ghosts as of the last refresh
 // (half a step older) -- the reference's "stale ghost" definition (SURVEY.md finding 2).
 //
-// Reduction is deterministic: fixed grid, per-block partials in block order, one final block.
+// Reduction is deterministic: one block per tile, per-block partials in block order, one final block.
 #include "comm.h"
-#include "unit.h"
+#include "tile.cuh"
 
 namespace mdb {
+
+TileGrid tile_grid(const Unit *u);  // tile_search.cu
 
 static const int TPB = 256;
 static const int MAXBLK = 1184;  // 8 x 148 SMs
@@ -55,13 +57,18 @@ __device__ __forceinline__ void pair_uw(double dx, double dy, double dz, double 
   we += fma(-48.0 * s3, s3, 24.0 * s3) + 8.0 * c2r2;
 }
 
-// K over locals (grid-stride over particles) and U, W over the list (grid-stride over force-warps: kG lanes
-// per local, each lane takes every kG-th entry of the row, unit.h).
+// K over locals (grid-stride over particles) and U, W over the OUTER list, one block per tile (tile.cuh): the
+// positions of the tile and its halo are staged in shared memory, kG lanes per local, each lane takes every
+// kG-th entry of the row (unit.h).
 __global__ void __launch_bounds__(TPB)
-k_observe(const double4 *__restrict__ q, const double4 *__restrict__ p, const unsigned *__restrict__ list,
-          const long long *__restrict__ warp_off, const int *__restrict__ warp_len, int pn, long long nwarps,
-          int have_list, double CL2, double C2, double C0, double *__restrict__ partial) {
+k_observe(TileGrid g, Consts c, const int *__restrict__ cell_start, const int *__restrict__ gcell_start,
+          const int *__restrict__ gitems, const int *__restrict__ tile_fw0, const double4 *__restrict__ q,
+          const double4 *__restrict__ p, const uint2 *__restrict__ list, const long long *__restrict__ fw_off,
+          const int *__restrict__ fw_len, int pn, int have_list, double *__restrict__ partial) {
+  extern __shared__ __align__(128) unsigned char smem[];
   __shared__ double sh[TPB / 32];
+  TileShared &ts = *reinterpret_cast<TileShared *>(smem);
+  double4 *sq = reinterpret_cast<double4 *>(smem + tile_shared_offset());
   double k = 0.0, uu = 0.0, ww = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pn;
        i += (long long)gridDim.x * blockDim.x) {
@@ -72,20 +79,30 @@ k_observe(const double4 *__restrict__ q, const double4 *__restrict__ p, const un
     k += 0.5 * pp.w * pp.w;
   }
   if (have_list) {
+    const int tile = blockIdx.x;
+    tile_setup(ts, tile, g, c, cell_start, gcell_start);
+    tile_stage_f64(ts, q, gitems, sq, nullptr);
+    __syncthreads();
     const int lane = threadIdx.x & 31;
-    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
-    for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < nwarps; w += wstride) {
-      const long long a = w * kPW + lane / kG;
-      const double4 qa = q[a < pn ? a : (long long)pn - 1];
-      const uint2 *__restrict__ lp = reinterpret_cast<const uint2 *>(list + warp_off[w]) + lane;
-      const int len2 = warp_len[w] >> 1;  // one 8-byte load = the entries of two steps (unit.h)
+    const int nfw = (ts.n_int + kPW - 1) / kPW, gfw0 = tile_fw0[tile];
+    for (int fw = threadIdx.x >> 5; fw < nfw; fw += blockDim.x >> 5) {
+      const int a = fw * kPW + lane / kG;
+      const bool act = a < ts.n_int;  // the last force-warp of a tile may own fewer than 8 locals
+      const double4 qa = sq[act ? a : ts.n_all];
+      const uint2 *__restrict__ lp = list + fw_off[gfw0 + fw] + lane;
+      const int steps = act ? fw_len[gfw0 + fw] : 0;
       double ue = 0.0, we = 0.0;
-      for (int k = 0; k < len2; k++) {
-        // padding entries point at the far-away sentinel particle: r2 > CL2, no contribution
-        const uint2 e = __ldg(lp + (long long)k * 32);
-        const double4 q0 = q[e.x], q1 = q[e.y];
-        pair_uw(q0.x - qa.x, q0.y - qa.y, q0.z - qa.z, CL2, C2, C0, ue, we);
-        pair_uw(q1.x - qa.x, q1.y - qa.y, q1.z - qa.z, CL2, C2, C0, ue, we);
+      for (int s0 = 0; s0 < steps; s0 += 4) {
+        // padding entries point at the far-away sentinel record: r2 > CL2, no contribution
+        const uint2 w = __ldg(lp + 8 * s0);  // chunk s0 / 4: 32 words per chunk
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+          if (s0 + s < steps) {
+            const unsigned j = ((s < 2 ? w.x : w.y) >> (16 * (s & 1))) & 0xffffu;
+            const double4 qj = sq[j];
+            pair_uw(qj.x - qa.x, qj.y - qa.y, qj.z - qa.z, c.CL2, c.C2, c.C0, ue, we);
+          }
+        }
       }
       // every directed entry carries weight 0.5 (see the header)
       uu += 0.5 * ue;
@@ -120,13 +137,15 @@ static int observe_impl(Unit *u, double out[4], bool with_list) {
   out[0] = out[1] = out[2] = 0.0;
   out[3] = (double)u->pn;
   if (u->pn == 0) return MDB200_OK;
-  long long nb = (u->pn * kG + TPB - 1) / TPB;
-  if (nb > MAXBLK) nb = MAXBLK;
-  MDB_TRY(u->partial.ensure((size_t)3 * MAXBLK + 8));
-  k_observe<<<(unsigned)nb, TPB, 0, u->stream>>>(u->q.ptr, u->p.ptr, u->list.ptr, u->warp_off.ptr, u->warp_len.ptr,
-                                                  (int)u->pn, u->nwarps,
-                                                  (with_list && u->list_initialized) ? 1 : 0, u->c.CL2, u->c.C2, u->c.C0,
-                                                  u->partial.ptr);
+  const bool walk = with_list && u->list_initialized && u->ntiles > 0;
+  long long nb = walk ? u->ntiles : (u->pn + TPB - 1) / TPB;
+  if (!walk && nb > MAXBLK) nb = MAXBLK;
+  MDB_TRY(u->partial.ensure((size_t)3 * nb + 8));
+  const size_t sm = walk ? tile_smem_bytes_f64(u->tile_cap) : tile_shared_offset();
+  MDB_CUDA(cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes_f64(walk ? u->tile_cap : 0)));
+  k_observe<<<(unsigned)nb, TPB, sm, u->stream>>>(tile_grid(u), u->c, u->cell_start.ptr, u->gcell_start.ptr, u->gcell_items.ptr,
+                                                  u->tile_fw0.ptr, u->q.ptr, u->p.ptr, u->list.ptr, u->fw_off.ptr, u->fw_len.ptr,
+                                                  (int)u->pn, walk ? 1 : 0, u->partial.ptr);
   k_observe_final<<<1, TPB, 0, u->stream>>>(u->partial.ptr, (int)nb, u->ctrl);
   u->launches += 2;
   MDB_CUDA(cudaGetLastError());

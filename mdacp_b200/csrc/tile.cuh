@@ -1,0 +1,215 @@
+// Tiles: the unit of work of the search, force and observe kernels (device code shared by tile_search.cu,
+// force.cu and observe.cu).
+//
+// The reference walks its CSR list with one gather of q[j] per listed pair (fcalculator.cc:182-223) and builds
+// the list by testing every particle of the 27 surrounding cells (meshlist.cc:220-271).  On the B200 both loops
+// are bound by the L1 data pipe when the partner positions are gathered from global memory (round 1: 20
+// wavefronts per warp-wide gather, 63 % sector hits, profiles/r01c_force_ncu.txt).  So a thread block here
+// owns a TILE of up to 3 x 3 x 3 cells, copies the positions of those cells and of the one-cell halo around them
+// into shared memory once (coalesced, ~3,150 records of 32 bytes at density 0.7), and every partner is then
+// addressed by a 16-bit index into that STAGED array:
+//   * a gather is two bank-conflict-free shared-memory loads (8 wavefronts per warp-gather, no tags, no misses);
+//   * the list stream halves (2 bytes per entry);
+//   * the search reads its candidates as shared-memory broadcasts.
+//
+// Staged order of a tile: the locals of its interior cells (cell order z, y, x; inside a cell the slot order),
+// then the locals of the halo cells, then the ghosts binned into the halo cells, then one far-away SENTINEL
+// record that list padding points at.  It follows from cell_start / gcell_start / gcell_items alone, which only
+// change at a rebuild, so a staged index means the same particle in every kernel until then.
+#pragma once
+#include "unit.h"
+
+namespace mdb {
+
+struct TileGrid {
+  int t[3];     // cells per tile edge (1..3)
+  int nt[3];    // tiles per axis
+  int ntiles;
+};
+
+constexpr int kTileMaxEdge = 3;
+constexpr int kTileMaxCells = (kTileMaxEdge + 2) * (kTileMaxEdge + 2) * (kTileMaxEdge + 2);
+constexpr int kTileMaxInterior = kTileMaxEdge * kTileMaxEdge * kTileMaxEdge;
+
+struct TileCell {            // one cell of the tile's halo box
+  int src_l, n_l, off_l;     // locals: first slot, count, first staged index
+  int src_g, n_g, off_g;     // ghosts: first entry of gcell_items, count, first staged index
+};
+
+struct TileShared {          // per-block bookkeeping in shared memory
+  int lo[3];                 // first cell of the halo box (cell coordinates of the unit's grid)
+  int n[3];                  // cells of the halo box per axis (interior cells + 2)
+  int ncells;
+  int n_int;                 // staged interior locals: [0, n_int)
+  int n_loc;                 // staged locals:          [0, n_loc)
+  int n_all;                 // staged records:         [0, n_all); the sentinel sits at n_all
+  int nicell;                // interior cells
+  int next_row;              // work counter (dynamic row hand-out)
+  TileCell cell[kTileMaxCells];
+  int icell_off[kTileMaxInterior + 1];  // staged offset of interior cell i (ascending)
+  int icell_src[kTileMaxInterior];      // its first slot
+  int icell_k[kTileMaxInterior];        // its index in cell[]
+};
+
+// Shared memory of a kernel that stages FP64 records: bookkeeping + (records + sentinel) x 32 bytes
+__host__ __device__ inline size_t tile_shared_offset() { return (sizeof(TileShared) + 127) & ~(size_t)127; }
+inline size_t tile_smem_bytes_f64(int cap_records) { return tile_shared_offset() + (size_t)(cap_records + 1) * 32; }
+
+__device__ __forceinline__ bool tile_cell_interior(const TileShared &ts, int k) {
+  const int kx = k % ts.n[0], ky = (k / ts.n[0]) % ts.n[1], kz = k / (ts.n[0] * ts.n[1]);
+  return kx >= 1 && kx <= ts.n[0] - 2 && ky >= 1 && ky <= ts.n[1] - 2 && kz >= 1 && kz <= ts.n[2] - 2;
+}
+
+// Fills ts for tile `tile`.  Called by every thread of the block (blockDim.x >= 128); ends with a barrier.
+__device__ __forceinline__ void tile_setup(TileShared &ts, int tile, const TileGrid &g, const Consts &c,
+                                           const int *__restrict__ cell_start, const int *__restrict__ gcell_start) {
+  const int tid = threadIdx.x;
+  int T[3];
+  T[0] = tile % g.nt[0];
+  T[1] = (tile / g.nt[0]) % g.nt[1];
+  T[2] = tile / (g.nt[0] * g.nt[1]);
+  int lo[3], n[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const int first = 1 + T[d] * g.t[d];                  // first interior cell (cells 1..ms are the unit's own)
+    const int last = min(first + g.t[d], c.ms[d] + 1);    // one past the last
+    lo[d] = first - 1;
+    n[d] = last - first + 2;
+  }
+  const int ncells = n[0] * n[1] * n[2];
+  if (tid == 0) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) { ts.lo[d] = lo[d]; ts.n[d] = n[d]; }
+    ts.ncells = ncells;
+    ts.next_row = 0;
+  }
+  if (tid < ncells) {
+    const int kx = tid % n[0], ky = (tid / n[0]) % n[1], kz = tid / (n[0] * n[1]);
+    const int gc = (lo[0] + kx) + c.m[0] * ((lo[1] + ky) + c.m[1] * (lo[2] + kz));
+    TileCell tc;
+    tc.src_l = cell_start[gc];
+    tc.n_l = cell_start[gc + 1] - tc.src_l;
+    tc.src_g = gcell_start[gc];
+    tc.n_g = gcell_start[gc + 1] - tc.src_g;
+    tc.off_l = 0;
+    tc.off_g = 0;
+    ts.cell[tid] = tc;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    // exclusive prefix sums per category (interior locals / halo locals / ghosts) in cell order
+    int base_a = 0, base_b = 0, base_c = 0, base_i = 0;
+    for (int k0 = 0; k0 < ncells; k0 += 32) {
+      const int k = k0 + tid;
+      const bool valid = k < ncells;
+      const bool inter = valid && tile_cell_interior(ts, k);
+      const int nl = valid ? ts.cell[k].n_l : 0, ng = valid ? ts.cell[k].n_g : 0;
+      int a = inter ? nl : 0, b = inter ? 0 : nl, cg = ng, fi = inter ? 1 : 0;
+      int sa = a, sb = b, sc = cg, si = fi;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int ta = __shfl_up_sync(0xffffffffu, sa, o), tb = __shfl_up_sync(0xffffffffu, sb, o);
+        const int tc = __shfl_up_sync(0xffffffffu, sc, o), ti = __shfl_up_sync(0xffffffffu, si, o);
+        if (tid >= o) { sa += ta; sb += tb; sc += tc; si += ti; }
+      }
+      if (valid) {
+        ts.cell[k].off_l = inter ? base_a + sa - a : base_b + sb - b;  // halo locals: n_int added below
+        ts.cell[k].off_g = base_c + sc - cg;                            // n_loc added below
+        if (inter) {
+          const int i = base_i + si - 1;
+          ts.icell_off[i] = base_a + sa - a;
+          ts.icell_src[i] = ts.cell[k].src_l;
+          ts.icell_k[i] = k;
+        }
+      }
+      base_a += __shfl_sync(0xffffffffu, sa, 31);
+      base_b += __shfl_sync(0xffffffffu, sb, 31);
+      base_c += __shfl_sync(0xffffffffu, sc, 31);
+      base_i += __shfl_sync(0xffffffffu, si, 31);
+    }
+    __syncwarp();
+    for (int k = tid; k < ncells; k += 32) {
+      if (!tile_cell_interior(ts, k)) ts.cell[k].off_l += base_a;
+      ts.cell[k].off_g += base_a + base_b;
+    }
+    if (tid == 0) {
+      ts.n_int = base_a;
+      ts.n_loc = base_a + base_b;
+      ts.n_all = base_a + base_b + base_c;
+      ts.nicell = base_i;
+      ts.icell_off[base_i] = base_a;
+    }
+  }
+  __syncthreads();
+}
+
+// slot of the interior local with staged index a (binary search over <= 27 interior cells)
+__device__ __forceinline__ int tile_interior_slot(const TileShared &ts, int a) {
+  int i = 0;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1)
+    if (i + s < ts.nicell && ts.icell_off[i + s] <= a) i += s;
+  return ts.icell_src[i] + (a - ts.icell_off[i]);
+}
+
+__device__ __forceinline__ double4 ld_q256(const double4 *p) {
+  double4 v;
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+
+// Copies the tile's records into sq as (x, y, z, y): the duplicate y lets odd lane groups read (z, y) first and
+// x second while even groups read (x, y) and z -- see force.cu.  The sentinel goes to sq[n_all].  sslot (may be
+// null): the slot of every staged record.  No barrier at the end.
+__device__ __forceinline__ void tile_stage_f64(const TileShared &ts, const double4 *__restrict__ q,
+                                               const int *__restrict__ gitems, double4 *sq, int *sslot) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int ncells = ts.ncells;
+#pragma unroll 2
+  for (int k = wid; k < ncells; k += nw) {
+    const TileCell tc = ts.cell[k];
+    for (int l = lane; l < tc.n_l; l += 32) {
+      double4 v = ld_q256(q + tc.src_l + l);
+      v.w = v.y;
+      sq[tc.off_l + l] = v;
+      if (sslot) sslot[tc.off_l + l] = tc.src_l + l;
+    }
+    for (int l = lane; l < tc.n_g; l += 32) {
+      const int s = gitems[tc.src_g + l];
+      double4 v = ld_q256(q + s);
+      v.w = v.y;
+      sq[tc.off_g + l] = v;
+      if (sslot) sslot[tc.off_g + l] = s;
+    }
+  }
+  if (threadIdx.x == 0) sq[ts.n_all] = make_double4(1.0e8, 1.0e8, 1.0e8, 1.0e8);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// list layout (unit.h): entry e of the local in group m of a force-warp: lane 4 m + (e & 3), step e >> 2; the
+// four steps 4 c .. 4 c + 3 of a lane are the four 16-bit fields of uint2 word (c, lane) at fw_off + 32 c + lane.
+// ---------------------------------------------------------------------------------------------------------
+// byte offset of entry e inside the local's 32-byte sector of chunk e >> 4
+__host__ __device__ inline int sector_byte(int e) { return ((e & 3) << 3) + (((e >> 2) & 3) << 1); }
+// storage steps of a row block walked for `steps` steps
+__host__ __device__ inline int store_steps(int steps) { return (steps + 3) & ~3; }
+
+// "Rainbow" row order of the inner list: tot = partners per class (staged index mod 4), 4 x 8 bits; m = smallest
+// class count.  Steps < m hold one partner of every class (lane c of the group takes class c: with 32-byte
+// records the class is the record's 16-byte bank group pair, so the four lanes of a group never conflict);
+// what is left over is dealt out in (ordinal, class) order.
+__device__ __forceinline__ int rainbow_min(unsigned tot) {
+  return (int)min(min(tot & 0xFFu, (tot >> 8) & 0xFFu), min((tot >> 16) & 0xFFu, (tot >> 24) & 0xFFu));
+}
+__device__ __forceinline__ int rainbow_place(unsigned tot, int m, int c, int t) {
+  if (t < m) return 4 * t + c;
+  int r = 0;
+#pragma unroll
+  for (int cc = 0; cc < 4; cc++) {
+    const int left = (int)((tot >> (8 * cc)) & 0xFFu) - m;
+    r += min(left, (t - m) + (cc < c ? 1 : 0));
+  }
+  return 4 * m + r;
+}
+
+}  // namespace mdb

@@ -155,30 +155,43 @@ struct Unit {
   DevBuf<double4> mig_send_q, mig_send_p, mig_recv_q, mig_recv_p;
   DevBuf<int> mig_send_t, mig_recv_t;
 
-  // FULL neighbour list (every local's row holds all its partners), G = LANES_PER_LOCAL lanes per local:
-  // force-warp w owns the PW = 32 / G locals in slots [PW w, PW w + PW); entry e of the local in group m
-  // is handled by lane G m + (e % G) at step k = e / G and stored at
-  //   list[warp_off[w] + 64 (k >> 1) + 2 lane + (k & 1)]
-  // so that one 8-byte load per lane fetches two steps and a warp's load is one contiguous 256-byte run.
-  // Row order: cells.cu ("rainbow" order); rows are padded to the warp's (even) step count with the sentinel.
-  long long nwarps = 0;           // force-warps = ceil(pn / PW)
-  DevBuf<int> row_count;          // entries per local slot
-  DevBuf<unsigned> row_cls;       // entries per class (partner index mod 4), 4 x 8 bits
-  DevBuf<int> warp_len;           // steps per force-warp (even)
-  DevBuf<long long> warp_off;     // first list word of the force-warp (multiple of 64)
-  DevBuf<unsigned> list;
-  // interior / boundary split of the force-warps (boundary = some row of the warp holds a ghost): lets the
-  // interior force run while the ghost exchange is still in flight (api.cu, multi-process runs)
-  DevBuf<int> warp_flag, warp_order;   // order: interior warps first, then boundary warps
-  long long n_interior = 0;
-  // INNER list (force.cu, PRUNE): the entries of `list` that were within cutoff + inner_delta when it was last
-  // derived, same row offsets (warp_off), own step counts.  The fused NVE step walks it instead of `list`
-  // until the velocity budget inner_budget (host side, global max |p|) is used up; see api.cu.
-  DevBuf<unsigned> list_in;
-  DevBuf<int> warp_len_in;
+  // ---- tiles (tile.cuh) ------------------------------------------------------------------------------------
+  // The interior cells of the unit are grouped into TILES of tdim[0] x tdim[1] x tdim[2] cells (at most 3 per
+  // axis).  A force / search / observe block owns one tile: it stages the positions of the tile's cells and of
+  // the one-cell halo around them in shared memory (32-byte records, ~3,150 of them for 3x3x3 cells at density
+  // 0.7) and all partner indices are 16-bit indices into that STAGED array.  The staged order -- interior cells,
+  // then the halo's local cells, then the halo's ghost cells -- follows from cell_start / gcell_start alone, so
+  // it is the same in every kernel between two rebuilds.
+  int tdim[3] = {1, 1, 1};        // cells per tile edge
+  int tnum[3] = {0, 0, 0};        // tiles per axis
+  int ntiles = 0;
+  int tile_cap = 0;               // staged records of the largest tile (sizes the kernels' shared memory)
+  int tile_maxint = 0;            // interior locals of the largest tile
+  DevBuf<int> tile_fw0;           // first force-warp of tile t (ntiles + 1 entries)
+  DevBuf<int> tile_flag;          // 1 = the tile stages ghosts (boundary tile)
+  DevBuf<int> tile_order;         // interior tiles first, then boundary tiles (overlapped exchange, api.cu)
+  int n_interior_tiles = 0;
+  // FULL neighbour lists (every local's row holds all its partners), kG = 4 lanes per local: force-warp w of
+  // a tile owns the tile's interior locals with staged index [8 w', 8 w' + 8); entry e of the local in group m
+  // is handled by lane 4 m + (e & 3) at step e >> 2.  Storage: 16-bit entries, four steps of a lane in one
+  // 8-byte word, word (c, lane) of the row block at uint2 index fw_off[w] + 32 c + lane -- so a local's 16
+  // entries of chunk c are one aligned 32-byte sector.  Rows are padded with the tile's sentinel record to
+  // the force-warp's step count (even), storage to a multiple of 4 steps.
+  //   list     OUTER list: every partner within the search length, in ARRIVAL order (tile_search.cu); walked
+  //            by the observers and by the derivation below
+  //   list_in  INNER list: the entries of `list` within cutoff + inner_delta when it was last derived
+  //            (force.cu: k_tile_derive), re-dealt in "rainbow" order (partner index mod 4 = lane in group, so
+  //            that a quarter-warp's shared-memory reads are bank-conflict free), same row offsets, own step
+  //            counts.  The force kernel always walks this list; api.cu keeps its velocity budget.
+  long long nfw = 0;              // force-warps of the unit = sum over tiles of ceil(interior locals / 8)
+  DevBuf<int> row_count;          // outer entries per local slot
+  DevBuf<int> fw_len, fw_len_in;  // steps per force-warp (even)
+  DevBuf<long long> fw_off;       // first uint2 word of the force-warp's row block (both lists)
+  DevBuf<uint2> list, list_in;
   bool inner_valid = false;
   double inner_left = -1.0, inner_delta = 0.0;  // budget of the unit GROUP, kept in its first unit (api.cu)
-  long long list_entries = 0;     // padded entries
+  double inner_keep = 0.0;        // radius the present inner list was derived with
+  long long list_entries = 0;     // stored 16-bit entries (padded)
   long long npairs = 0;           // reference-style count of listed pairs (meshlist.cc:309)
   int max_row = 0;
 
@@ -221,37 +234,16 @@ struct Unit {
   bool ev_ready = false;
   cudaEvent_t fev[2];              // light force timer
   bool fev_ready = false, fev_pending = false;
+  cudaEvent_t dev[2];              // the same for the inner-list derivation
+  bool dev_ready = false, dev_pending = false;
+  double derive_ms = 0.0;
+  long long derive_launches = 0;
 };
 
-inline int sentinel_index(const Unit *u) { return (int)u->cap_t; }
 
-// lanes that share one local in the force / observe kernels (power of two, <= 32)
-#ifndef LANES_PER_LOCAL
-#define LANES_PER_LOCAL 4
-#endif
-constexpr int kG = LANES_PER_LOCAL;
-constexpr int kPW = 32 / kG;  // locals per force-warp
-// list word of (step k, lane l) relative to the warp's first word
-__host__ __device__ inline long long list_word(int k, int lane) { return 64LL * (k >> 1) + 2 * lane + (k & 1); }
-
-#ifdef __CUDACC__
-// "Rainbow" row order (cells.cu): tot = partners per class (index mod 4), 4 x 8 bits; m = smallest class count.
-// Entry index (step * 4 + lane-in-group) of the t-th partner of class c: steps < m hold one partner of every
-// class, what is left over is dealt out in (ordinal, class) order.
-__device__ __forceinline__ int rainbow_min(unsigned tot) {
-  return (int)min(min(tot & 0xFFu, (tot >> 8) & 0xFFu), min((tot >> 16) & 0xFFu, (tot >> 24) & 0xFFu));
-}
-__device__ __forceinline__ int rainbow_place(unsigned tot, int m, int c, int t) {
-  if (t < m) return 4 * t + c;
-  int r = 0;
-#pragma unroll
-  for (int cc = 0; cc < 4; cc++) {
-    const int left = (int)((tot >> (8 * cc)) & 0xFFu) - m;
-    r += min(left, (t - m) + (cc < c ? 1 : 0));
-  }
-  return 4 * m + r;
-}
-#endif
+// lanes that share one local in the force / observe kernels, locals per force-warp
+constexpr int kG = 4;
+constexpr int kPW = 32 / kG;
 
 // ---------------------------------------------------------------------------------------------
 // kernels / phases (host launchers; all asynchronous on u->stream unless stated)
@@ -272,8 +264,10 @@ int wrap_periodic(Unit *u);
 int cell_sort_locals(Unit *u);
 int find_border(Unit *u, int dir, long long *n_border);                  // sync
 int bin_ghosts(Unit *u);
-int build_pair_list(Unit *u);                                            // sync (list size)
 int snapshot_positions(Unit *u);
+
+// tile_search.cu
+int build_pair_list(Unit *u);                                            // sync (tile census, list size)
 int extract_pairs(Unit *u, int *key, int *partner, long long cap, long long *npairs); // sync
 
 // exchange.cu
@@ -288,11 +282,12 @@ int langevin_kick(Unit *u);
 int expiry_check_local(Unit *u, int *expired);                           // sync
 
 // force.cu
-int force_kick(Unit *u);
+// inner list = the outer entries within keep_len of the CURRENT positions (rainbow order); sets inner_valid
+int derive_inner(Unit *u, double keep_len);
+int force_kick(Unit *u);                                                 // derives a full inner list if there is none
 // fused kick + second half drift (+ the next step's first half drift if predrift); swaps q / q_alt.
-// part: 0 every force-warp, 1 interior, 2 boundary; inner: 0 walk the outer list, 1 walk the inner list,
-// 2 walk the outer list and derive the inner one (pairs within keep_len)
-int force_kick_drift(Unit *u, bool predrift, int part, int inner, double keep_len);
+// part: 0 every tile, 1 interior tiles, 2 boundary tiles.  Walks the inner list (derived on demand).
+int force_kick_drift(Unit *u, bool predrift, int part);
 int force_impulse(Unit *u, double *f3_host, long long cap_rows);         // sync
 
 // observe.cu

@@ -22,8 +22,14 @@ from oracle import refdump  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-# name -> (cfg, nunits, steps)
+# name -> (cfg, nunits, steps[, reference binary under oracle/_ref; default mdacp_scalar])
 CASES = {
+    # cutoff 2.5 (BASELINE.json configs[0]; mdconfig.h:15-16 -- a compile-time constant of the reference, so these
+    # two come from oracle/_ref/mdacp_scalar_c25, the scalar build of a scratch copy with that one line edited)
+    "bench1_c25": ({"DumpInit": "Benchmark", "SystemSize": 14, "TimeStep": 0.004, "InitialVelocity": 2.5}, 1, 100,
+                   "mdacp_scalar_c25"),
+    "bench8_c25": ({"DumpInit": "Benchmark", "SystemSize": 14, "TimeStep": 0.004, "InitialVelocity": 2.0}, 8, 100,
+                   "mdacp_scalar_c25"),
     "bench1": ({"DumpInit": "Benchmark", "SystemSize": 14, "TimeStep": 0.004, "InitialVelocity": 2.5}, 1, 100),
     "bench8": ({"DumpInit": "Benchmark", "SystemSize": 14, "TimeStep": 0.004, "InitialVelocity": 2.0}, 8, 100),
     "slab2": ({"DumpInit": "Benchmark", "UnitLength": 10, "TimeStep": 0.004, "InitialVelocity": 2.0,
@@ -65,14 +71,15 @@ def sha(a):
 
 
 def make(name):
-    cfg, nunits, steps = CASES[name]
+    cfg, nunits, steps = CASES[name][:3]
+    exe = os.path.join(HERE, "_ref", CASES[name][3]) if len(CASES[name]) > 3 else refdump.REF_SCALAR
     kv = dict(cfg)
     init_build = kv.get("DumpInit", "Benchmark") != "Collision"
     first = 0 if init_build else 1
     kv.update({"DumpSteps": steps, "DumpStateAt": "0,%d" % steps, "DumpPairsAt": "",
                "DumpForceAt": "%d,%d" % (first, steps), "DumpPairsAtBuild": "yes"})
     workdir = tempfile.mkdtemp(prefix="gold_")
-    rec, out = refdump.run_reference(kv, nunits=nunits, workdir=workdir)
+    rec, out = refdump.run_reference(kv, nunits=nunits, exe=exe, workdir=workdir)
     files = {}
     for fn in sorted(os.listdir(workdir)):
         if fn.startswith("final.") or fn.endswith(".cnf"):

@@ -178,7 +178,9 @@ def check_cuda_against_records(rec, steps, init_build, seed=None, observe_every=
                 assert c["pn"] == pn_ref[s, u] and c["tn"] == tn_ref[s, u], "pn/tn differ at step %d unit %d" % (s, u)
                 rebuilt = c["nbuilds"] != last_builds[u]
                 last_builds[u] = c["nbuilds"]
-                if rebuilt and has_pairs(rec, s, u):
+                # at every rebuild the record holds, and at any other step it holds a pair record for (the big
+                # live cases dump the list of the last step only: DumpPairsAt, not DumpPairsAtBuild)
+                if has_pairs(rec, s, u) and c["nbuilds"] > 0:
                     k, p = unit.pairs()
                     assert pairs_match_set(rec, s, u, k, p), "pair set differs at step %d unit %d" % (s, u)
                 if ("impulse.s%d.u%d" % (s, u)) in rec:
