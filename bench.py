@@ -7,9 +7,12 @@
 
 A "step" is one MDManager::Calculate() (mdmanager.cc:116-148) on the benchmark.cfg-shaped workload:
 FCC LJ, density 0.7, cutoff 3.0 (as shipped), dt 0.001, v0 1.0, one cubic unit of edge UNIT_LENGTH per
-GPU (284 -> 16,034,412 particles/GPU; BASELINE.json configs[1]/[2]); the timed window contains the
-margin-based pair-list rebuilds, the ghost refresh and an observation every 100 steps, exactly like
-the reference's Benchmark::Run window (benchmark.cc:28-45).  value = N_total * K / seconds.
+GPU (284 -> 16,034,412 particles/GPU; BASELINE.json configs[1]/[2]).  Like Benchmark::Run (benchmark.cc:24-45) the
+state is thermalised first (ThermalizeLoop = 150 steps, untimed set-up, --thermalize), then W warm-up steps, then the
+K timed steps with whatever margin-based pair-list rebuilds, ghost refreshes and observations (every 100 steps) fall
+into them.  value = N_total * K / seconds.  Because K may be too short to hold a rebuild (one every ~85 steps), the line
+also carries `steady_state`: the same metric over a long window (>= 300 steps, several rebuilds) measured right after,
+plus the cost and cadence of the rebuild and of the inner-list derivation.
 
 Rank 0 prints ONE JSON line (contract in the task statement): value (state resident in HBM), e2e
 (same metric through the C-ABI from/to pinned HOST buffers: upload + first list build + K steps +
@@ -329,6 +332,8 @@ def run_ours(args):
     mdm.MakePairList()
     W, K = args.warmup, args.steps
     obs = None
+    for i in range(args.thermalize):   # ThermalizeLoop of benchmark.cfg (benchmark.cc:24-27): untimed set-up
+        mdm.Calculate()
     for i in range(W):
         mdm.Calculate()
     unit.synchronize()
@@ -365,6 +370,44 @@ def run_ours(args):
     rebuilds = c1["nbuilds"] - c0["nbuilds"]
     n_obs = (K + OBSERVE_LOOP - 1) // OBSERVE_LOOP
 
+    # --- steady state: the same metric over a window long enough for several rebuilds (untimed for `value`) ---
+    S = max(int(args.steady_steps), 0)
+    steady = None
+    if S > 0:
+        unit.set_profiling(1)
+        unit.timers(reset=True)
+        cs0 = unit.counts()
+        barrier()
+        unit.event_record(2)
+        for i in range(S):
+            mdm.Calculate()
+            if i % OBSERVE_LOOP == 0:
+                mdm.observables()
+        unit.event_record(3)
+        unit.synchronize()
+        barrier()
+        ms_s = allmax(unit.event_elapsed_ms(2, 3))
+        tms, lss, cs1 = unit.timers(), unit.list_stats(), unit.counts()
+        unit.set_profiling(0)
+        nreb = cs1["nbuilds"] - cs0["nbuilds"]
+        # one forced rebuild, timed on the device (MDManager::MakePairList on the current state)
+        unit.event_record(4)
+        mdm.MakePairList()
+        unit.event_record(5)
+        unit.synchronize()
+        reb_ms = allmax(unit.event_elapsed_ms(4, 5))
+        walk_ms = tms["force"] / max(tms["force_launches"], 1)
+        der_n, der_ms = lss["derive_launches"], lss["derive_ms"] / max(lss["derive_launches"], 1)
+        steady = {"steps": S, "thermalize_steps": args.thermalize, "ms_per_step": ms_s / S,
+                  "value": n_total * S / (ms_s * 1e-3), "unit": UNIT,
+                  "rebuilds": nreb, "rebuild_every_steps": (S / nreb) if nreb else None, "rebuild_ms": reb_ms,
+                  "force_walk_ms": walk_ms, "inner_list_derivations": der_n, "derive_ms": der_ms,
+                  "derive_every_steps": (S / der_n) if der_n else None,
+                  "observations": (S + OBSERVE_LOOP - 1) // OBSERVE_LOOP,
+                  "pairs_per_particle": cs1["npairs"] / max(cs1["pn"], 1),
+                  "note": "device time over S consecutive steps with rebuilds, derivations and observations at their "
+                          "natural cadence; rebuild_ms = one forced MakePairList timed on its own"}
+
     # --- roofline of the dominant kernel (force kick), measured live in the timed region above ---
     peak, peak_src = measured_peaks()
     P = npairs / max(n_local, 1)  # listed unordered pairs per particle (reference count)
@@ -372,22 +415,31 @@ def run_ours(args):
     alg_bytes = (4.0 * P + 96.0) * n_local   # half-list indices + q read + p read/write
     alg_flops = 30.0 * P * n_local
     achieved = alg_bytes / (f_ms * 1e-3) / 1e9 if f_ms > 0 else 0.0
-    traffic = None
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "force_traffic.json")
     if os.path.exists(tp):
         try:
             tj = json.load(open(tp))
-            # measured dram bytes per particle of the force kernel (ncu --set full), scaled to this launch
+            # dram bytes per particle of the force kernel from one ncu --set full capture (static: a number taken
+            # under the profiler cannot be re-measured inside this run), scaled to this launch
             traffic = tj["dram_bytes_per_particle"] * n_local
+            traffic_src = "static: " + tj.get("source", "ncu --set full capture under profiles/")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_force (LJ force kick)", "achieved": achieved, "peak": peak,
+    try:
+        fp64_peak = capi.measure_fp64_peak(local_rank)
+        fp64_src = "measured here: DFMA loop, 16 chains per thread (mdb200_measure_fp64_peak)"
+    except Exception:
+        fp64_peak, fp64_src = 37.0, "nominal B200 FP64 (measurement failed)"
+    roofline = {"bound": "hbm", "kernel": "k_tile_force (LJ force kick + half drifts)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": peak_src, "ms_per_launch": f_ms, "launches_timed": tm["force_launches"],
                 "algorithmic_bytes_per_particle": 4.0 * P + 96.0, "pairs_per_particle": P,
                 "force_share_of_step": (tm["force"] / ms_total) if ms_total else None,
                 "fp64": {"achieved_tflops": alg_flops / (f_ms * 1e-3) / 1e12 if f_ms > 0 else 0.0,
-                         "peak_tflops": 37.0, "peak_source": "nominal B200 FP64 (not in MEASURED_PEAKS.json)",
+                         "peak_tflops": fp64_peak, "peak_source": fp64_src,
+                         "frac": (alg_flops / (f_ms * 1e-3) / 1e12 / fp64_peak) if (f_ms > 0 and fp64_peak) else None,
                          "flops_per_pair": 30}}
 
     # --- timed region 2: `e2e` through the C-ABI with HOST buffers ---
@@ -410,6 +462,22 @@ def run_ours(args):
     h2d = (2 * n_now * 32) / K
     d2h = (2 * n_now * 32 + n_obs * 32) / K
 
+    # --- multi-GPU parity (untimed): a small system on the same rank grid against the oracle, through the same
+    #     transport the timed regions used (tests/multigpu_parity_lib.py; the oracle is the checker here) ---
+    parity = None
+    if world > 1 and not args.no_parity:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import multigpu_parity_lib
+        pr = multigpu_parity_lib.run_parity(world, rank, local_rank, uid, unit_length=14.0, steps=120, dt=0.004, v0=2.0)
+        bad = allsum(0.0 if pr["ok"] else 1.0)
+        parity = {"ok": bad == 0.0, "failed_ranks": int(bad), "worst_KUW": allmax(pr.get("worst_KUW") or 0.0),
+                  "worst_q": allmax(pr.get("worst_q") or 0.0), "worst_p": allmax(pr.get("worst_p") or 0.0),
+                  "builds": pr.get("builds"), "n_unit": pr.get("n_unit"), "grid": pr.get("grid"), "steps": pr["steps"],
+                  "error": pr.get("error"),
+                  "transport": "NCCL send/recv" if os.environ.get("MDB200_P2P", "1")[:1] == "0" else "peer-to-peer windows",
+                  "what": "UnitLength 14 per rank, 120 hot steps (dt 0.004, v0 2.0): pair sets / rebuild schedule / pn / tn "
+                          "exact, K,U,W <= 1e-9, final q,p <= 1e-10 against the CPU oracle on the same unit grid"}
+
     out = None
     if rank == 0:
         out = {
@@ -420,7 +488,10 @@ def run_ours(args):
                                    "cutoff 3.0 (as shipped), skin 0.3, dt 0.001, v0 1.0; unit grid %dx%dx%d; "
                                    "BASELINE.json configs[%d]" % (UL, n_local, grid[0], grid[1], grid[2],
                                                                   1 if world == 1 else 2),
-                       "n_particles": n_total, "rebuilds_in_window": rebuilds, "observations_in_window": n_obs,
+                       "n_particles": n_total, "thermalize_steps": args.thermalize, "rebuilds_in_window": rebuilds,
+                       "observations_in_window": n_obs,
+                       "window_note": ("no rebuild fell into the K timed steps: steady_state.value is the rebuild-inclusive "
+                                       "figure" if rebuilds == 0 else "the timed steps contain %d rebuild(s)" % rebuilds),
                        "l2": "inputs (%.1f GB of positions, momenta and pair list per GPU) far exceed the 126 MB L2; "
                              "no flush needed" % ((n_local * 64 + (2 * npairs * 4.4)) / 1e9),
                        "parallelism": ("domain decomposition, one unit per GPU; per-step ghost refresh by %s, migration and "
@@ -434,6 +505,8 @@ def run_ours(args):
                                                   "observations, download of q and p"},
             "gpu_launches": launches,
             "roofline": roofline,
+            "steady_state": steady,
+            "parity_n": parity,
             "observables_last": obs,
         }
     mdm.close()
@@ -444,7 +517,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=150)  # ThermalizeLoop of benchmark.cfg (benchmark.cc:25-27)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--thermalize", type=int, default=150)   # ThermalizeLoop of benchmark.cfg (benchmark.cc:24-27)
+    ap.add_argument("--steady-steps", type=int, default=300)  # length of the steady_state window (0 = skip)
+    ap.add_argument("--no-parity", action="store_true")      # skip the multi-GPU parity block
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--unit-length", type=float, default=float(os.environ.get("MDB200_BENCH_UNIT_LENGTH", "284")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -456,7 +532,10 @@ def main():
         rank = int(os.environ.get("RANK", "0"))
         if rank != 0:
             return 0
-        therm = max(3, min(args.warmup, 5))
+        # same cadence as the GPU arm: ThermalizeLoop steps (benchmark.cc:24-27) + the warm-up, then the timed steps --
+        # the reference's own [MUPS] line covers exactly its TotalLoop steps after ThermalizeLoop; K is bounded so that
+        # the run ends within a few minutes (about 0.25 s per step for two one-GPU systems on 16 cores)
+        therm = args.thermalize + max(3, min(args.warmup, 5))
         loop = max(5, min(args.steps, 20))
         r = run_reference_cpu(args.unit_length, args.gpus, therm, loop)
         n_units = r.get("cores", 1)
@@ -467,8 +546,8 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "benchmark.cfg-shaped LJ FCC on the host CPU (reference arm of the %d-GPU run): one "
                                    "cubic unit per host core, units of the 2x2x2 split of the one-GPU box (UnitLength=%g "
-                                   "per GPU), cutoff 3.0; each run a bounded sample: %d thermalise + %d timed steps" % (
-                                       args.gpus, args.unit_length, therm, loop)},
+                                   "per GPU), cutoff 3.0; each run a bounded sample: %d thermalise + %d timed steps, one "
+                                   "observation per %d steps" % (args.gpus, args.unit_length, therm, loop, OBSERVE_LOOP)},
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": n_units, "kind": r["kind"],
                              "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -481,7 +560,8 @@ def main():
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:
-                r = run_reference_cpu(args.unit_length, 1, 3, 12)
+                # bounded sample of the same workload in the same (thermalised) state: ThermalizeLoop + 12 timed steps
+                r = run_reference_cpu(args.unit_length, 1, args.thermalize, 12)
                 out["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                                        "sample": r["sample"]}
             except Exception as ex:  # the baseline is reported, never required for the GPU number

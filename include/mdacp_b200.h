@@ -180,9 +180,14 @@ int mdb200_get_impulse(mdb200_unit *u, double *f3, long long cap_rows);
 int mdb200_timers(mdb200_unit *u, double out_ms[6], long long out_counts[2], int reset);
 /* Enable per-phase CUDA-event timing (adds event records to the stream; default off). */
 int mdb200_set_profiling(mdb200_unit *u, int on);
-/* Diagnostics of the device neighbour list: out = {force warps, padded list entries, longest row,
- * unpadded entries, lanes per local, list words the force kernel walks, 0, 0}. */
+/* Diagnostics of the device neighbour lists: out = {force warps, stored 16-bit entries of the outer list (padded),
+ * longest row, unpadded outer entries, lanes per local, entries the force kernel walks (inner list, padded),
+ * device ms spent deriving inner lists (profiling level 1), number of derivations}; the last two are reset by
+ * mdb200_timers(reset). */
 int mdb200_list_stats(mdb200_unit *u, double out[8]);
+/* Measured FP64 throughput of a device in TFLOP/s (a DFMA loop; ~10 ms): the denominator of the force kernel's
+ * FP64 roofline fraction, which BASELINE.json only quotes as a nominal ~37. */
+int mdb200_measure_fp64_peak(int device, double *tflops);
 /* CUDA-event stopwatch on the unit's stream (the stream every kernel of the unit is launched on):
  * record slot 0..7, then elapsed milliseconds between two recorded slots (synchronises on b). */
 int mdb200_event_record(mdb200_unit *u, int slot);

@@ -25,7 +25,7 @@ SYMBOLS = [
     "mdb200_set_zeta", "mdb200_set_control_temperature", "mdb200_set_aimed_temperature", "mdb200_observe",
     "mdb200_observe_unit", "mdb200_get_pairs", "mdb200_get_impulse", "mdb200_timers", "mdb200_set_profiling",
     "mdb200_synchronize", "mdb200_event_record", "mdb200_event_elapsed_ms", "mdb200_list_stats",
-    "mdb200_snapshot_begin", "mdb200_snapshot_wait", "mdb200_change_scale",
+    "mdb200_snapshot_begin", "mdb200_snapshot_wait", "mdb200_change_scale", "mdb200_measure_fp64_peak",
 ]
 
 
@@ -90,6 +90,7 @@ def lib():
         L.mdb200_event_record.argtypes = [vp, C.c_int]
         L.mdb200_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, dp]
         L.mdb200_list_stats.argtypes = [vp, dp]
+        L.mdb200_measure_fp64_peak.argtypes = [C.c_int, dp]
         L.mdb200_snapshot_begin.argtypes = [vp]
         L.mdb200_change_scale.argtypes = [C.POINTER(vp), C.c_int, C.c_double]
         L.mdb200_snapshot_wait.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), llp]
@@ -100,6 +101,13 @@ def lib():
 def check(rc):
     if rc != OK:
         raise MDB200Error(rc, lib().mdb200_last_error().decode(errors="replace"))
+
+
+def measure_fp64_peak(device=0):
+    """measured FP64 TFLOP/s of a device (DFMA loop)"""
+    t = C.c_double()
+    check(lib().mdb200_measure_fp64_peak(int(device), C.byref(t)))
+    return t.value
 
 
 def device_count():
@@ -246,7 +254,8 @@ class Unit:
         o = (C.c_double * 8)()
         check(lib().mdb200_list_stats(self.handle, o))
         return {"warps": int(o[0]), "padded_entries": int(o[1]), "max_row": int(o[2]), "entries": int(o[3]),
-                "lanes_per_local": int(o[4]), "walked_entries": int(o[5])}
+                "lanes_per_local": int(o[4]), "walked_entries": int(o[5]), "derive_ms": float(o[6]),
+                "derive_launches": int(o[7])}
 
     def event_record(self, slot):
         check(lib().mdb200_event_record(self.handle, slot))

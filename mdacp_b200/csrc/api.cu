@@ -707,6 +707,10 @@ int mdb200_upload(mdb200_unit *h, const double (*q)[4], const double (*p)[4], co
   // migrate_unpack), so the per-local arrays must reach past tn as well -- matters for small boxes, where the
   // ghost shell is as large as the box; sized here so that no rebuild re-allocates
   need_p = std::max<long long>(need_p, need_t - need_p / 4);
+  // test hook (tests/test_gpu_multiprocess.py): start from the bare minimum so that the rebuilds have to grow the
+  // position buffers -- the path that re-exports the peer-to-peer windows and parks replaced allocations
+  static const bool small_cap = getenv("MDB200_DEBUG_SMALL_CAPACITY") != nullptr;
+  if (small_cap) { need_p = pn + 64; need_t = pn + 64; }
   MDB_TRY(ensure_capacity(u, need_p, need_t));
   if (pn > 0) {
     // stage through the alt buffers (device-side repack keeps lane 3 == 0)
@@ -1122,6 +1126,53 @@ int mdb200_event_elapsed_ms(mdb200_unit *h, int a, int b, double *ms) {
   *ms = f;
   return MDB200_OK;
 }
+// Measured FP64 peak of the device (the denominator of the force kernel's FP64 roofline fraction): 16 independent
+// DFMA chains per thread, two 1024-thread blocks per SM.
+__global__ void __launch_bounds__(1024, 2) k_fp64_peak(double *out, int iters, double a, double b) {
+  double x[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) x[i] = (double)(threadIdx.x + i) * 1e-3;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = fma(x[i], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s += x[i];
+  if (s == 12345.678) out[0] = s;  // never true: keeps the chains alive
+}
+int mdb200_measure_fp64_peak(int device, double *tflops) {
+  if (!tflops) return MDB200_EINVAL;
+  int ndev = 0;
+  MDB_TRY(mdb200_device_count(&ndev));
+  if (device < 0 || device >= ndev) { set_error("device %d out of range", device); return MDB200_ECUDA; }
+  DeviceGuard g(device);
+  int sms = 0;
+  MDB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  double *d = nullptr;
+  MDB_CUDA(cudaMalloc(&d, 64));
+  cudaEvent_t e0, e1;
+  MDB_CUDA(cudaEventCreate(&e0));
+  MDB_CUDA(cudaEventCreate(&e1));
+  const int iters = 4096, grid = 2 * sms;
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    MDB_CUDA(cudaEventRecord(e0, 0));
+    k_fp64_peak<<<grid, 1024>>>(d, iters, 0.999999, 1e-7);
+    MDB_CUDA(cudaEventRecord(e1, 0));
+    MDB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    MDB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double tf = 2.0 * 16.0 * iters * 1024.0 * grid / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  return MDB200_OK;
+}
+
 int mdb200_synchronize(mdb200_unit *h) {
   if (!h) return MDB200_EINVAL;
   DeviceGuard g(h->u.device);

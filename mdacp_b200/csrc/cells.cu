@@ -154,10 +154,12 @@ __global__ void k_write_sentinel(double4 *q, long long idx) {
 int ensure_capacity(Unit *u, long long need_p, long long need_t) {
   bool grow = false;
   long long ncp = u->cap_p, nct = u->cap_t;
-  if (need_p > u->cap_p) { ncp = need_p + need_p / 4 + 1024; grow = true; }
+  // MDB200_DEBUG_SMALL_CAPACITY (test hook, see mdb200_upload): no head-room, so that rebuilds keep re-allocating
+  static const bool small_cap = getenv("MDB200_DEBUG_SMALL_CAPACITY") != nullptr;
+  if (need_p > u->cap_p) { ncp = small_cap ? need_p + 16 : need_p + need_p / 4 + 1024; grow = true; }
   if (need_t > u->cap_t || ncp > u->cap_t) {
     long long want = need_t > ncp ? need_t : ncp;
-    nct = want + want / 4 + 4096;
+    nct = small_cap ? want + 16 : want + want / 4 + 4096;
     grow = true;
   }
   if (!grow) return MDB200_OK;

@@ -26,6 +26,9 @@
 // Roofline: algorithmic HBM bytes per particle = 4 B x P (half-list indices) + 96 B
 // (q read, p read + write), 30 flop per listed unordered pair.
 #include <stdlib.h>
+#include <string.h>
+#include <map>
+#include <mutex>
 #include <utility>
 #include "tile.cuh"
 
@@ -147,14 +150,21 @@ k_tile_force(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__re
     const double a2 = lds64(ao + hx2);
     const int steps = fw_len[gfw0 + fw];
     const uint2 *__restrict__ lp = list + fw_off[gfw0 + fw] + lane;
+    // the writer lane's momentum is needed at the end of the row: start fetching its line now
+    int slot = 0;
+    if (act && (lane & 3) == 0) {
+      slot = tile_interior_slot(ts, a);
+      if (MODE != FORCE_IMPULSE) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + slot));
+    }
     double f0 = 0.0, f1 = 0.0, f2 = 0.0;
-    // the list allocation is padded: loading one chunk and prefetching three chunks past a row is harmless
-    uint2 wn = __ldg(lp);
+    // List words two chunks (8 steps) ahead of their use: a chunk takes a warp ~500 clk at 8 warps per scheduler,
+    // a miss to HBM ~1000.  The allocation is padded: loading two chunks past a row is harmless.
+    uint2 w1 = __ldg(lp), w2 = __ldg(lp + 32);
 #pragma unroll 1
     for (int k = 0; k < steps; k += 4) {
-      const uint2 w = wn;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(lp + 96));
-      wn = __ldg(lp + 32);
+      const uint2 w = w1;
+      w1 = w2;
+      w2 = __ldg(lp + 64);
       lp += 32;
       const unsigned e0 = (w.x & 0xffffu) << 5, e1 = (w.x >> 16) << 5;
       pair_kick<EXACT>(e0 + hx, e0 + hx2, a0, a1, a2, fc, f0, f1, f2);
@@ -173,7 +183,6 @@ k_tile_force(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__re
     }
     if (act && (lane & 3) == 0) {
       const double fx = gp ? f2 : f0, fy = f1, fz = gp ? f0 : f2;
-      const int slot = tile_interior_slot(ts, a);
       if (MODE == FORCE_IMPULSE) {
         const long long ra = ref_of_slot[slot];
         fout[3 * ra + 0] = fx; fout[3 * ra + 1] = fy; fout[3 * ra + 2] = fz;
@@ -336,9 +345,18 @@ static TileArgs make_ta(const Unit *u, int part) {
   return ta;
 }
 
+// opt-in dynamic shared memory of a kernel, raised when a launch needs more than any before it (per device)
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
+  static std::map<std::pair<const void *, int>, size_t> granted;
+  static std::mutex mtx;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mtx);
+  size_t &g = granted[std::make_pair(reinterpret_cast<const void *>(kernel), dev)];
+  if (bytes <= g) return MDB200_OK;
   MDB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  g = bytes;
   return MDB200_OK;
 }
 

@@ -34,6 +34,8 @@ constexpr int kTileMaxInterior = kTileMaxEdge * kTileMaxEdge * kTileMaxEdge;
 struct TileCell {            // one cell of the tile's halo box
   int src_l, n_l, off_l;     // locals: first slot, count, first staged index
   int src_g, n_g, off_g;     // ghosts: first entry of gcell_items, count, first staged index
+  int interior;              // 1 = one of the tile's own cells
+  int pad;
 };
 
 struct TileShared {          // per-block bookkeeping in shared memory
@@ -55,19 +57,21 @@ struct TileShared {          // per-block bookkeeping in shared memory
 __host__ __device__ inline size_t tile_shared_offset() { return (sizeof(TileShared) + 127) & ~(size_t)127; }
 inline size_t tile_smem_bytes_f64(int cap_records) { return tile_shared_offset() + (size_t)(cap_records + 1) * 32; }
 
-__device__ __forceinline__ bool tile_cell_interior(const TileShared &ts, int k) {
-  const int kx = k % ts.n[0], ky = (k / ts.n[0]) % ts.n[1], kz = k / (ts.n[0] * ts.n[1]);
-  return kx >= 1 && kx <= ts.n[0] - 2 && ky >= 1 && ky <= ts.n[1] - 2 && kz >= 1 && kz <= ts.n[2] - 2;
-}
+// k / n for the small operands of a halo box (k < 128, n <= 25) without the integer-division sequence:
+// floor(k M / 65536) = floor(k / n) for every M in [ceil(65536 / n), ceil(65536 / n) + 1] while 2 k n < 65536,
+// and floor(65536.f / n) + 2 lies in that range whatever the last bit of the single-precision quotient is
+__device__ __forceinline__ int small_magic(int n) { return (int)__fdividef(65536.0f, (float)n) + 2; }
+__device__ __forceinline__ int small_div(int k, int magic) { return (k * magic) >> 16; }
 
 // Fills ts for tile `tile`.  Called by every thread of the block (blockDim.x >= 128); ends with a barrier.
 __device__ __forceinline__ void tile_setup(TileShared &ts, int tile, const TileGrid &g, const Consts &c,
                                            const int *__restrict__ cell_start, const int *__restrict__ gcell_start) {
   const int tid = threadIdx.x;
   int T[3];
-  T[0] = tile % g.nt[0];
-  T[1] = (tile / g.nt[0]) % g.nt[1];
   T[2] = tile / (g.nt[0] * g.nt[1]);
+  const int rem = tile - T[2] * (g.nt[0] * g.nt[1]);
+  T[1] = rem / g.nt[0];
+  T[0] = rem - T[1] * g.nt[0];
   int lo[3], n[3];
 #pragma unroll
   for (int d = 0; d < 3; d++) {
@@ -76,7 +80,8 @@ __device__ __forceinline__ void tile_setup(TileShared &ts, int tile, const TileG
     lo[d] = first - 1;
     n[d] = last - first + 2;
   }
-  const int ncells = n[0] * n[1] * n[2];
+  const int n01 = n[0] * n[1];
+  const int ncells = n01 * n[2];
   if (tid == 0) {
 #pragma unroll
     for (int d = 0; d < 3; d++) { ts.lo[d] = lo[d]; ts.n[d] = n[d]; }
@@ -84,7 +89,7 @@ __device__ __forceinline__ void tile_setup(TileShared &ts, int tile, const TileG
     ts.next_row = 0;
   }
   if (tid < ncells) {
-    const int kx = tid % n[0], ky = (tid / n[0]) % n[1], kz = tid / (n[0] * n[1]);
+    const int kz = small_div(tid, small_magic(n01)), r = tid - kz * n01, ky = small_div(r, small_magic(n[0])), kx = r - ky * n[0];
     const int gc = (lo[0] + kx) + c.m[0] * ((lo[1] + ky) + c.m[1] * (lo[2] + kz));
     TileCell tc;
     tc.src_l = cell_start[gc];
@@ -93,6 +98,8 @@ __device__ __forceinline__ void tile_setup(TileShared &ts, int tile, const TileG
     tc.n_g = gcell_start[gc + 1] - tc.src_g;
     tc.off_l = 0;
     tc.off_g = 0;
+    tc.interior = (kx >= 1 && kx <= n[0] - 2 && ky >= 1 && ky <= n[1] - 2 && kz >= 1 && kz <= n[2] - 2) ? 1 : 0;
+    tc.pad = 0;
     ts.cell[tid] = tc;
   }
   __syncthreads();
@@ -102,7 +109,7 @@ __device__ __forceinline__ void tile_setup(TileShared &ts, int tile, const TileG
     for (int k0 = 0; k0 < ncells; k0 += 32) {
       const int k = k0 + tid;
       const bool valid = k < ncells;
-      const bool inter = valid && tile_cell_interior(ts, k);
+      const bool inter = valid && ts.cell[k].interior;
       const int nl = valid ? ts.cell[k].n_l : 0, ng = valid ? ts.cell[k].n_g : 0;
       int a = inter ? nl : 0, b = inter ? 0 : nl, cg = ng, fi = inter ? 1 : 0;
       int sa = a, sb = b, sc = cg, si = fi;
@@ -129,7 +136,7 @@ __device__ __forceinline__ void tile_setup(TileShared &ts, int tile, const TileG
     }
     __syncwarp();
     for (int k = tid; k < ncells; k += 32) {
-      if (!tile_cell_interior(ts, k)) ts.cell[k].off_l += base_a;
+      if (!ts.cell[k].interior) ts.cell[k].off_l += base_a;
       ts.cell[k].off_g += base_a + base_b;
     }
     if (tid == 0) {
@@ -161,25 +168,52 @@ __device__ __forceinline__ double4 ld_q256(const double4 *p) {
 // Copies the tile's records into sq as (x, y, z, y): the duplicate y lets odd lane groups read (z, y) first and
 // x second while even groups read (x, y) and z -- see force.cu.  The sentinel goes to sq[n_all].  sslot (may be
 // null): the slot of every staged record.  No barrier at the end.
+constexpr int kStageBatch = 3;
 __device__ __forceinline__ void tile_stage_f64(const TileShared &ts, const double4 *__restrict__ q,
                                                const int *__restrict__ gitems, double4 *sq, int *sslot) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int ncells = ts.ncells;
-#pragma unroll 2
-  for (int k = wid; k < ncells; k += nw) {
-    const TileCell tc = ts.cell[k];
-    for (int l = lane; l < tc.n_l; l += 32) {
-      double4 v = ld_q256(q + tc.src_l + l);
-      v.w = v.y;
-      sq[tc.off_l + l] = v;
-      if (sslot) sslot[tc.off_l + l] = tc.src_l + l;
+  // three cells per trip, their loads issued together: a thread copies only ~6 records, so the copy is pure latency
+  for (int k0 = wid; k0 < ncells; k0 += kStageBatch * nw) {
+    int src[kStageBatch], off[kStageBatch], nl[kStageBatch];
+    double4 v[kStageBatch];
+#pragma unroll
+    for (int u = 0; u < kStageBatch; u++) {
+      const int k = k0 + u * nw;
+      nl[u] = 0;
+      if (k < ncells) { src[u] = ts.cell[k].src_l; off[u] = ts.cell[k].off_l; nl[u] = ts.cell[k].n_l; }
+      if (lane < nl[u]) v[u] = ld_q256(q + src[u] + lane);
     }
-    for (int l = lane; l < tc.n_g; l += 32) {
-      const int s = gitems[tc.src_g + l];
-      double4 v = ld_q256(q + s);
-      v.w = v.y;
-      sq[tc.off_g + l] = v;
-      if (sslot) sslot[tc.off_g + l] = s;
+#pragma unroll
+    for (int u = 0; u < kStageBatch; u++) {
+      if (lane < nl[u]) {
+        v[u].w = v[u].y;
+        sq[off[u] + lane] = v[u];
+        if (sslot) sslot[off[u] + lane] = src[u] + lane;
+      }
+    }
+    // the rest: cells with more than 32 locals, and the ghosts binned into the (outermost) cells
+#pragma unroll
+    for (int u = 0; u < kStageBatch; u++) {
+      const int k = k0 + u * nw;
+      if (k >= ncells) continue;
+      for (int l = lane + 32; l < nl[u]; l += 32) {
+        double4 w = ld_q256(q + src[u] + l);
+        w.w = w.y;
+        sq[off[u] + l] = w;
+        if (sslot) sslot[off[u] + l] = src[u] + l;
+      }
+      const int ng = ts.cell[k].n_g;
+      if (ng > 0) {
+        const int sg = ts.cell[k].src_g, og = ts.cell[k].off_g;
+        for (int l = lane; l < ng; l += 32) {
+          const int s = gitems[sg + l];
+          double4 w = ld_q256(q + s);
+          w.w = w.y;
+          sq[og + l] = w;
+          if (sslot) sslot[og + l] = s;
+        }
+      }
     }
   }
   if (threadIdx.x == 0) sq[ts.n_all] = make_double4(1.0e8, 1.0e8, 1.0e8, 1.0e8);

@@ -161,7 +161,8 @@ k_tile_search(TileGrid g, Consts c, const double4 *__restrict__ q, const int *__
     if (ic >= ts.nicell) break;
     const int k = ts.icell_k[ic];
     const TileCell own = ts.cell[k];
-    const int kx = k % ts.n[0], ky = (k / ts.n[0]) % ts.n[1], kz = k / (ts.n[0] * ts.n[1]);
+    const int n01 = ts.n[0] * ts.n[1];
+    const int kz = small_div(k, small_magic(n01)), kr = k - kz * n01, ky = small_div(kr, small_magic(ts.n[0])), kx = kr - ky * ts.n[0];
     for (int l0 = 0; l0 < own.n_l; l0 += 32) {
       const int l = l0 + lane;
       const bool act = l < own.n_l;
