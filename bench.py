@@ -232,6 +232,64 @@ def run_reference_cpu(unit_length, n_gpus_equiv, therm, loop, timeout=1500):
             "n": n, "sec": sec, "steps": loop}
 
 
+def run_reference_cpu_project(workload, unit_length, collision_scale, loop, timeout=1500):
+    """The reference's own CPU path on the other BASELINE.json workloads (Mode=Langevin / Mode=Collision print no
+    timing line, benchmark.cfg as shipped does): the unmodified binary is run twice, with TotalLoop = a and a + loop
+    steps, and the difference of the wall-clock times is the time of `loop` steps -- set-up (lattice generation, first
+    pair list) cancels.  Bounded samples: one cubic unit per host core as in run_reference_cpu."""
+    from oracle import refdump
+    cores = host_cores()
+    lgrid = list(unit_grid_for(cores)) if cores >= 8 else [2, 2, 2]
+    units = lgrid[0] * lgrid[1] * lgrid[2]
+    if workload == "shipped":
+        n3 = cubic_units(cores)
+        g = round(n3 ** (1.0 / 3.0))
+        lgrid, units = [g, g, g], n3
+        base = "Mode=Benchmark\nThermalizeLoop=150\nSystemSize=50\nTimeStep=0.001\nInitialVelocity=1.0\n"
+        what = "benchmark.cfg as shipped (SystemSize 50), %d OpenMP units" % units
+    elif workload == "langevin":
+        edge = min(unit_length / 2.0, (2.1 * DENSITY * unit_length ** 3 / DENSITY / units) ** (1.0 / 3.0))
+        L = [edge * lgrid[0], edge * lgrid[1], edge * lgrid[2]]
+        base = ("Mode=Langevin\nInitialVelocity=1.8\nTimeStep=0.005\nSystemSizeX=%r\nSystemSizeY=%r\nSystemSizeZ=%r\n"
+                "ObserveLoop=100000\nAimedTemperature=0.9\nDensity=0.70\nHeatbathTau=0.1\nHeatbathGamma=0.1\n"
+                "HeatbathType=Langevin\nSeed=12345\n" % (L[0], L[1], L[2]))
+        what = "langevin.cfg scaled to a %gx%gx%g box, %d OpenMP units" % (L[0], L[1], L[2], units)
+    else:
+        k = collision_scale
+        # the droplets sit in the x halves: units along x first keeps every core busy
+        lgrid = [4, 2, 2] if cores >= 16 else [2, 2, 2]
+        units = lgrid[0] * lgrid[1] * lgrid[2]
+        base = ("Mode=Collision\nSystemSizeX=%r\nSystemSizeY=%r\nSystemSizeZ=%r\nTimeStep=0.002\nObserveLoop=100000\n"
+                "DropletSpeed=1.0\nSaveCdviewFile=no\n" % (120.0 * k, 60.0 * k, 60.0 * k))
+        what = "collision.cfg scaled x%g per axis, %d OpenMP units" % (k, units)
+    base += "LocalGridX=%d\nLocalGridY=%d\nLocalGridZ=%d\n" % (lgrid[0], lgrid[1], lgrid[2])
+    exe = refdump.REF_AVX2_BIG if refdump.have_ref(refdump.REF_AVX2_BIG) else refdump.REF_AVX2
+    if not refdump.have_ref(exe):
+        return {"value": None, "unit": UNIT, "cores": units, "kind": "reference", "sample": "oracle/_ref not built"}
+    env = dict(os.environ, OMP_NUM_THREADS=str(units), OMP_PROC_BIND="true")
+    times, n = [], None
+    first = 30 if workload != "shipped" else 0   # past the first builds / the start-up transient
+    for total in (first, first + loop):
+        tmp = tempfile.mkdtemp(prefix="refproj_")
+        with open(os.path.join(tmp, "input.cfg"), "w") as f:
+            f.write(base + "TotalLoop=%d\n" % total)
+        t0 = time.time()
+        res = subprocess.run([exe, "input.cfg"], cwd=tmp, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                             text=True, timeout=timeout)
+        times.append(time.time() - t0)
+        m = re.search(r"# Number of Particles = (\d+)", res.stdout)
+        if m:
+            n = int(m.group(1))
+        if res.returncode != 0 or n is None:
+            return {"value": None, "unit": UNIT, "cores": units, "kind": "reference", "sample": "failed: " + res.stdout[-300:]}
+    sec = max(times[1] - times[0], 1e-9)
+    return {"value": n * loop / sec, "unit": UNIT, "cores": units, "kind": "reference",
+            "sample": "unmodified reference (%s, AVX2 kernel): %s, N=%d; wall time of TotalLoop=%d minus TotalLoop=%d: "
+                      "%.1f s for %d steps; host %s, %d cores" % (os.path.basename(exe), what, n, first + loop, first, sec,
+                                                                  loop, cpu_model(), cores),
+            "n": n, "sec": sec, "steps": loop}
+
+
 def run_oracle_port_cpu(therm, loop):
     """Fallback when oracle/_ref is absent: the C restatement (oracle/liboracle.so), 8 OpenMP units,
     on a bounded 2M-particle sample of the same lattice."""
@@ -305,27 +363,72 @@ def run_ours(args):
         return float(t.item())
 
     UL = float(args.unit_length)
-    cfg = {"Mode": "Benchmark", "UnitLength": repr(UL), "TimeStep": repr(DT), "InitialVelocity": repr(V0)}
+    wl = args.workload
+    # --- the workload (BASELINE.json configs): cfg of the reference project, host-side generator, step variant ---
+    if wl == "benchmark":      # configs[1] / [2]: benchmark.cfg scaled, one cubic unit of edge UL per GPU (weak scaling)
+        cfg = {"Mode": "Benchmark", "UnitLength": repr(UL), "TimeStep": repr(DT), "InitialVelocity": repr(V0)}
+        wl_text = ("benchmark.cfg-shaped LJ FCC, UnitLength=%g per GPU, density 0.7, cutoff 3.0 (as shipped), skin 0.3, "
+                   "dt 0.001, v0 1.0" % UL)
+        scaling = "weak"
+    elif wl == "shipped":      # configs[0]: benchmark.cfg verbatim (SystemSize 50 -> 87,500 particles), one unit
+        cfg = {"Mode": "Benchmark", "SystemSize": "50", "TimeStep": repr(DT), "InitialVelocity": repr(V0)}
+        wl_text = "benchmark.cfg as shipped: SystemSize=50 (87,500 particles), cutoff 3.0, dt 0.001, v0 1.0, one unit"
+        scaling = "strong"
+    elif wl == "langevin":     # configs[3]: langevin.cfg with UnitLength = UL per GPU (langevin.cc:11-32)
+        cfg = {"Mode": "Langevin", "UnitLength": repr(UL), "TimeStep": "0.005", "AimedTemperature": "0.9",
+               "HeatbathGamma": "0.1", "HeatbathTau": "0.1", "HeatbathType": "Langevin", "ControlTemperature": "yes",
+               "Density": "0.70", "InitialVelocity": "1.8", "Seed": "12345"}
+        wl_text = ("langevin.cfg scaled: Langevin thermostat (gamma 0.1, T0 0.9, per-particle counter RNG), global FCC lattice "
+                   "density 0.70, UnitLength=%g per GPU, dt 0.005, v0 1.8, cutoff 3.0" % UL)
+        scaling = "weak"
+    else:                      # configs[4]: collision.cfg with the box scaled x10 per axis (collision.cc:54-80)
+        k = float(args.collision_scale)
+        cfg = {"Mode": "Collision", "SystemSizeX": repr(120.0 * k), "SystemSizeY": repr(60.0 * k),
+               "SystemSizeZ": repr(60.0 * k), "TimeStep": "0.002"}
+        wl_text = ("collision.cfg scaled x%g per axis: two FCC droplets (density 0.374, radius %g, +-1 along x) in a "
+                   "%gx%gx%g box, the rest vacuum, dt 0.002, cutoff 3.0; the SAME box on every GPU count" % (
+                       k, 15.0 * k, 120.0 * k, 60.0 * k, 60.0 * k))
+        scaling = "strong"
     mdm = driver.MDManager(cfg, num_procs=world, rank=rank, num_threads=1, devices=[local_rank], unique_id=uid,
                            cutoff=CUTOFF)
     unit = mdm.GetMDUnit(0)
     s, e = mdm.GetRect(0)
     grid = mdm.pinfo.GetGridSize()
 
-    # --- synthetic input: the reference's own benchmark generator semantics (host side, C++) ---
+    # --- synthetic input: the reference's own generator semantics (host side, C++: mdacp_b200/host/hostlib.cpp) ---
     t0 = time.time()
-    cap0 = int((e[0] - s[0]) * (e[1] - s[1]) * (e[2] - s[2]) * DENSITY) + 64
-    cap = int(cap0 * 1.02) + 65536  # head-room: migration changes the per-unit count
+    vol = (e[0] - s[0]) * (e[1] - s[1]) * (e[2] - s[2])
+    if wl in ("benchmark", "shipped"):
+        cap = int((int(vol * DENSITY) + 64) * 1.02) + 65536  # head-room: migration changes the per-unit count
+    elif wl == "langevin":
+        cap = int(vol * 0.70 * 1.05) + 65536
+    else:
+        cap = int(vol * 0.374 * 1.3) + 65536
     q_pin = torch.zeros((cap, 4), dtype=torch.float64).pin_memory()
     p_pin = torch.zeros((cap, 4), dtype=torch.float64).pin_memory()
     qh, ph = q_pin.numpy(), p_pin.numpy()
-    q0 = hostlib.benchmark_config(s, e, DENSITY, rank, out=qh)
-    n_local = q0.shape[0]
-    hostlib.initial_velocity(n_local, V0, rank, out=ph)
+    if wl in ("benchmark", "shipped"):
+        n_local = hostlib.benchmark_config(s, e, DENSITY, rank, out=qh).shape[0]
+        hostlib.initial_velocity(n_local, V0, rank, out=ph)
+    elif wl == "langevin":
+        q0 = hostlib.lattice_config(mdm.sinfo.L, s, e, density=0.70)
+        n_local = q0.shape[0]
+        qh[:n_local] = q0
+        hostlib.initial_velocity(n_local, 1.8, rank, out=ph)
+        del q0
+    else:
+        q0, p0 = hostlib.collision_config(mdm.sinfo.L, s, e)
+        n_local = q0.shape[0]
+        qh[:n_local] = q0
+        ph[:n_local] = p0
+        del q0, p0
     t_gen = time.time() - t0
     n_total = int(allsum(float(n_local)))
-    log("[rank %d] unit %s box %s..%s  N_local=%d N_total=%d  (generated in %.1f s)" % (
-        rank, grid, [round(x, 3) for x in s], [round(x, 3) for x in e], n_local, n_total, t_gen))
+    n_max = int(allmax(float(n_local)))
+    log("[rank %d] %s unit grid %s box %s..%s  N_local=%d N_total=%d  (generated in %.1f s)" % (
+        rank, wl, grid, [round(x, 3) for x in s], [round(x, 3) for x in e], n_local, n_total, t_gen))
+    if wl == "langevin":
+        mdm.SetSeed(12345)
 
     # --- state resident in HBM: upload, first build, warm-up (untimed) ---
     unit.upload4(qh[:n_local], ph[:n_local])
@@ -482,12 +585,14 @@ def run_ours(args):
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "benchmark.cfg-shaped LJ FCC, UnitLength=%g per GPU (%d particles/GPU), density 0.7, "
-                                   "cutoff 3.0 (as shipped), skin 0.3, dt 0.001, v0 1.0; unit grid %dx%dx%d; "
-                                   "BASELINE.json configs[%d]" % (UL, n_local, grid[0], grid[1], grid[2],
-                                                                  1 if world == 1 else 2),
+            "config": {"workload": "%s; %d particles on rank 0, unit grid %dx%dx%d; BASELINE.json configs[%d]" % (
+                           wl_text, n_local, grid[0], grid[1], grid[2],
+                           {"benchmark": 1 if world == 1 else 2, "shipped": 0, "langevin": 3, "collision": 4}[wl]),
+                       "workload_key": wl,
+                       "load_balance": {"particles_max_over_ranks": n_max, "particles_mean": n_total / world,
+                                        "efficiency_bound": (n_total / world) / max(n_max, 1)},
                        "n_particles": n_total, "thermalize_steps": args.thermalize, "rebuilds_in_window": rebuilds,
                        "observations_in_window": n_obs,
                        "window_note": ("no rebuild fell into the K timed steps: steady_state.value is the rebuild-inclusive "
@@ -523,6 +628,8 @@ def main():
     ap.add_argument("--no-parity", action="store_true")      # skip the multi-GPU parity block
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--unit-length", type=float, default=float(os.environ.get("MDB200_BENCH_UNIT_LENGTH", "284")))
+    ap.add_argument("--workload", default="benchmark", choices=["benchmark", "shipped", "langevin", "collision"])
+    ap.add_argument("--collision-scale", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -537,17 +644,24 @@ def main():
         # the run ends within a few minutes (about 0.25 s per step for two one-GPU systems on 16 cores)
         therm = args.thermalize + max(3, min(args.warmup, 5))
         loop = max(5, min(args.steps, 20))
-        r = run_reference_cpu(args.unit_length, args.gpus, therm, loop)
+        if args.workload == "benchmark":
+            r = run_reference_cpu(args.unit_length, args.gpus, therm, loop)
+        else:
+            r = run_reference_cpu_project(args.workload, args.unit_length, args.collision_scale, loop)
         n_units = r.get("cores", 1)
         line = {
             "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": (r["sec"] / r["steps"] * 1e3) if r.get("sec") else None, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "benchmark.cfg-shaped LJ FCC on the host CPU (reference arm of the %d-GPU run): one "
-                                   "cubic unit per host core, units of the 2x2x2 split of the one-GPU box (UnitLength=%g "
-                                   "per GPU), cutoff 3.0; each run a bounded sample: %d thermalise + %d timed steps, one "
-                                   "observation per %d steps" % (args.gpus, args.unit_length, therm, loop, OBSERVE_LOOP)},
+            "config": {"workload_key": args.workload,
+                       "workload": ("benchmark.cfg-shaped LJ FCC on the host CPU (reference arm of the %d-GPU run): one "
+                                    "cubic unit per host core, units of the 2x2x2 split of the one-GPU box (UnitLength=%g "
+                                    "per GPU), cutoff 3.0; each run a bounded sample: %d thermalise + %d timed steps, one "
+                                    "observation per %d steps" % (args.gpus, args.unit_length, therm, loop, OBSERVE_LOOP))
+                       if args.workload == "benchmark" else
+                       "reference arm of the %d-GPU %s run on the host CPU, bounded sample: %s" % (
+                           args.gpus, args.workload, r["sample"])},
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": n_units, "kind": r["kind"],
                              "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -558,7 +672,7 @@ def main():
 
     out, rank, world = run_ours(args)
     if rank == 0:
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "benchmark":
             try:
                 # bounded sample of the same workload in the same (thermalised) state: ThermalizeLoop + 12 timed steps
                 r = run_reference_cpu(args.unit_length, 1, args.thermalize, 12)

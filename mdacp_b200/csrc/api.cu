@@ -177,9 +177,11 @@ static int stage_barrier(Unit **us, int n) {
 static int materialize(Unit *u) {
   if (!u->predrifted) return MDB200_OK;
   DeviceGuard g(u->device);
-  MDB_TRY(drift_half_buffer(u, u->q_alt.ptr));  // last half-step positions + p dt/2, bit-identical to the plain path
+  // NVE: last half-step positions + p dt/2, bit-identical to the plain path; Langevin: they are the end-of-step
+  // positions already (mdmanager.cc:186-192 has no second half drift)
+  if (u->predrifted == 1) MDB_TRY(drift_half_buffer(u, u->q_alt.ptr));
   std::swap(u->q, u->q_alt);
-  u->predrifted = false;
+  u->predrifted = 0;
   return MDB200_OK;
 }
 
@@ -256,14 +258,17 @@ __global__ void k_pack_host_rows(const double *__restrict__ src4, double4 *__res
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double4 v = reinterpret_cast<const double4 *>(src4)[i];
-  if (zero_w) v.w = 0.0;
+  if (zero_w) v.w = v.y;  // positions: lane 3 repeats y on the device (tile.cuh)
   dst[i] = v;
 }
+// zero_w: positions leave the device with lane 3 = 0 as the reference's Variables::q has it
 __global__ void k_gather_ref_order(const double4 *__restrict__ src, const int *__restrict__ slot_of_ref,
-                                   double4 *__restrict__ dst, int pn, int tn) {
+                                   double4 *__restrict__ dst, int pn, int tn, int zero_w) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= tn) return;
-  dst[r] = src[(r < pn) ? slot_of_ref[r] : r];
+  double4 v = src[(r < pn) ? slot_of_ref[r] : r];
+  if (zero_w) v.w = 0.0;
+  dst[r] = v;
 }
 __global__ void k_gather_ref_order_i(const int *__restrict__ src, const int *__restrict__ slot_of_ref,
                                      int *__restrict__ dst, int pn) {
@@ -449,7 +454,9 @@ static int calculate(Unit **us, int n) {
   int expired = 0;
   MDB_TRY(any_expired(us, n, &expired));
   const bool ct = us[0]->prm.control_temperature != 0;
-  if (expired || ct)
+  const bool langevin = ct && us[0]->prm.heatbath_type != MDB200_HT_NOSEHOOVER;
+  static const bool no_predrift = getenv("MDB200_NO_PREDRIFT") != nullptr;
+  if (expired || (ct && !langevin) || no_predrift)
     for (int i = 0; i < n; i++) MDB_TRY(materialize(us[i]));
   if (expired) MDB_TRY(make_pairlist(us, n));
   // The force kernel walks the INNER list (force.cu): the entries of the pair list within cutoff + delta when it
@@ -466,11 +473,11 @@ static int calculate(Unit **us, int n) {
   for (int i = 0; i < n; i++) {
     DeviceGuard g(us[i]->device);
     PhaseTimer t(us[i], PH_INTEG);
-    if (us[i]->predrifted) us[i]->predrifted = false;  // the previous force kernel already did this half drift
+    if (us[i]->predrifted) us[i]->predrifted = 0;  // the previous force kernel already did this half drift
     else MDB_TRY(drift_half(us[i]));
   }
   // plain NVE: let the force kernel also do the first half drift of the next step (undone on demand)
-  const bool predrift = !ct && !getenv("MDB200_NO_PREDRIFT");
+  const bool predrift = !ct && !no_predrift;
   // one unit per process, neighbours behind NCCL, plain NVE: run the ghost exchange on a second stream and
   // let the interior force-warps (no ghost in their rows) start without waiting for it
   const bool split_test = getenv("MDB200_FORCE_SPLIT") != nullptr;
@@ -538,8 +545,17 @@ static int calculate(Unit **us, int n) {
     // MDManager::CalculateLangevin (mdmanager.cc:186-192): no second half drift (finding 5)
     for (int i = 0; i < n; i++) {
       DeviceGuard g(us[i]->device);
-      { PhaseTimer t(us[i], PH_FORCE); MDB_TRY(force_kick(us[i])); }
-      MDB_TRY(langevin_kick(us[i]));
+      PhaseTimer t(us[i], PH_FORCE);
+      force_timer_begin(us[i]);
+      if (no_predrift) {
+        MDB_TRY(force_kick(us[i]));
+        MDB_TRY(langevin_kick(us[i]));
+      } else {
+        // kick, Langevin update and the next step's first half drift in one launch (force.cu)
+        MDB_TRY(force_kick_langevin(us[i]));
+        us[i]->predrifted = 2;
+      }
+      force_timer_end(us[i]);
     }
   } else if (overlap) {
     // MDManager::CalculateForce (mdmanager.cc:151-157) with the ghost exchange (queued above on the second
@@ -551,7 +567,7 @@ static int calculate(Unit **us, int n) {
     MDB_CUDA(cudaStreamWaitEvent(u->stream, u->ev_ghost, 0));
     MDB_TRY(force_kick_drift(u, predrift, 2));
     force_timer_end(u);
-    u->predrifted = predrift;
+    u->predrifted = predrift ? 1 : 0;
   } else {
     // MDManager::CalculateForce (mdmanager.cc:151-157)
     for (int i = 0; i < n; i++) {
@@ -567,7 +583,7 @@ static int calculate(Unit **us, int n) {
           MDB_TRY(force_kick_drift(us[i], predrift, 0));
         }
         force_timer_end(us[i]);
-        us[i]->predrifted = predrift;
+        us[i]->predrifted = predrift ? 1 : 0;
       }
     }
   }
@@ -732,7 +748,7 @@ int mdb200_upload(mdb200_unit *h, const double (*q)[4], const double (*p)[4], co
   u->scratch_tail = pn;
   u->list_initialized = false;
   u->vmax_ready = false;
-  u->predrifted = false;
+  u->predrifted = 0;
   u->inner_valid = false;
   u->max_row = 0;
   u->npairs = 0;
@@ -760,12 +776,12 @@ int mdb200_download(mdb200_unit *h, double (*q)[4], double (*p)[4], int *type, l
   const long long qrows = cap_rows < u->tn ? cap_rows : u->tn;  // locals always, ghosts as far as they fit
   const unsigned nbt = (unsigned)((qrows + 255) / 256), nbp = (unsigned)((u->pn + 255) / 256);
   if (q) {
-    k_gather_ref_order<<<nbt, 256, 0, u->stream>>>(u->q.ptr, u->slot_of_ref.ptr, u->q_alt.ptr, (int)u->pn, (int)qrows);
+    k_gather_ref_order<<<nbt, 256, 0, u->stream>>>(u->q.ptr, u->slot_of_ref.ptr, u->q_alt.ptr, (int)u->pn, (int)qrows, 1);
     u->launches++;
     MDB_CUDA(cudaMemcpyAsync(q, u->q_alt.ptr, sizeof(double) * 4 * (size_t)qrows, cudaMemcpyDeviceToHost, u->stream));
   }
   if (p && u->pn) {
-    k_gather_ref_order<<<nbp, 256, 0, u->stream>>>(u->p.ptr, u->slot_of_ref.ptr, u->p_alt.ptr, (int)u->pn, (int)u->pn);
+    k_gather_ref_order<<<nbp, 256, 0, u->stream>>>(u->p.ptr, u->slot_of_ref.ptr, u->p_alt.ptr, (int)u->pn, (int)u->pn, 0);
     u->launches++;
     MDB_CUDA(cudaMemcpyAsync(p, u->p_alt.ptr, sizeof(double) * 4 * (size_t)u->pn, cudaMemcpyDeviceToHost, u->stream));
   }
@@ -814,8 +830,8 @@ int mdb200_snapshot_begin(mdb200_unit *h) {
     MDB_TRY(u->snap_p.ensure((size_t)pn));
     MDB_TRY(u->snap_t.ensure((size_t)pn));
     const unsigned nb = (unsigned)((pn + 255) / 256);
-    k_gather_ref_order<<<nb, 256, 0, u->stream>>>(u->q.ptr, u->slot_of_ref.ptr, u->snap_q.ptr, (int)pn, (int)pn);
-    k_gather_ref_order<<<nb, 256, 0, u->stream>>>(u->p.ptr, u->slot_of_ref.ptr, u->snap_p.ptr, (int)pn, (int)pn);
+    k_gather_ref_order<<<nb, 256, 0, u->stream>>>(u->q.ptr, u->slot_of_ref.ptr, u->snap_q.ptr, (int)pn, (int)pn, 1);
+    k_gather_ref_order<<<nb, 256, 0, u->stream>>>(u->p.ptr, u->slot_of_ref.ptr, u->snap_p.ptr, (int)pn, (int)pn, 0);
     k_gather_ref_order_i<<<nb, 256, 0, u->stream>>>(u->type.ptr, u->slot_of_ref.ptr, u->snap_t.ptr, (int)pn);
     u->launches += 3;
     MDB_CUDA(cudaGetLastError());
@@ -894,6 +910,7 @@ __global__ void k_scale_positions(double4 *__restrict__ q, int pn, double alpha)
   if (i >= pn) return;
   double4 v = q[i];
   v.x *= alpha; v.y *= alpha; v.z *= alpha;  // Variables::ChangeScale (variables.cc:133-139)
+  v.w = v.y;
   q[i] = v;
 }
 
@@ -1127,8 +1144,8 @@ int mdb200_event_elapsed_ms(mdb200_unit *h, int a, int b, double *ms) {
   return MDB200_OK;
 }
 // Measured FP64 peak of the device (the denominator of the force kernel's FP64 roofline fraction): 16 independent
-// DFMA chains per thread, two 1024-thread blocks per SM.
-__global__ void __launch_bounds__(1024, 2) k_fp64_peak(double *out, int iters, double a, double b) {
+// DFMA chains per thread, four 256-thread blocks per SM (64 registers per thread: the chains stay in registers).
+__global__ void __launch_bounds__(256, 4) k_fp64_peak(double *out, int iters, double a, double b) {
   double x[16];
 #pragma unroll
   for (int i = 0; i < 16; i++) x[i] = (double)(threadIdx.x + i) * 1e-3;
@@ -1154,16 +1171,16 @@ int mdb200_measure_fp64_peak(int device, double *tflops) {
   cudaEvent_t e0, e1;
   MDB_CUDA(cudaEventCreate(&e0));
   MDB_CUDA(cudaEventCreate(&e1));
-  const int iters = 4096, grid = 2 * sms;
+  const int iters = 4096, grid = 16 * sms;
   double best = 0.0;
   for (int rep = 0; rep < 5; rep++) {
     MDB_CUDA(cudaEventRecord(e0, 0));
-    k_fp64_peak<<<grid, 1024>>>(d, iters, 0.999999, 1e-7);
+    k_fp64_peak<<<grid, 256>>>(d, iters, 0.999999, 1e-7);
     MDB_CUDA(cudaEventRecord(e1, 0));
     MDB_CUDA(cudaEventSynchronize(e1));
     float ms = 0.f;
     MDB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    const double tf = 2.0 * 16.0 * iters * 1024.0 * grid / (ms * 1e-3) / 1e12;
+    const double tf = 2.0 * 16.0 * iters * 256.0 * grid / (ms * 1e-3) / 1e12;
     if (rep > 0 && tf > best) best = tf;
   }
   cudaEventDestroy(e0);

@@ -218,6 +218,7 @@ __global__ void k_wrap(double4 *__restrict__ q, const int *__restrict__ ord, int
   if (v.x < 0.0) v.x += c.L[0]; else if (v.x > c.L[0]) v.x -= c.L[0];
   if (v.y < 0.0) v.y += c.L[1]; else if (v.y > c.L[1]) v.y -= c.L[1];
   if (v.z < 0.0) v.z += c.L[2]; else if (v.z > c.L[2]) v.z -= c.L[2];
+  v.w = v.y;
   q[h] = v;
   bool bad = (v.x < 0.0 || v.x > c.L[0] || v.y < 0.0 || v.y > c.L[1] || v.z < 0.0 || v.z > c.L[2]);
   // NaN positions also count as invalid here (the reference would wander on)
@@ -307,7 +308,7 @@ __global__ void k_permute_locals(const double4 *__restrict__ q, const double4 *_
   int k = items[s];
   int h = ord[k];
   double4 qq = q[h];
-  qq.w = 0.0;
+  qq.w = qq.y;  // lane 3 of a position record repeats y (tile.cuh)
   q2[s] = qq;
   p2[s] = p[h];
   type2[s] = type[h];

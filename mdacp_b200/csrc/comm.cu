@@ -160,7 +160,7 @@ __global__ void k_ghost_put_p2p(const double4 *__restrict__ sq, const int *__res
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (ok && i < n) {
     double4 v = sq[border[i]];
-    v = make_double4(v.x + sx, v.y + sy, v.z + sz, 0.0);  // mdunit.cc:167
+    v = make_double4(v.x + sx, v.y + sy, v.z + sz, v.y + sy);  // mdunit.cc:167; lane 3 repeats y (tile.cuh)
     dq[i] = v;
     dq2[i] = v;
   }

@@ -17,7 +17,7 @@ __global__ void k_ghost_put(const double4 *__restrict__ sq, const int *__restric
   if (i >= n) return;
   double4 v = sq[border[i]];
   // q + diff per component, as mdunit.cc:167 (adding 0.0 is exact)
-  v = make_double4(v.x + sx, v.y + sy, v.z + sz, 0.0);
+  v = make_double4(v.x + sx, v.y + sy, v.z + sz, v.y + sy);  // lane 3 repeats y (tile.cuh)
   dq[i] = v;
   if (dq2) dq2[i] = v;
 }

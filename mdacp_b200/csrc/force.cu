@@ -25,11 +25,13 @@
 //
 // Roofline: algorithmic HBM bytes per particle = 4 B x P (half-list indices) + 96 B
 // (q read, p read + write), 30 flop per listed unordered pair.
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <map>
 #include <mutex>
 #include <utility>
+#include "rng.cuh"
 #include "tile.cuh"
 
 namespace mdb {
@@ -40,7 +42,7 @@ TileGrid tile_grid(const Unit *u);  // tile_search.cu
 #define FORCE_TPB 512
 #endif
 #ifndef DERIVE_TPB
-#define DERIVE_TPB 384
+#define DERIVE_TPB 512
 #endif
 
 struct ForceConsts {
@@ -51,6 +53,9 @@ struct ForceConsts {
   double c2x8dt;  // 8 C2 dt
   int cl2_hi;     // high word of CL2
   int exact_cut;  // low word of CL2 != 0: compare all 64 bits
+  // FORCE_KICK_LANGEVIN: ForceCalculator::Langevin (fcalculator.cc:765-778) in the epilogue
+  double dt, gamma, amp;
+  unsigned key0, key1, step_lo, step_hi;
 };
 
 __device__ __forceinline__ void lds128(unsigned a, double &x, double &y) {
@@ -108,7 +113,10 @@ __device__ __forceinline__ void pair_kick(unsigned o0, unsigned o1, double a0, d
 //   k_drift_half passes.  The end-of-step positions q[a] + p_new dt/2 are not stored; whoever needs them
 //   (rebuild, observation, download, displacement test) recomputes them bit-identically from the untouched
 //   input buffer and p_new (api.cu:materialize, integrate.cu).
-enum { FORCE_IMPULSE = 0, FORCE_KICK = 1, FORCE_KICK_DRIFT = 2, FORCE_KICK_DRIFT2 = 3 };
+// MODE 4: the Langevin step of MDManager::CalculateLangevin (mdmanager.cc:186-192): kick, then p += (-gamma p + xi) dt
+//   (rng.cuh), NO second half drift (SURVEY.md finding 5); the first half drift of the NEXT step is done
+//   speculatively, q_out[a] = q[a] + p_new dt/2, so the end-of-step positions are simply the untouched input buffer.
+enum { FORCE_IMPULSE = 0, FORCE_KICK = 1, FORCE_KICK_DRIFT = 2, FORCE_KICK_DRIFT2 = 3, FORCE_KICK_LANGEVIN = 4 };
 
 struct TileArgs {
   TileGrid g;
@@ -127,54 +135,81 @@ k_tile_force(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__re
   double4 *sq = reinterpret_cast<double4 *>(smem + tile_shared_offset());
   const int tile = ta.tile_order ? ta.tile_order[ta.tile_base + blockIdx.x] : (int)blockIdx.x;
   tile_setup(ts, tile, ta.g, c, ta.cell_start, ta.gcell_start);
-  tile_stage_f64(ts, q, ta.gitems, sq, nullptr);
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
+  const int gfw0 = ta.tile_fw0[tile];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int n_int = ts.n_int;
+  const int nfw = (n_int + kPW - 1) / kPW;
+  // A warp walks a CONTIGUOUS range of the tile's rows: their row blocks are contiguous in the list, so the list
+  // words are one stream per warp, loaded two chunks ahead across row boundaries.  The first two chunks are
+  // requested here, before the tile is staged.
+  const int rbase = nfw / nwarps, rrem = nfw - rbase * nwarps;
+  const int r0 = wid * rbase + min(wid, rrem), r1 = r0 + rbase + (wid < rrem ? 1 : 0);
+  const uint2 *__restrict__ lp = list + (r0 < r1 ? fw_off[gfw0 + r0] : fw_off[gfw0]) + lane;
+  uint2 wa = __ldg(lp), wb = __ldg(lp + 32);
+  tile_stage_rows(ts, gfw0, fw_off, fw_len);
+  tile_stage_tma(ts, q, ta.gitems, sq);
+  tile_stage_wait(ts);
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(sq);
   const unsigned gp = (lane >> 2) & 1u;                                // odd groups: x and z exchanged
   const unsigned hx = sbase + (gp << 4), hx2 = sbase + ((gp ^ 1u) << 4);
-  const int n_int = ts.n_int;
-  const int nfw = (n_int + kPW - 1) / kPW;
-  const int gfw0 = ta.tile_fw0[tile];
   double v2max = 0.0;
-  for (;;) {
-    int fw = 0;
-    if (lane == 0) fw = atomicAdd(&ts.next_row, 1);
-    fw = __shfl_sync(0xffffffffu, fw, 0);
-    if (fw >= nfw) break;
+  for (int fw = r0; fw < r1; fw++) {
+    // keep the stream ahead in L2: the row block two rows further on (one instruction, a 128-byte line per lane)
+    if (fw + 2 < r1) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(lp - lane + ts.row_off[fw + 2] - ts.row_off[fw]) + 128 * lane));
     const int a = fw * kPW + (lane >> 2);
     const bool act = a < n_int;
     const unsigned ao = (unsigned)(act ? a : ts.n_all) << 5;
     double a0, a1;
     lds128(ao + hx, a0, a1);
     const double a2 = lds64(ao + hx2);
-    const int steps = fw_len[gfw0 + fw];
-    const uint2 *__restrict__ lp = list + fw_off[gfw0 + fw] + lane;
-    // the writer lane's momentum is needed at the end of the row: start fetching its line now
+    const int steps = ts.row_len[fw];
+    // the writer lane's momentum is needed at the end of the row: pull its line (and the next row's) towards the SM
     int slot = 0;
     if (act && (lane & 3) == 0) {
       slot = tile_interior_slot(ts, a);
-      if (MODE != FORCE_IMPULSE) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + slot));
+      if (MODE != FORCE_IMPULSE) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + slot + kPW));
     }
     double f0 = 0.0, f1 = 0.0, f2 = 0.0;
-    // List words two chunks (8 steps) ahead of their use: a chunk takes a warp ~500 clk at 8 warps per scheduler,
-    // a miss to HBM ~1000.  The allocation is padded: loading two chunks past a row is harmless.
-    uint2 w1 = __ldg(lp), w2 = __ldg(lp + 32);
+    // List words two chunks (8 steps) ahead of their use: a chunk takes a warp ~500 clk at 8 warps per scheduler, a
+    // miss to HBM ~1000.  Two named buffers, reloaded in place (rotating one into the other makes the copy wait for
+    // the younger load: ncu showed 14 % of all stall samples there); at the end of a row they already hold the first
+    // two chunks of the next one.  The allocation is padded: loading three chunks past the last row is harmless.
+#define WALK_CHUNK(W, K)                                                          \
+  do {                                                                            \
+    const unsigned e0 = ((W).x & 0xffffu) << 5, e1 = ((W).x >> 16) << 5;          \
+    const unsigned e2 = ((W).y & 0xffffu) << 5, e3 = ((W).y >> 16) << 5;          \
+    pair_kick<EXACT>(e0 + hx, e0 + hx2, a0, a1, a2, fc, f0, f1, f2);              \
+    pair_kick<EXACT>(e1 + hx, e1 + hx2, a0, a1, a2, fc, f0, f1, f2);              \
+    if ((K) + 2 < steps) {                                                        \
+      pair_kick<EXACT>(e2 + hx, e2 + hx2, a0, a1, a2, fc, f0, f1, f2);            \
+      pair_kick<EXACT>(e3 + hx, e3 + hx2, a0, a1, a2, fc, f0, f1, f2);            \
+    }                                                                             \
+  } while (0)
 #pragma unroll 1
-    for (int k = 0; k < steps; k += 4) {
-      const uint2 w = w1;
-      w1 = w2;
-      w2 = __ldg(lp + 64);
-      lp += 32;
-      const unsigned e0 = (w.x & 0xffffu) << 5, e1 = (w.x >> 16) << 5;
-      pair_kick<EXACT>(e0 + hx, e0 + hx2, a0, a1, a2, fc, f0, f1, f2);
-      pair_kick<EXACT>(e1 + hx, e1 + hx2, a0, a1, a2, fc, f0, f1, f2);
-      if (k + 2 < steps) {
-        const unsigned e2 = (w.y & 0xffffu) << 5, e3 = (w.y >> 16) << 5;
-        pair_kick<EXACT>(e2 + hx, e2 + hx2, a0, a1, a2, fc, f0, f1, f2);
-        pair_kick<EXACT>(e3 + hx, e3 + hx2, a0, a1, a2, fc, f0, f1, f2);
+    for (int k = 0; k < steps; k += 8) {
+      {
+        const uint2 w = wa;
+        wa = __ldg(lp + 64);
+        WALK_CHUNK(w, k);
       }
+      if (k + 4 < steps) {
+        const uint2 w = wb;
+        wb = __ldg(lp + 96);
+        WALK_CHUNK(w, k + 4);
+      }
+      lp += 64;
     }
+#undef WALK_CHUNK
+    if (((steps + 3) >> 2) & 1) {
+      // odd number of chunks: wb still holds the chunk after the row's last one = the next row's first, wa the one
+      // after it, and lp is one chunk too far.  The older word moves (it has long arrived), the other is asked for again.
+      lp -= 32;
+      wa = wb;
+      wb = __ldg(lp + 32);
+    }
+    // the writer lane's momentum: requested before the reduction below needs it
+    double4 pa = make_double4(0.0, 0.0, 0.0, 0.0);
+    if (MODE != FORCE_IMPULSE && act && (lane & 3) == 0) pa = p[slot];
 #pragma unroll
     for (int o = kG / 2; o > 0; o >>= 1) {
       f0 += __shfl_xor_sync(0xffffffffu, f0, o);
@@ -187,22 +222,23 @@ k_tile_force(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__re
         const long long ra = ref_of_slot[slot];
         fout[3 * ra + 0] = fx; fout[3 * ra + 1] = fy; fout[3 * ra + 2] = fz;
       } else {
-        double4 pa = p[slot];
         pa.x += fx; pa.y += fy; pa.z += fz;
+        if (MODE == FORCE_KICK_LANGEVIN)
+          langevin_update(pa, (unsigned)ref_of_slot[slot], fc.gamma, fc.amp, fc.dt, fc.key0, fc.key1, fc.step_lo, fc.step_hi);
         p[slot] = pa;
-        if (MODE == FORCE_KICK_DRIFT || MODE == FORCE_KICK_DRIFT2) {
+        if (MODE == FORCE_KICK_DRIFT || MODE == FORCE_KICK_DRIFT2 || MODE == FORCE_KICK_LANGEVIN) {
           const double4 qa = sq[a];
           // fcalculator.cc:22-32, no FMA contraction: identical to k_drift_half
           const double sx = __dmul_rn(pa.x, fc.dt2), sy = __dmul_rn(pa.y, fc.dt2), sz = __dmul_rn(pa.z, fc.dt2);
           double nx = __dadd_rn(qa.x, sx), ny = __dadd_rn(qa.y, sy), nz = __dadd_rn(qa.z, sz);
           if (MODE == FORCE_KICK_DRIFT2) { nx = __dadd_rn(nx, sx); ny = __dadd_rn(ny, sy); nz = __dadd_rn(nz, sz); }
-          q_out[slot] = make_double4(nx, ny, nz, 0.0);
+          q_out[slot] = make_double4(nx, ny, nz, ny);  // lane 3 repeats y (tile.cuh)
           v2max = fmax(v2max, __dadd_rn(__dadd_rn(__dmul_rn(pa.x, pa.x), __dmul_rn(pa.y, pa.y)), __dmul_rn(pa.z, pa.z)));
         }
       }
     }
   }
-  if (MODE == FORCE_KICK_DRIFT || MODE == FORCE_KICK_DRIFT2) {
+  if (MODE == FORCE_KICK_DRIFT || MODE == FORCE_KICK_DRIFT2 || MODE == FORCE_KICK_LANGEVIN) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v2max = fmax(v2max, __shfl_xor_sync(0xffffffffu, v2max, o));
     if (lane == 0) {
@@ -236,44 +272,55 @@ k_tile_derive(TileArgs ta, Consts c, const double4 *__restrict__ q, const uint2 
   double4 *sq = reinterpret_cast<double4 *>(smem + tile_shared_offset());
   const int tile = ta.tile_order ? ta.tile_order[ta.tile_base + blockIdx.x] : (int)blockIdx.x;
   tile_setup(ts, tile, ta.g, c, ta.cell_start, ta.gcell_start);
-  tile_stage_f64(ts, q, ta.gitems, sq, nullptr);
-  __syncthreads();
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int gfw0 = ta.tile_fw0[tile];
+  tile_stage_rows(ts, gfw0, fw_off, fw_len);
+  tile_stage_tma(ts, q, ta.gitems, sq);
+  tile_stage_wait(ts);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   // row block of this warp: max_chunks x 32 words
   uint2 *rb = reinterpret_cast<uint2 *>(sq + ta.cap + 1) + (size_t)wid * max_chunks * 32;
   unsigned short *rb16 = reinterpret_cast<unsigned short *>(rb);
   const int n_int = ts.n_int;
   const int nfw = (n_int + kPW - 1) / kPW;
-  const int gfw0 = ta.tile_fw0[tile];
   const unsigned sent = (unsigned)ts.n_all;
   const uint2 sent2 = make_uint2(sent | (sent << 16), sent | (sent << 16));
   const int c4 = lane & 3, glane0 = lane & ~3;
-  for (;;) {
-    int fw = 0;
-    if (lane == 0) fw = atomicAdd(&ts.next_row, 1);
-    fw = __shfl_sync(0xffffffffu, fw, 0);
-    if (fw >= nfw) break;
+  // contiguous rows per warp, as in the force kernel
+  const int rbase = nfw / nwarps, rrem = nfw - rbase * nwarps;
+  const int r0 = wid * rbase + min(wid, rrem), r1 = r0 + rbase + (wid < rrem ? 1 : 0);
+  constexpr int NB = 8;  // chunks held in registers (rows of up to 32 steps; longer rows take another trip)
+  for (int fw = r0; fw < r1; fw++) {
     const int a = fw * kPW + (lane >> 2);
-    const double4 qa = sq[a < n_int ? a : ts.n_all];
-    const int steps = fw_len[gfw0 + fw];
-    const uint2 *__restrict__ lp = list + fw_off[gfw0 + fw] + lane;
+    const bool act = a < n_int;       // the last force-warp of a tile may own fewer than 8 locals
+    const double4 qa = sq[act ? a : ts.n_all];
+    const int steps = ts.row_len[fw];
+    const uint2 *__restrict__ lp = list + ts.row_base + ts.row_off[fw] + lane;
+    if (fw + 1 < r1) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(lp - lane + ts.row_off[fw + 1] - ts.row_off[fw]) + 128 * lane));
     const int nchunk = (steps + 3) >> 2;
     // ---- pass A: which of this lane's entries stay (bit 4 c + s of the mask: step 4 c + s), how many per class
     unsigned long long keep = 0ull;   // rows of at most 16 chunks = 64 steps = 256 entries (derive_inner checks)
     unsigned kcnt = 0u;
-    const bool act = a < n_int;       // the last force-warp of a tile may own fewer than 8 locals
-    for (int ch = 0; ch < nchunk; ch++) {
-      const uint2 w = __ldg(lp + 32 * ch);
-      unsigned m = 0u;
+    uint2 w[NB];
+#pragma unroll 1
+    for (int cb = 0; cb < nchunk; cb += NB) {
 #pragma unroll
-      for (int s = 0; s < 4; s++) {
-        const unsigned j = ((s < 2 ? w.x : w.y) >> (16 * (s & 1))) & 0xffffu;
-        const double4 qj = sq[j];
-        const double dx = qj.x - qa.x, dy = qj.y - qa.y, dz = qj.z - qa.z;
-        const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-        if (act && r2 <= keep2 && 4 * ch + s < steps) { m |= 1u << s; kcnt += 1u << (8 * (j & 3u)); }
+      for (int i = 0; i < NB; i++) w[i] = (cb + i < nchunk) ? __ldg(lp + 32 * (cb + i)) : sent2;  // all in flight together
+#pragma unroll
+      for (int i = 0; i < NB; i++) {
+        const int ch = cb + i;
+        if (ch < nchunk) {
+          unsigned m = 0u;
+#pragma unroll
+          for (int s2 = 0; s2 < 4; s2++) {
+            const unsigned j = ((s2 < 2 ? w[i].x : w[i].y) >> (16 * (s2 & 1))) & 0xffffu;
+            const double4 qj = sq[j];
+            const double dx = qj.x - qa.x, dy = qj.y - qa.y, dz = qj.z - qa.z;
+            const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            if (act && r2 <= keep2 && 4 * ch + s2 < steps) { m |= 1u << s2; kcnt += 1u << (8 * (j & 3u)); }
+          }
+          keep |= (unsigned long long)m << (4 * ch);
+        }
       }
-      keep |= (unsigned long long)m << (4 * ch);
     }
     // ---- ordinals: inclusive scan of the packed class counts over the 4 lanes of the group
     unsigned incl = kcnt;
@@ -293,25 +340,32 @@ k_tile_derive(TileArgs ta, Consts c, const double4 *__restrict__ q, const uint2 
     for (int i = lane; i < nchunk_in * 32; i += 32) rb[i] = sent2;
     __syncwarp();
     const int m = rainbow_min(tot);
-    for (int ch = 0; ch < nchunk; ch++) {
-      const unsigned km = (unsigned)((keep >> (4 * ch)) & 0xFull);
-      if (km == 0u) continue;
-      const uint2 w = __ldg(lp + 32 * ch);  // the row was just read: L1 / L2 hit
+#pragma unroll 1
+    for (int cb = 0; cb < nchunk; cb += NB) {
+      if (nchunk > NB) {  // long row: the words of this trip again (the short ones are still in registers)
 #pragma unroll
-      for (int s = 0; s < 4; s++) {
-        if (km & (1u << s)) {
-          const unsigned j = ((s < 2 ? w.x : w.y) >> (16 * (s & 1))) & 0xffffu;
-          const int cc = (int)(j & 3u);
-          const int tt = (int)((run >> (8 * cc)) & 0xFFu);
-          run += 1u << (8 * cc);
-          const int ee = rainbow_place(tot, m, cc, tt);  // entry index of the local: lane ee & 3, step ee >> 2
-          const int st = ee >> 2;
-          rb16[((st >> 2) * 32 + glane0 + (ee & 3)) * 4 + (st & 3)] = (unsigned short)j;
+        for (int i = 0; i < NB; i++) w[i] = (cb + i < nchunk) ? __ldg(lp + 32 * (cb + i)) : sent2;
+      }
+#pragma unroll
+      for (int i = 0; i < NB; i++) {
+        const int ch = cb + i;
+        const unsigned km = (ch < nchunk) ? (unsigned)((keep >> (4 * ch)) & 0xFull) : 0u;
+#pragma unroll
+        for (int s2 = 0; s2 < 4; s2++) {
+          if (km & (1u << s2)) {
+            const unsigned j = ((s2 < 2 ? w[i].x : w[i].y) >> (16 * (s2 & 1))) & 0xffffu;
+            const int cc = (int)(j & 3u);
+            const int tt = (int)((run >> (8 * cc)) & 0xFFu);
+            run += 1u << (8 * cc);
+            const int ee = rainbow_place(tot, m, cc, tt);  // entry index of the local: lane ee & 3, step ee >> 2
+            const int st = ee >> 2;
+            rb16[((st >> 2) * 32 + glane0 + (ee & 3)) * 4 + (st & 3)] = (unsigned short)j;
+          }
         }
       }
     }
     __syncwarp();
-    uint2 *__restrict__ dst = list_in + fw_off[gfw0 + fw];
+    uint2 *__restrict__ dst = list_in + ts.row_base + ts.row_off[fw];
     for (int i = lane; i < nchunk_in * 32; i += 32) dst[i] = rb[i];
     if (lane == 0) fw_len_in[gfw0 + fw] = steps_in;
     __syncwarp();
@@ -329,6 +383,15 @@ static ForceConsts make_fc(const Unit *u) {
   memcpy(&b, &fc.CL2, sizeof(b));
   fc.cl2_hi = (int)(b >> 32);
   fc.exact_cut = (unsigned)(b & 0xffffffffll) != 0u;
+  // Langevin constants as in integrate.cu:langevin_kick
+  fc.dt = u->c.dt;
+  fc.gamma = u->prm.heatbath_gamma;
+  fc.amp = sqrt(2.0 * u->prm.heatbath_gamma * u->prm.aimed_temperature / u->c.dt);  // hb_D, fcalculator.cc:771
+  const unsigned long long sc = (unsigned long long)u->step_count;
+  fc.key0 = (unsigned)(u->seed + u->prm.unit_id);  // MDUnit::SetSeed: seed + id (mdunit.h:58)
+  fc.key1 = 0x6d646163u;                            // "mdac"
+  fc.step_lo = (unsigned)(sc & 0xffffffffu);
+  fc.step_hi = (unsigned)(sc >> 32);
   return fc;
 }
 
@@ -402,6 +465,7 @@ static int force_launch(Unit *u, int mode, double *fout, int part = 0) {
     if (mode == FORCE_IMPULSE) KLAUNCH(FORCE_IMPULSE, E);  \
     else if (mode == FORCE_KICK) KLAUNCH(FORCE_KICK, E);   \
     else if (mode == FORCE_KICK_DRIFT) KLAUNCH(FORCE_KICK_DRIFT, E); \
+    else if (mode == FORCE_KICK_LANGEVIN) KLAUNCH(FORCE_KICK_LANGEVIN, E); \
     else KLAUNCH(FORCE_KICK_DRIFT2, E);                    \
   } while (0)
   if (fc.exact_cut) LAUNCH(true);
@@ -442,6 +506,17 @@ int force_kick_drift(Unit *u, bool predrift, int part) {
     std::swap(u->q, u->q_alt);  // ghosts live in both buffers (exchange.cu)
     u->vmax_ready = true;
   }
+  return MDB200_OK;
+}
+
+// MDManager::CalculateLangevin (mdmanager.cc:186-192) in one kernel: kick, Langevin update of the momenta and --
+// speculatively -- the next step's first half drift (the caller sets u->predrifted = 2: the end-of-step positions
+// are the untouched input buffer).  Swaps q / q_alt.
+int force_kick_langevin(Unit *u) {
+  if (u->pn == 0 || u->ntiles == 0) return MDB200_OK;
+  MDB_TRY(force_launch(u, FORCE_KICK_LANGEVIN, nullptr, 0));
+  std::swap(u->q, u->q_alt);  // ghosts live in both buffers (exchange.cu)
+  u->vmax_ready = true;
   return MDB200_OK;
 }
 

@@ -11,6 +11,7 @@
 // contraction happens: it then matches the scalar x86-64 reference bit for bit on equal inputs.
 // All kernels are HBM-bound streams: 64 B read + 32 B written per particle for the drift.
 #include <math.h>
+#include "rng.cuh"
 #include "unit.h"
 
 namespace mdb {
@@ -46,6 +47,7 @@ __global__ void k_drift_half(double4 *__restrict__ q, const double4 *__restrict_
   qq.x = __dadd_rn(qq.x, __dmul_rn(pp.x, dt2));
   qq.y = __dadd_rn(qq.y, __dmul_rn(pp.y, dt2));
   qq.z = __dadd_rn(qq.z, __dmul_rn(pp.z, dt2));
+  qq.w = qq.y;  // lane 3 of a position record repeats y (tile.cuh)
   q[i] = qq;
 }
 
@@ -80,59 +82,14 @@ int heatbath_momenta(Unit *u) {
   return MDB200_OK;
 }
 
-// Counter-based per-particle RNG (Philox4x32-10): the reference draws 3 normals per particle in
-// index order from one sequential std::mt19937 per unit (fcalculator.cc:772-777), which a
-// data-parallel kernel cannot reproduce bit-wise (SURVEY.md finding 5 / row a10).  Parity is
-// exact for AimedTemperature = 0 (noise amplitude 0) and statistical otherwise.
-__device__ __forceinline__ void philox_round(unsigned &c0, unsigned &c1, unsigned &c2, unsigned &c3, unsigned k0,
-                                             unsigned k1) {
-  const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
-  unsigned hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
-  unsigned hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
-  unsigned n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-  c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-}
-__device__ __forceinline__ void philox4x32(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0,
-                                           unsigned k1, unsigned out[4]) {
-#pragma unroll
-  for (int r = 0; r < 10; r++) {
-    philox_round(c0, c1, c2, c3, k0, k1);
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-__device__ __forceinline__ double u01(unsigned hi, unsigned lo) {
-  // (0,1]: 53 random bits, never 0 so that log() is finite
-  unsigned long long b = (((unsigned long long)hi << 32) | lo) >> 11;
-  return ((double)b + 1.0) * (1.0 / 9007199254740992.0);
-}
-
+// (per-particle counter RNG and the Langevin update: rng.cuh, shared with the fused force kernel)
 __global__ void k_langevin(double4 *__restrict__ p, const int *__restrict__ ref_of_slot, int pn, double gamma,
                            double amp, double dt, unsigned key0, unsigned key1, unsigned step_lo,
                            unsigned step_hi) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= pn) return;
-  double n0 = 0.0, n1 = 0.0, n2 = 0.0;
-  if (amp != 0.0) {
-    unsigned r[4], s[4];
-    unsigned id = (unsigned)ref_of_slot[i];
-    philox4x32(id, step_lo, step_hi, 0u, key0, key1, r);
-    philox4x32(id, step_lo, step_hi, 1u, key0, key1, s);
-    double ua = u01(r[0], r[1]), ub = u01(r[2], r[3]);
-    double uc = u01(s[0], s[1]), ud = u01(s[2], s[3]);
-    double ra = sqrt(-2.0 * log(ua)), rc = sqrt(-2.0 * log(uc));
-    double sa, ca, sc, cc;
-    sincospi(2.0 * ub, &sa, &ca);
-    sincospi(2.0 * ud, &sc, &cc);
-    n0 = ra * ca; n1 = ra * sa; n2 = rc * cc;
-    (void)sc;
-  }
   double4 v = p[i];
-  // p += (-gamma * p + xi) * dt, evaluated in the reference's operation order without FMA
-  v.x = __dadd_rn(v.x, __dmul_rn(__dadd_rn(__dmul_rn(-gamma, v.x), __dmul_rn(amp, n0)), dt));
-  v.y = __dadd_rn(v.y, __dmul_rn(__dadd_rn(__dmul_rn(-gamma, v.y), __dmul_rn(amp, n1)), dt));
-  v.z = __dadd_rn(v.z, __dmul_rn(__dadd_rn(__dmul_rn(-gamma, v.z), __dmul_rn(amp, n2)), dt));
+  langevin_update(v, (unsigned)ref_of_slot[i], gamma, amp, dt, key0, key1, step_lo, step_hi);
   p[i] = v;
 }
 
@@ -318,9 +275,12 @@ int expiry_check_launch(Unit *u) {
     k_expiry_vmax<<<grid_p, TPB, 0, u->stream>>>(u->p.ptr, (int)u->pn, u->ctrl, u->c.dt, u->c.BL);
   u->vmax_ready = false;
   const double4 *qprev = u->predrifted ? u->q_alt.ptr : nullptr;
-  k_expiry_disp<<<grid_t, TPB, 0, u->stream>>>(u->q.ptr, qprev, u->p.ptr, (int)u->pn, u->c.dt2, u->q0.ptr, u->disp.ptr,
+  // pre-drifted after a Langevin step (predrifted == 2): the end-of-step positions are the previous buffer as it
+  // is, i.e. "previous + p * 0" (adding +-0 is exact)
+  const double dt2 = (u->predrifted == 2) ? 0.0 : u->c.dt2;
+  k_expiry_disp<<<grid_t, TPB, 0, u->stream>>>(u->q.ptr, qprev, u->p.ptr, (int)u->pn, dt2, u->q0.ptr, u->disp.ptr,
                                                (int)u->tn, u->ctrl, u->c.BL);
-  k_expiry_cand<<<grid_t, TPB, 0, u->stream>>>(u->q.ptr, qprev, u->p.ptr, (int)u->pn, u->c.dt2, u->q0.ptr, u->disp.ptr,
+  k_expiry_cand<<<grid_t, TPB, 0, u->stream>>>(u->q.ptr, qprev, u->p.ptr, (int)u->pn, dt2, u->q0.ptr, u->disp.ptr,
                                                u->cand.ptr, (int)u->tn, Nl, u->ctrl, u->c.SL2, u->c.CL2);
   u->launches += 3;
   MDB_CUDA(cudaGetLastError());

@@ -18,7 +18,7 @@ namespace mdb {
 
 TileGrid tile_grid(const Unit *u);  // tile_search.cu
 
-static const int TPB = 256;
+static const int TPB = 512;   // two blocks of 512 threads per SM next to their staged tiles
 static const int MAXBLK = 1184;  // 8 x 148 SMs
 
 __device__ __forceinline__ double block_sum(double v, double *sh) {
@@ -60,7 +60,7 @@ __device__ __forceinline__ void pair_uw(double dx, double dy, double dz, double 
 // K over locals (grid-stride over particles) and U, W over the OUTER list, one block per tile (tile.cuh): the
 // positions of the tile and its halo are staged in shared memory, kG lanes per local, each lane takes every
 // kG-th entry of the row (unit.h).
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(TPB, 2)
 k_observe(TileGrid g, Consts c, const int *__restrict__ cell_start, const int *__restrict__ gcell_start,
           const int *__restrict__ gitems, const int *__restrict__ tile_fw0, const double4 *__restrict__ q,
           const double4 *__restrict__ p, const uint2 *__restrict__ list, const long long *__restrict__ fw_off,
@@ -81,8 +81,8 @@ k_observe(TileGrid g, Consts c, const int *__restrict__ cell_start, const int *_
   if (have_list) {
     const int tile = blockIdx.x;
     tile_setup(ts, tile, g, c, cell_start, gcell_start);
-    tile_stage_f64(ts, q, gitems, sq, nullptr);
-    __syncthreads();
+    tile_stage_tma(ts, q, gitems, sq);
+    tile_stage_wait(ts);
     const int lane = threadIdx.x & 31;
     const int nfw = (ts.n_int + kPW - 1) / kPW, gfw0 = tile_fw0[tile];
     for (int fw = threadIdx.x >> 5; fw < nfw; fw += blockDim.x >> 5) {

@@ -30,12 +30,12 @@ struct TileGrid {
 constexpr int kTileMaxEdge = 3;
 constexpr int kTileMaxCells = (kTileMaxEdge + 2) * (kTileMaxEdge + 2) * (kTileMaxEdge + 2);
 constexpr int kTileMaxInterior = kTileMaxEdge * kTileMaxEdge * kTileMaxEdge;
+constexpr int kTileMaxRows = 144;    // force-warps of a tile (8 interior locals each): tile_search.cu checks the census
 
-struct TileCell {            // one cell of the tile's halo box
-  int src_l, n_l, off_l;     // locals: first slot, count, first staged index
-  int src_g, n_g, off_g;     // ghosts: first entry of gcell_items, count, first staged index
-  int interior;              // 1 = one of the tile's own cells
-  int pad;
+struct TileCell {                 // one cell of the tile's halo box (16 bytes: the table shares the SM's shared
+  int src_l, src_g;               // memory with the staged tile) -- first slot of the locals / first entry of gcell_items
+  unsigned short n_l, n_g;        // counts
+  unsigned short off_l, off_g;    // first staged index of the locals / ghosts
 };
 
 struct TileShared {          // per-block bookkeeping in shared memory
@@ -51,11 +51,43 @@ struct TileShared {          // per-block bookkeeping in shared memory
   int icell_off[kTileMaxInterior + 1];  // staged offset of interior cell i (ascending)
   int icell_src[kTileMaxInterior];      // its first slot
   int icell_k[kTileMaxInterior];        // its index in cell[]
+  unsigned char interior[kTileMaxCells + 3];  // 1 = one of the tile's own cells
+  // row blocks of the tile's force-warps in the list being walked (filled by tile_stage_rows): first uint2 word
+  // relative to the tile's first row block, and steps
+  long long row_base;
+  unsigned long long mbar;              // mbarrier of the bulk copies that stage the tile (tile_stage_tma)
+  int row_off[kTileMaxRows];
+  unsigned short row_len[kTileMaxRows];
 };
 
 // Shared memory of a kernel that stages FP64 records: bookkeeping + (records + sentinel) x 32 bytes
 __host__ __device__ inline size_t tile_shared_offset() { return (sizeof(TileShared) + 127) & ~(size_t)127; }
 inline size_t tile_smem_bytes_f64(int cap_records) { return tile_shared_offset() + (size_t)(cap_records + 1) * 32; }
+
+// ---- mbarrier / bulk-copy (TMA) primitives ------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy (16-byte aligned, a multiple of 16 bytes); completion is counted on the mbarrier
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
 
 // k / n for the small operands of a halo box (k < 128, n <= 25) without the integer-division sequence:
 // floor(k M / 65536) = floor(k / n) for every M in [ceil(65536 / n), ceil(65536 / n) + 1] while 2 k n < 65536,
@@ -87,19 +119,19 @@ __device__ __forceinline__ void tile_setup(TileShared &ts, int tile, const TileG
     for (int d = 0; d < 3; d++) { ts.lo[d] = lo[d]; ts.n[d] = n[d]; }
     ts.ncells = ncells;
     ts.next_row = 0;
+    mbar_init(&ts.mbar, 1);  // made visible to the async proxy by the fence + barriers below
   }
   if (tid < ncells) {
     const int kz = small_div(tid, small_magic(n01)), r = tid - kz * n01, ky = small_div(r, small_magic(n[0])), kx = r - ky * n[0];
     const int gc = (lo[0] + kx) + c.m[0] * ((lo[1] + ky) + c.m[1] * (lo[2] + kz));
     TileCell tc;
     tc.src_l = cell_start[gc];
-    tc.n_l = cell_start[gc + 1] - tc.src_l;
+    tc.n_l = (unsigned short)min(cell_start[gc + 1] - tc.src_l, 65535);   // the census bounds a tile to 6,400 records
     tc.src_g = gcell_start[gc];
-    tc.n_g = gcell_start[gc + 1] - tc.src_g;
+    tc.n_g = (unsigned short)min(gcell_start[gc + 1] - tc.src_g, 65535);
     tc.off_l = 0;
     tc.off_g = 0;
-    tc.interior = (kx >= 1 && kx <= n[0] - 2 && ky >= 1 && ky <= n[1] - 2 && kz >= 1 && kz <= n[2] - 2) ? 1 : 0;
-    tc.pad = 0;
+    ts.interior[tid] = (kx >= 1 && kx <= n[0] - 2 && ky >= 1 && ky <= n[1] - 2 && kz >= 1 && kz <= n[2] - 2) ? 1 : 0;
     ts.cell[tid] = tc;
   }
   __syncthreads();
@@ -109,7 +141,7 @@ __device__ __forceinline__ void tile_setup(TileShared &ts, int tile, const TileG
     for (int k0 = 0; k0 < ncells; k0 += 32) {
       const int k = k0 + tid;
       const bool valid = k < ncells;
-      const bool inter = valid && ts.cell[k].interior;
+      const bool inter = valid && ts.interior[k];
       const int nl = valid ? ts.cell[k].n_l : 0, ng = valid ? ts.cell[k].n_g : 0;
       int a = inter ? nl : 0, b = inter ? 0 : nl, cg = ng, fi = inter ? 1 : 0;
       int sa = a, sb = b, sc = cg, si = fi;
@@ -120,8 +152,8 @@ __device__ __forceinline__ void tile_setup(TileShared &ts, int tile, const TileG
         if (tid >= o) { sa += ta; sb += tb; sc += tc; si += ti; }
       }
       if (valid) {
-        ts.cell[k].off_l = inter ? base_a + sa - a : base_b + sb - b;  // halo locals: n_int added below
-        ts.cell[k].off_g = base_c + sc - cg;                            // n_loc added below
+        ts.cell[k].off_l = (unsigned short)(inter ? base_a + sa - a : base_b + sb - b);  // halo locals: n_int added below
+        ts.cell[k].off_g = (unsigned short)(base_c + sc - cg);                            // n_loc added below
         if (inter) {
           const int i = base_i + si - 1;
           ts.icell_off[i] = base_a + sa - a;
@@ -136,8 +168,8 @@ __device__ __forceinline__ void tile_setup(TileShared &ts, int tile, const TileG
     }
     __syncwarp();
     for (int k = tid; k < ncells; k += 32) {
-      if (!ts.cell[k].interior) ts.cell[k].off_l += base_a;
-      ts.cell[k].off_g += base_a + base_b;
+      if (!ts.interior[k]) ts.cell[k].off_l = (unsigned short)(ts.cell[k].off_l + base_a);
+      ts.cell[k].off_g = (unsigned short)(ts.cell[k].off_g + base_a + base_b);
     }
     if (tid == 0) {
       ts.n_int = base_a;
@@ -168,12 +200,12 @@ __device__ __forceinline__ double4 ld_q256(const double4 *p) {
 // Copies the tile's records into sq as (x, y, z, y): the duplicate y lets odd lane groups read (z, y) first and
 // x second while even groups read (x, y) and z -- see force.cu.  The sentinel goes to sq[n_all].  sslot (may be
 // null): the slot of every staged record.  No barrier at the end.
-constexpr int kStageBatch = 3;
+constexpr int kStageBatch = 2;
 __device__ __forceinline__ void tile_stage_f64(const TileShared &ts, const double4 *__restrict__ q,
                                                const int *__restrict__ gitems, double4 *sq, int *sslot) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int ncells = ts.ncells;
-  // three cells per trip, their loads issued together: a thread copies only ~6 records, so the copy is pure latency
+  // two cells per trip, their loads issued together: a thread copies only ~6 records, so the copy is pure latency
   for (int k0 = wid; k0 < ncells; k0 += kStageBatch * nw) {
     int src[kStageBatch], off[kStageBatch], nl[kStageBatch];
     double4 v[kStageBatch];
@@ -217,6 +249,52 @@ __device__ __forceinline__ void tile_stage_f64(const TileShared &ts, const doubl
     }
   }
   if (threadIdx.x == 0) sq[ts.n_all] = make_double4(1.0e8, 1.0e8, 1.0e8, 1.0e8);
+}
+
+// The same staging without the load/store units: position records carry (x, y, z, y) in global memory already
+// (every kernel that writes a position keeps lane 3 = y), so the locals of a cell are ONE contiguous bulk copy
+// (TMA, cp.async.bulk) into their place in the staged array; the lanes of warp 0 issue one copy per cell, the
+// mbarrier in ts counts the bytes.  Ghosts (binned by index, boundary tiles only) are gathered by the other warps
+// as before.  Every thread must call tile_stage_wait before it reads sq; no barrier here.
+__device__ __forceinline__ void tile_stage_tma(TileShared &ts, const double4 *__restrict__ q, const int *__restrict__ gitems,
+                                               double4 *sq) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int ncells = ts.ncells;
+  if (wid == 0) {
+    if (lane == 0) mbar_arrive_expect_tx(&ts.mbar, (unsigned)ts.n_loc * 32u);
+    __syncwarp();
+    for (int k = lane; k < ncells; k += 32) {
+      const int nl = ts.cell[k].n_l;
+      if (nl > 0) bulk_copy_g2s(sq + ts.cell[k].off_l, q + ts.cell[k].src_l, (unsigned)nl * 32u, &ts.mbar);
+    }
+    if (lane == 0) sq[ts.n_all] = make_double4(1.0e8, 1.0e8, 1.0e8, 1.0e8);
+  } else if (ts.n_all > ts.n_loc) {
+    for (int k = wid - 1; k < ncells; k += nw - 1) {
+      const int ng = ts.cell[k].n_g;
+      if (ng > 0) {
+        const int sg = ts.cell[k].src_g, og = ts.cell[k].off_g;
+        for (int l = lane; l < ng; l += 32) sq[og + l] = ld_q256(q + gitems[sg + l]);
+      }
+    }
+  }
+}
+// completes tile_stage_tma: the bulk copies have landed and every thread's own stores are visible
+__device__ __forceinline__ void tile_stage_wait(TileShared &ts) {
+  mbar_wait(&ts.mbar, 0u);
+  __syncthreads();
+}
+
+// Row table of the tile in shared memory: the walk then starts a row without waiting for two dependent global loads.
+// No barrier at the end.
+__device__ __forceinline__ void tile_stage_rows(TileShared &ts, int gfw0, const long long *__restrict__ fw_off,
+                                                const int *__restrict__ fw_len) {
+  const int nfw = (ts.n_int + kPW - 1) / kPW;
+  const long long base = fw_off[gfw0];
+  if (threadIdx.x == 0) ts.row_base = base;
+  for (int r = threadIdx.x; r < nfw; r += blockDim.x) {
+    ts.row_off[r] = (int)(fw_off[gfw0 + r] - base);
+    ts.row_len[r] = (unsigned short)fw_len[gfw0 + r];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -191,32 +191,51 @@ k_tile_search(TileGrid g, Consts c, const double4 *__restrict__ q, const int *__
         for (int j0 = 0; j0 < cnt_all; j0 += 32) {
           const int cnt = min(32, cnt_all - j0);
           const float4 *cand = sf + jb + j0;
-          unsigned hm = 0u, am = 0u;
-#pragma unroll 4
-          for (int t = 0; t < cnt; t++) {
-            const float4 s = cand[t];
-            const float dx = s.x - me.x, dy = s.y - me.y, dz = s.z - me.z;
-            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            hm |= (r2 <= lo_t ? 1u : 0u) << t;
-            am |= (r2 > hi_t ? 0u : 1u) << t;   // not a sure miss (NaN included)
+          // bit t: candidate t is not a sure miss (r2 <= hi_t, NaN included): a superset of the hits
+          unsigned hm = 0u, bit = 1u;
+          int t = 0;
+          for (; t + 4 <= cnt; t += 4) {
+            const float4 s0 = cand[t], s1 = cand[t + 1], s2 = cand[t + 2], s3 = cand[t + 3];
+            const float x0 = s0.x - me.x, y0 = s0.y - me.y, z0 = s0.z - me.z;
+            const float x1 = s1.x - me.x, y1 = s1.y - me.y, z1 = s1.z - me.z;
+            const float x2 = s2.x - me.x, y2 = s2.y - me.y, z2 = s2.z - me.z;
+            const float x3 = s3.x - me.x, y3 = s3.y - me.y, z3 = s3.z - me.z;
+            const float q0 = fmaf(z0, z0, fmaf(y0, y0, x0 * x0)), q1 = fmaf(z1, z1, fmaf(y1, y1, x1 * x1));
+            const float q2 = fmaf(z2, z2, fmaf(y2, y2, x2 * x2)), q3 = fmaf(z3, z3, fmaf(y3, y3, x3 * x3));
+            if (!(q0 > hi_t)) hm |= bit;
+            if (!(q1 > hi_t)) hm |= bit << 1;
+            if (!(q2 > hi_t)) hm |= bit << 2;
+            if (!(q3 > hi_t)) hm |= bit << 3;
+            bit <<= 4;
           }
-          am &= ~hm;
-          if (!act) { hm = 0u; am = 0u; }
+          for (; t < cnt; t++) {
+            const float4 s0 = cand[t];
+            const float x0 = s0.x - me.x, y0 = s0.y - me.y, z0 = s0.z - me.z;
+            if (!(fmaf(z0, z0, fmaf(y0, y0, x0 * x0)) > hi_t)) hm |= bit;
+            bit <<= 1;
+          }
+          if (!act) hm = 0u;
           const unsigned self = (unsigned)(a - (jb + j0));
-          if (self < 32u) { hm &= ~(1u << self); am &= ~(1u << self); }
-          // the shell around SL^2: exact FP64 predicate on the global records
-          while (am) {
-            const int b = __ffs(am) - 1;
-            am &= am - 1u;
-            const int sj = gh ? gitems[tc.src_g + j0 + b] : tc.src_l + j0 + b;
-            if (within_search(q[own.src_l + l], q[sj], c.SL2)) hm |= 1u << b;
-          }
-          n += __popc(hm);
-          if (FILL) {
+          if (self < 32u) hm &= ~(1u << self);
+          if (!FILL) {
+            // row lengths from the superset: at most a few entries per thousand rows too many, which can only make
+            // a row block one step longer than needed
+            n += __popc(hm);
+          } else {
             while (hm) {
               const int b = __ffs(hm) - 1;
               hm &= hm - 1u;
-              my[sector_byte(e) >> 1] = (unsigned short)(jb + j0 + b);
+              const int j = jb + j0 + b;
+              // the shell around SL^2 (r2 between the sure-hit and the sure-miss threshold): exact FP64 predicate
+              // on the global records
+              const float4 sj = sf[j];
+              const float xj = sj.x - me.x, yj = sj.y - me.y, zj = sj.z - me.z;
+              if (!(fmaf(zj, zj, fmaf(yj, yj, xj * xj)) <= lo_t)) {
+                const int gj = gh ? gitems[tc.src_g + j0 + b] : tc.src_l + j0 + b;
+                if (!within_search(q[own.src_l + l], q[gj], c.SL2)) continue;
+              }
+              n++;
+              my[sector_byte(e) >> 1] = (unsigned short)j;
               e++;
               if ((e & 15) == 0) {
                 const uint4 *s4 = reinterpret_cast<const uint4 *>(my);
@@ -246,26 +265,27 @@ k_tile_search(TileGrid g, Consts c, const double4 *__restrict__ q, const int *__
             rowp[16 * ch + 1] = s4;
           }
         }
+        if (act) {
+          row_count[own.src_l + l] = n;   // exact
+          nref += (unsigned long long)(nloc + 2 * (n - nloc));
+        }
       } else {
         if (act) {
-          row_n[a] = n;
-          row_count[own.src_l + l] = n;
-          nref += (unsigned long long)(nloc + 2 * (n - nloc));
+          row_n[a] = n;                   // upper bound (see above)
           mrow = max(mrow, n);
         }
       }
     }
   }
+  if (FILL) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nref += __shfl_xor_sync(0xffffffffu, nref, o);
+    if (lane == 0 && nref) atomicAdd(&ctrl->npairs, nref);
+  }
   if (!FILL) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      mrow = max(mrow, __shfl_xor_sync(0xffffffffu, mrow, o));
-      nref += __shfl_xor_sync(0xffffffffu, nref, o);
-    }
-    if (lane == 0) {
-      if (nref) atomicAdd(&ctrl->npairs, nref);
-      if (mrow > *(volatile int *)&ctrl->max_row) atomicMax(&ctrl->max_row, mrow);
-    }
+    for (int o = 16; o > 0; o >>= 1) mrow = max(mrow, __shfl_xor_sync(0xffffffffu, mrow, o));
+    if (lane == 0 && mrow > *(volatile int *)&ctrl->max_row) atomicMax(&ctrl->max_row, mrow);
     __syncthreads();
     // steps of every force-warp: the longest of its (up to) 8 rows in steps of 4 entries, rounded up to even
     const int nfw_t = (ts.n_int + kPW - 1) / kPW;
@@ -306,7 +326,8 @@ static size_t search_smem_bytes(int cap, int maxint, bool fill) {
 // tile shapes tried in this order (balanced per axis afterwards); a shape is taken if its largest tile fits two
 // blocks per SM in the force kernel
 static const int kShapes[][3] = {{3, 3, 3}, {3, 3, 2}, {3, 2, 2}, {2, 2, 2}, {2, 2, 1}, {2, 1, 1}, {1, 1, 1}};
-static const int kCapTwoBlocks = 3500;  // (233472 / 2 - 1024 - bookkeeping) / 32 - 1 records
+// two force blocks per SM: (233,472 B per SM - 1 KB reserved per block) / 2 - bookkeeping (tile_shared_offset), in records
+static const int kCapTwoBlocks = (int)(((233472 - 2048) / 2 - (long)tile_shared_offset()) / 32) - 1;
 static const int kCapOneBlock = 6400;
 
 static void set_shape(Unit *u, const int want[3]) {
@@ -373,8 +394,12 @@ int build_pair_list(Unit *u) {
     MDB_CUDA(cudaStreamSynchronize(u->stream));
     u->tile_cap = u->ctrl_host->scratch[2];
     u->tile_maxint = u->ctrl_host->scratch[3];
-    ok = u->tile_cap <= kCapTwoBlocks || last;
+    ok = (u->tile_cap <= kCapTwoBlocks && u->tile_maxint <= kTileMaxRows * kPW) || last;
     if (forced[0]) break;
+  }
+  if (u->tile_maxint > kTileMaxRows * kPW) {
+    set_error("a tile holds %d particles of its own: more than %d force-warp rows", u->tile_maxint, kTileMaxRows);
+    return MDB200_ECAPACITY;
   }
   if (u->tile_cap > kCapOneBlock || u->tile_cap >= 65535) {
     set_error("a tile of one cell and its halo holds %d particles: more than shared memory can stage", u->tile_cap);
@@ -411,21 +436,19 @@ int build_pair_list(Unit *u) {
   MDB_CUDA(cudaGetLastError());
   MDB_TRY(exclusive_scan_i32_to_i64(u->scan.ptr, u->fw_off.ptr, nfw, u->scan_ws64.ptr, u->stream, &u->launches, 1));
   MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->scratch[4], u->fw_off.ptr + nfw, sizeof(long long), cudaMemcpyDeviceToHost, u->stream));
-  MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->npairs, &u->ctrl->npairs, sizeof(unsigned long long), cudaMemcpyDeviceToHost, u->stream));
   MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->max_row, &u->ctrl->max_row, sizeof(int), cudaMemcpyDeviceToHost, u->stream));
   MDB_CUDA(cudaStreamSynchronize(u->stream));
   long long words;
   memcpy(&words, &u->ctrl_host->scratch[4], sizeof(long long));
   u->list_entries = words * 4;
-  u->npairs = (long long)(u->ctrl_host->npairs / 2);
-  u->max_row = u->ctrl_host->max_row;
+  u->max_row = u->ctrl_host->max_row;   // upper bound of the longest row (sizes the derivation's row buffers)
   if (u->max_row > 252) {
     set_error("a particle has %d partners within the search length: rows above 252 entries are not supported", u->max_row);
     return MDB200_ECAPACITY;
   }
   // Head-room: rows of a freshly generated lattice grow by ~20 % once it thermalises, and re-allocating a multi-GB
   // list inside the step loop stalls for hundreds of ms; the walk reads one chunk past a row block, hence the slack.
-  const size_t need = (size_t)words + 4096;
+  const size_t need = (size_t)words + 8192;
   if (need > u->list.cap) {
     if (getenv("MDB200_DEBUG")) fprintf(stderr, "[mdb200] list grows: %zu words > capacity %zu\n", need, u->list.cap);
     MDB_TRY(u->list.ensure(need + need * 3 / 10));
@@ -437,6 +460,10 @@ int build_pair_list(Unit *u) {
                                                           u->scan.ptr, u->fw_off.ptr, u->list.ptr, u->tile_cap, u->tile_maxint, u->ctrl);
   u->launches++;
   MDB_CUDA(cudaGetLastError());
+  // the reference-style pair count (exact: counted by the fill pass); the caller synchronises anyway
+  MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->npairs, &u->ctrl->npairs, sizeof(unsigned long long), cudaMemcpyDeviceToHost, u->stream));
+  MDB_CUDA(cudaStreamSynchronize(u->stream));
+  u->npairs = (long long)(u->ctrl_host->npairs / 2);
   return MDB200_OK;
 }
 

@@ -126,7 +126,9 @@ struct Unit {
   // speculative pre-drift (force.cu MODE 3): q holds the locals ALREADY advanced by the next step's first half
   // drift; q_alt still holds them at the last half step, from which the end-of-step positions are
   // q_alt + p dt/2 (bit-identical).  api.cu:materialize() undoes it on demand.
-  bool predrifted = false;
+  // 1 = NVE (end-of-step positions = q_alt + p dt/2), 2 = Langevin (the step has no second half drift: the
+  // end-of-step positions are q_alt itself)
+  int predrifted = 0;
 
   // particle store, SLOT order: locals [0,pn) cell-sorted, ghosts [pn,tn) in arrival order
   DevBuf<double4> q, q_alt;       // positions (x,y,z,0)
@@ -288,6 +290,7 @@ int force_kick(Unit *u);                                                 // deri
 // fused kick + second half drift (+ the next step's first half drift if predrift); swaps q / q_alt.
 // part: 0 every tile, 1 interior tiles, 2 boundary tiles.  Walks the inner list (derived on demand).
 int force_kick_drift(Unit *u, bool predrift, int part);
+int force_kick_langevin(Unit *u);                                        // fused Langevin step (+ next first half drift)
 int force_impulse(Unit *u, double *f3_host, long long cap_rows);         // sync
 
 // observe.cu
