@@ -139,9 +139,9 @@ k_tile_force(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__re
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int n_int = ts.n_int;
   const int nfw = (n_int + kPW - 1) / kPW;
-  // A warp walks a CONTIGUOUS range of the tile's rows: their row blocks are contiguous in the list, so the list
-  // words are one stream per warp, loaded two chunks ahead across row boundaries.  The first two chunks are
-  // requested here, before the tile is staged.
+  // A warp walks a CONTIGUOUS range of the tile's rows (neighbouring row blocks: one L2 prefetch covers what comes
+  // next); the list words are loaded two chunks ahead.  The first two chunks are requested here, before the tile is
+  // staged.
   const int rbase = nfw / nwarps, rrem = nfw - rbase * nwarps;
   const int r0 = wid * rbase + min(wid, rrem), r1 = r0 + rbase + (wid < rrem ? 1 : 0);
   const uint2 *__restrict__ lp = list + (r0 < r1 ? fw_off[gfw0 + r0] : fw_off[gfw0]) + lane;
@@ -155,7 +155,7 @@ k_tile_force(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__re
   double v2max = 0.0;
   for (int fw = r0; fw < r1; fw++) {
     // keep the stream ahead in L2: the row block two rows further on (one instruction, a 128-byte line per lane)
-    if (fw + 2 < r1) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(lp - lane + ts.row_off[fw + 2] - ts.row_off[fw]) + 128 * lane));
+    if (fw + 2 < r1) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(list + ts.row_base + ts.row_off[fw + 2]) + 128 * lane));
     const int a = fw * kPW + (lane >> 2);
     const bool act = a < n_int;
     const unsigned ao = (unsigned)(act ? a : ts.n_all) << 5;
@@ -172,8 +172,8 @@ k_tile_force(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__re
     double f0 = 0.0, f1 = 0.0, f2 = 0.0;
     // List words two chunks (8 steps) ahead of their use: a chunk takes a warp ~500 clk at 8 warps per scheduler, a
     // miss to HBM ~1000.  Two named buffers, reloaded in place (rotating one into the other makes the copy wait for
-    // the younger load: ncu showed 14 % of all stall samples there); at the end of a row they already hold the first
-    // two chunks of the next one.  The allocation is padded: loading three chunks past the last row is harmless.
+    // the younger load: ncu showed 14 % of all stall samples there).  The allocation is padded: loading three chunks
+    // past the last row is harmless.
 #define WALK_CHUNK(W, K)                                                          \
   do {                                                                            \
     const unsigned e0 = ((W).x & 0xffffu) << 5, e1 = ((W).x >> 16) << 5;          \
@@ -200,11 +200,12 @@ k_tile_force(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__re
       lp += 64;
     }
 #undef WALK_CHUNK
-    if (((steps + 3) >> 2) & 1) {
-      // odd number of chunks: wb still holds the chunk after the row's last one = the next row's first, wa the one
-      // after it, and lp is one chunk too far.  The older word moves (it has long arrived), the other is asked for again.
-      lp -= 32;
-      wa = wb;
+    // The next row: its first two chunks are requested now, so that they travel while this row is reduced and
+    // written back.  (The rows of the inner list keep the row offsets of the outer list, i.e. they are NOT packed
+    // back to back: the stream cannot simply run on.)  The L2 prefetch above has brought them close.
+    if (fw + 1 < r1) {
+      lp = list + ts.row_base + ts.row_off[fw + 1] + lane;
+      wa = __ldg(lp);
       wb = __ldg(lp + 32);
     }
     // the writer lane's momentum: requested before the reduction below needs it

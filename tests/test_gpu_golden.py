@@ -18,3 +18,15 @@ def test_cuda_matches_reference_golden(name):
     seed = int(cfg["Seed"]) if cfg.get("DumpInit") == "Langevin" else None
     worst = check_cuda_against_records(rec, steps, init_build, seed)
     print(name, worst)
+
+
+@pytest.mark.parametrize("shape", ["2,2,2", "3,3,3", "3,2,1"])
+@pytest.mark.parametrize("name", ["bench1", "bench8", "collision8", "langevinT0", "nosehoover", "bench1_c25"])
+def test_multi_cell_tiles(name, shape, monkeypatch):
+    """The committed fixtures are small enough that the library picks tiles of ONE cell for them; the tile shapes
+    the benchmark sizes use (up to 3 x 3 x 3 cells: several rows per warp, halo cells of neighbouring rows, edge
+    tiles narrower than the rest) are forced here through MDB200_TILE."""
+    monkeypatch.setenv("MDB200_TILE", shape)
+    rec, cfg, steps, init_build = load_golden(name)
+    seed = int(cfg["Seed"]) if cfg.get("DumpInit") == "Langevin" else None
+    check_cuda_against_records(rec, steps, init_build, seed)
