@@ -1113,7 +1113,7 @@ int mdb200_list_stats(mdb200_unit *h, double out[8]) {
     for (size_t k = 0; k < rc.size(); k++) s += rc[k];
     out[3] = s;                       // sum of outer row lengths (unpadded entries)
     std::vector<int> wl((size_t)u->nfw);
-    const int *src = u->inner_valid ? u->fw_len_in.ptr : u->fw_len.ptr;
+    const int *src = (u->inner_valid && !u->inner_is_outer) ? u->fw_len_in.ptr : u->fw_len.ptr;
     MDB_CUDA(cudaMemcpyAsync(wl.data(), src, sizeof(int) * wl.size(), cudaMemcpyDeviceToHost, u->stream));
     MDB_CUDA(cudaStreamSynchronize(u->stream));
     double w = 0;

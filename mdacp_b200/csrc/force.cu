@@ -185,8 +185,17 @@ k_tile_force(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__re
       pair_kick<EXACT>(e3 + hx, e3 + hx2, a0, a1, a2, fc, f0, f1, f2);            \
     }                                                                             \
   } while (0)
+    // The next row: its first two chunks are requested before the last trip of this row, so that they travel while it
+    // is finished, reduced and written back.  (The rows of the inner list keep the row offsets of the outer list,
+    // i.e. they are NOT packed back to back: the stream cannot simply run on.)
+    const uint2 *__restrict__ nlp = (fw + 1 < r1) ? list + ts.row_base + ts.row_off[fw + 1] + lane : lp;
+    uint2 na = wa, nb = wb;
 #pragma unroll 1
     for (int k = 0; k < steps; k += 8) {
+      if (k + 8 >= steps) {
+        na = __ldg(nlp);
+        nb = __ldg(nlp + 32);
+      }
       {
         const uint2 w = wa;
         wa = __ldg(lp + 64);
@@ -200,14 +209,13 @@ k_tile_force(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__re
       lp += 64;
     }
 #undef WALK_CHUNK
-    // The next row: its first two chunks are requested now, so that they travel while this row is reduced and
-    // written back.  (The rows of the inner list keep the row offsets of the outer list, i.e. they are NOT packed
-    // back to back: the stream cannot simply run on.)  The L2 prefetch above has brought them close.
-    if (fw + 1 < r1) {
-      lp = list + ts.row_base + ts.row_off[fw + 1] + lane;
-      wa = __ldg(lp);
-      wb = __ldg(lp + 32);
+    if (steps <= 0) {
+      na = __ldg(nlp);
+      nb = __ldg(nlp + 32);
     }
+    lp = nlp;
+    wa = na;
+    wb = nb;
     // the writer lane's momentum: requested before the reduction below needs it
     double4 pa = make_double4(0.0, 0.0, 0.0, 0.0);
     if (MODE != FORCE_IMPULSE && act && (lane & 3) == 0) pa = p[slot];
@@ -373,6 +381,106 @@ k_tile_derive(TileArgs ta, Consts c, const double4 *__restrict__ q, const uint2 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The periodic derivation: per-lane compaction of the RE-DEALT outer list.  Once per rebuild k_tile_derive re-deals
+// the outer list in place into rainbow order (keep = everything); after that a lane's column already holds the
+// partners of "its" class, so deriving the inner list is a filter that needs no exchange between lanes: every lane
+// walks its own column, keeps the entries with r2 <= keep2 and packs them into output words held in registers; the
+// row block is written out at the end, whole chunks per warp.  Columns end up with slightly different lengths (the
+// row is as long as its longest column: ~1.5 steps in 22 more than a perfect re-deal) -- the price of a derivation
+// that costs a third of a force walk instead of three.
+// ---------------------------------------------------------------------------------------------------------
+template <int DUMMY>
+__global__ void __launch_bounds__(FORCE_TPB, 2)
+k_tile_compact(TileArgs ta, Consts c, const double4 *__restrict__ q, const uint2 *__restrict__ list,
+               const long long *__restrict__ fw_off, const int *__restrict__ fw_len, uint2 *__restrict__ list_in,
+               int *__restrict__ fw_len_in, double keep2) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  TileShared &ts = *reinterpret_cast<TileShared *>(smem);
+  double4 *sq = reinterpret_cast<double4 *>(smem + tile_shared_offset());
+  const int tile = ta.tile_order ? ta.tile_order[ta.tile_base + blockIdx.x] : (int)blockIdx.x;
+  tile_setup(ts, tile, ta.g, c, ta.cell_start, ta.gcell_start);
+  const int gfw0 = ta.tile_fw0[tile];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int n_int = ts.n_int;
+  const int nfw = (n_int + kPW - 1) / kPW;
+  const int rbase = nfw / nwarps, rrem = nfw - rbase * nwarps;
+  const int r0 = wid * rbase + min(wid, rrem), r1 = r0 + rbase + (wid < rrem ? 1 : 0);
+  tile_stage_rows(ts, gfw0, fw_off, fw_len);
+  tile_stage_tma(ts, q, ta.gitems, sq);
+  tile_stage_wait(ts);
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(sq);
+  const unsigned gp = (lane >> 2) & 1u;  // same lane-group parity as the force walk: conflict-free on rainbow rows
+  const unsigned hx = sbase + (gp << 4), hx2 = sbase + ((gp ^ 1u) << 4);
+  const unsigned long long sent = (unsigned long long)ts.n_all;
+  const unsigned long long sent4 = sent | (sent << 16) | (sent << 32) | (sent << 48);
+  for (int fw = r0; fw < r1; fw++) {
+    const int a = fw * kPW + (lane >> 2);
+    const bool act = a < n_int;
+    const unsigned ao = (unsigned)(act ? a : ts.n_all) << 5;
+    double a0, a1;
+    lds128(ao + hx, a0, a1);
+    const double a2 = lds64(ao + hx2);
+    const int steps = ts.row_len[fw];
+    const int nchunk = (steps + 3) >> 2;
+    const uint2 *__restrict__ lp = list + ts.row_base + ts.row_off[fw] + lane;
+    unsigned long long *__restrict__ dst = reinterpret_cast<unsigned long long *>(list_in + ts.row_base + ts.row_off[fw]) + lane;
+    if (fw + 1 < r1) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(list + ts.row_base + ts.row_off[fw + 1]) + 128 * lane));
+    unsigned long long acc = 0ull;   // the output word being filled
+    int nk = 0;                      // kept entries of this lane
+    // A finished word goes straight to its place in the row block: the lanes of a warp fill their words at nearly the
+    // same pace, so these 8-byte stores mostly fall into the same one or two chunks, and L2 merges what is left.
+#define COMPACT_CHUNK(W, CH)                                                                     \
+  do {                                                                                           \
+    _Pragma("unroll") for (int s2 = 0; s2 < 4; s2++) {                                           \
+      const unsigned j = ((s2 < 2 ? (W).x : (W).y) >> (16 * (s2 & 1))) & 0xffffu;                \
+      double j0, j1;                                                                             \
+      lds128((j << 5) + hx, j0, j1);                                                             \
+      const double j2 = lds64((j << 5) + hx2);                                                   \
+      const double d0 = j0 - a0, d1 = j1 - a1, d2 = j2 - a2;                                     \
+      const double r2 = fma(d2, d2, fma(d1, d1, d0 * d0));                                       \
+      if (act && r2 <= keep2 && 4 * (CH) + s2 < steps) {                                         \
+        acc |= (unsigned long long)j << (16 * (nk & 3));                                         \
+        nk++;                                                                                    \
+        if ((nk & 3) == 0) {                                                                     \
+          dst[32 * ((nk >> 2) - 1)] = acc;                                                       \
+          acc = 0ull;                                                                            \
+        }                                                                                        \
+      }                                                                                          \
+    }                                                                                            \
+  } while (0)
+    // two named buffers reloaded in place, two chunks ahead (as in the force walk)
+    uint2 wa = __ldg(lp), wb = __ldg(lp + 32);
+#pragma unroll 1
+    for (int ch = 0; ch < nchunk; ch += 2) {
+      {
+        const uint2 w = wa;
+        wa = __ldg(lp + 32 * (ch + 2));
+        COMPACT_CHUNK(w, ch);
+      }
+      if (ch + 1 < nchunk) {
+        const uint2 w = wb;
+        wb = __ldg(lp + 32 * (ch + 3));
+        COMPACT_CHUNK(w, ch + 1);
+      }
+    }
+#undef COMPACT_CHUNK
+    int steps_in = nk;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) steps_in = max(steps_in, __shfl_xor_sync(0xffffffffu, steps_in, o));
+    steps_in = (steps_in + 1) & ~1;
+    const int nchunk_in = (steps_in + 3) >> 2;
+    // the word in progress, topped up with the sentinel, and sentinel words up to the row's length
+    int wi = nk >> 2;
+    if (nk & 3) {
+      dst[32 * wi] = acc | (sent4 & (~0ull << (16 * (nk & 3))));
+      wi++;
+    }
+    for (; wi < nchunk_in; wi++) dst[32 * wi] = sent4;
+    if (lane == 0) fw_len_in[gfw0 + fw] = steps_in;
+  }
+}
+
 static ForceConsts make_fc(const Unit *u) {
   ForceConsts fc;
   fc.CL2 = u->c.CL2;
@@ -424,9 +532,8 @@ static int set_smem(K kernel, size_t bytes) {
   return MDB200_OK;
 }
 
-int derive_inner(Unit *u, double keep_len) {
-  u->inner_valid = false;
-  if (u->pn == 0 || u->ntiles == 0) { u->inner_valid = true; u->inner_keep = keep_len; return MDB200_OK; }
+// k_tile_derive launch: in -> out (in place when they are the same list), entries within keep2
+static int launch_redeal(Unit *u, const uint2 *in, const int *in_len, uint2 *out, int *out_len, double keep2) {
   const int max_steps = (((u->max_row + kG - 1) / kG) + 1) & ~1;
   const int max_chunks = (max_steps + 3) >> 2;
   if (max_chunks > 16) { set_error("rows of %d entries are too long for the inner-list derivation", u->max_row); return MDB200_ECAPACITY; }
@@ -437,11 +544,43 @@ int derive_inner(Unit *u, double keep_len) {
   const size_t sm = base + warps * per_warp;
   if (sm > limit) { set_error("tile of %d records leaves no shared memory for the inner-list derivation", u->tile_cap); return MDB200_ECAPACITY; }
   MDB_TRY(set_smem(k_tile_derive<0>, sm));
-  MDB_TRY(u->list_in.ensure(u->list.cap));
-  k_tile_derive<0><<<u->ntiles, warps * 32, sm, u->stream>>>(make_ta(u, 0), u->c, u->q.ptr, u->list.ptr, u->fw_off.ptr, u->fw_len.ptr,
-                                                             u->list_in.ptr, u->fw_len_in.ptr, keep_len * keep_len, max_chunks);
+  k_tile_derive<0><<<u->ntiles, warps * 32, sm, u->stream>>>(make_ta(u, 0), u->c, u->q.ptr, in, u->fw_off.ptr, in_len, out, out_len,
+                                                             keep2, max_chunks);
   u->launches++;
   MDB_CUDA(cudaGetLastError());
+  return MDB200_OK;
+}
+
+// Inner list = the outer entries within keep_len of the CURRENT positions.  The first call after a rebuild re-deals the
+// outer list in place into rainbow order (k_tile_derive with keep = everything but the sentinel padding); every call
+// then filters it lane by lane (k_tile_compact).  keep_len >= search length: the inner list IS the outer list.
+int derive_inner(Unit *u, double keep_len) {
+  u->inner_valid = false;
+  u->inner_is_outer = false;
+  if (u->pn == 0 || u->ntiles == 0) { u->inner_valid = true; u->inner_keep = keep_len; return MDB200_OK; }
+  static const bool slow = getenv("MDB200_DERIVE_REDEAL") != nullptr;  // diagnostic: every derivation a full re-deal
+  const bool can_compact = !slow;
+  static const bool dbg = getenv("MDB200_DEBUG") != nullptr;
+  if (dbg) fprintf(stderr, "[mdb200] derive: keep %.4f, longest row <= %d entries, %s%s\n", keep_len, u->max_row,
+                   u->outer_rainbow ? "" : "re-deal + ", keep_len >= u->c.SL ? "walk the outer list" : (can_compact ? "compaction" : "full re-deal"));
+  if (!u->outer_rainbow) {
+    MDB_TRY(launch_redeal(u, u->list.ptr, u->fw_len.ptr, u->list.ptr, u->fw_len.ptr, 1.0e15));
+    u->outer_rainbow = true;
+  }
+  if (keep_len >= u->c.SL) {
+    u->inner_is_outer = true;
+  } else if (can_compact) {
+    MDB_TRY(u->list_in.ensure(u->list.cap));
+    const size_t sm = tile_smem_bytes_f64(u->tile_cap);
+    MDB_TRY(set_smem(k_tile_compact<0>, sm));
+    k_tile_compact<0><<<u->ntiles, FORCE_TPB, sm, u->stream>>>(make_ta(u, 0), u->c, u->q.ptr, u->list.ptr, u->fw_off.ptr, u->fw_len.ptr,
+                                                               u->list_in.ptr, u->fw_len_in.ptr, keep_len * keep_len);
+    u->launches++;
+    MDB_CUDA(cudaGetLastError());
+  } else {
+    MDB_TRY(u->list_in.ensure(u->list.cap));
+    MDB_TRY(launch_redeal(u, u->list.ptr, u->fw_len.ptr, u->list_in.ptr, u->fw_len_in.ptr, keep_len * keep_len));
+  }
   u->inner_valid = true;
   u->inner_keep = keep_len;
   return MDB200_OK;
@@ -455,11 +594,13 @@ static int force_launch(Unit *u, int mode, double *fout, int part = 0) {
   const ForceConsts fc = make_fc(u);
   const TileArgs ta = make_ta(u, part);
   const size_t sm = tile_smem_bytes_f64(u->tile_cap);
+  const uint2 *walk_list = u->inner_is_outer ? u->list.ptr : u->list_in.ptr;
+  const int *walk_len = u->inner_is_outer ? u->fw_len.ptr : u->fw_len_in.ptr;
 #define KLAUNCH(M, E)                                                                                               \
   do {                                                                                                              \
     MDB_TRY(set_smem(k_tile_force<M, E>, sm));                                                                      \
-    k_tile_force<M, E><<<ntl, FORCE_TPB, sm, u->stream>>>(ta, u->c, u->q.ptr, u->p.ptr, fout, u->list_in.ptr, u->fw_off.ptr, \
-                                                          u->fw_len_in.ptr, u->ref_of_slot.ptr, u->q_alt.ptr, u->ctrl, fc); \
+    k_tile_force<M, E><<<ntl, FORCE_TPB, sm, u->stream>>>(ta, u->c, u->q.ptr, u->p.ptr, fout, walk_list, u->fw_off.ptr, \
+                                                          walk_len, u->ref_of_slot.ptr, u->q_alt.ptr, u->ctrl, fc); \
   } while (0)
 #define LAUNCH(E)                                          \
   do {                                                     \

@@ -279,8 +279,10 @@ __device__ __forceinline__ void tile_stage_tma(TileShared &ts, const double4 *__
   }
 }
 // completes tile_stage_tma: the bulk copies have landed and every thread's own stores are visible
+// (one warp polls the mbarrier, the others sleep at the block barrier: sixteen polling warps were a fifth of all
+// instructions the force kernel issued)
 __device__ __forceinline__ void tile_stage_wait(TileShared &ts) {
-  mbar_wait(&ts.mbar, 0u);
+  if (threadIdx.x < 32) mbar_wait(&ts.mbar, 0u);
   __syncthreads();
 }
 

@@ -363,6 +363,8 @@ int build_pair_list(Unit *u) {
   u->nfw = 0;
   u->ntiles = 0;
   u->inner_valid = false;
+  u->outer_rainbow = false;
+  u->inner_is_outer = false;
   if (pn == 0) return MDB200_OK;
   // ---- tile shape: the largest that leaves enough blocks for the device and whose tiles fit shared memory
   int nshapes = (int)(sizeof(kShapes) / sizeof(kShapes[0]));

@@ -191,6 +191,8 @@ struct Unit {
   DevBuf<long long> fw_off;       // first uint2 word of the force-warp's row block (both lists)
   DevBuf<uint2> list, list_in;
   bool inner_valid = false;
+  bool outer_rainbow = false;     // the outer list has been re-dealt into rainbow order since the last rebuild
+  bool inner_is_outer = false;    // keep >= search length: the force kernel walks the (re-dealt) outer list itself
   double inner_left = -1.0, inner_delta = 0.0;  // budget of the unit GROUP, kept in its first unit (api.cu)
   double inner_keep = 0.0;        // radius the present inner list was derived with
   long long list_entries = 0;     // stored 16-bit entries (padded)
