@@ -685,7 +685,7 @@ int mdb200_destroy(mdb200_unit *h) {
   u->mig_recv_p.release(); u->mig_send_t.release(); u->mig_recv_t.release();
   u->row_count.release(); u->list_in.release(); u->fw_len_in.release(); u->tile_fw0.release(); u->tile_flag.release(); u->tile_order.release();
   if (u->cstream) { cudaStreamDestroy(u->cstream); cudaEventDestroy(u->ev_drift); cudaEventDestroy(u->ev_ghost); }
-  u->fw_len.release(); u->fw_off.release(); u->list.release();
+  u->fw_len.release(); u->fw_off.release(); u->fw_sent.release(); u->list.release();
   u->disp.release(); u->cand.release(); u->partial.release();
   u->snap_q.release(); u->snap_p.release(); u->snap_t.release();
   if (u->snap_stream) {

@@ -17,7 +17,7 @@
 //    read the high half (z, y) first and x second, and simply compute with x and z exchanged (r2 and the three
 //    accumulators do not care; the writer lane swaps them back).  The 8 lanes of a quarter-warp then touch 8
 //    different 16-byte bank groups as long as the 4 lanes of a group read records of 4 different classes
-//    (staged index mod 4) -- which is how k_tile_derive deals the rows out ("rainbow" order).
+//    (staged index mod 4) -- which is how k_redeal deals the rows out ("rainbow" order).
 //  * the cutoff test is one integer compare on the high word of r2 (exact when the low word of CL2 is zero, as
 //    for cutoff 3.0 and 2.5; a full 64-bit compare otherwise), and zeroes df with two integer selects.
 //  * list words for four steps come from one 8-byte load per lane (a contiguous 256-byte run per warp), loaded
@@ -27,6 +27,7 @@
 // (q read, p read + write), 30 flop per listed unordered pair.
 #include <math.h>
 #include <stdlib.h>
+#include <algorithm>
 #include <string.h>
 #include <map>
 #include <mutex>
@@ -40,9 +41,6 @@ TileGrid tile_grid(const Unit *u);  // tile_search.cu
 
 #ifndef FORCE_TPB
 #define FORCE_TPB 512
-#endif
-#ifndef DERIVE_TPB
-#define DERIVE_TPB 512
 #endif
 
 struct ForceConsts {
@@ -261,59 +259,43 @@ k_tile_force(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__re
 
 // ---------------------------------------------------------------------------------------------------------
 // Inner list.  ~25 % of the listed pairs lie between the cutoff and the search length and contribute exactly
-// zero.  k_tile_derive copies the entries of the outer list with r2 <= keep2 = (cutoff + delta)^2 at the CURRENT
-// positions into list_in, re-dealt in rainbow order (tile.cuh) at the same row offsets, with their own step counts
-// in fw_len_in.  Until some pair can have closed the distance delta (velocity budget kept by the host, api.cu)
-// the force launches walk the inner list and give identical contributions: the dropped ones are exact zeros.
-// With keep = search length it is a plain re-deal of the whole outer list.
+// zero.  The force kernel walks the INNER list: the entries of the outer list with r2 <= (cutoff + delta)^2 when it
+// was derived, at the same row offsets, with their own step counts in fw_len_in.  Until some pair can have closed
+// the distance delta (velocity budget kept by the host, api.cu) the force launches give identical contributions:
+// the dropped entries are exact zeros.
 //
-// A warp takes one force-warp row: pass A walks the outer row (arrival order) and marks what stays, a 4-lane
-// scan gives every kept entry its ordinal within its class, pass B scatters the kept entries into a row block
-// in shared memory, which is then written out as whole chunks.
+// Two steps.  (1) Once per rebuild k_redeal puts every row of the OUTER list (written by the search in arrival
+// order) into "rainbow" order in place (tile.cuh): lane c of a local's group then holds the partners of class c
+// (staged index mod 4), which is what makes the walk's shared-memory reads conflict-free.  Pure index shuffling:
+// no positions, no tile staging, one warp per row through a row block in shared memory.  (2) Every ~16 steps
+// k_tile_compact filters the re-dealt outer list lane by lane (below).
 // ---------------------------------------------------------------------------------------------------------
+#define REDEAL_TPB 256
 template <int DUMMY>
-__global__ void __launch_bounds__(DERIVE_TPB, 1)
-k_tile_derive(TileArgs ta, Consts c, const double4 *__restrict__ q, const uint2 *__restrict__ list,
-              const long long *__restrict__ fw_off, const int *__restrict__ fw_len, uint2 *__restrict__ list_in,
-              int *__restrict__ fw_len_in, double keep2, int max_chunks) {
+__global__ void __launch_bounds__(REDEAL_TPB)
+k_redeal(const long long *__restrict__ fw_off, int *__restrict__ fw_len, const int *__restrict__ fw_sent, uint2 *__restrict__ list,
+         long long nfw, int max_chunks) {
   extern __shared__ __align__(128) unsigned char smem[];
-  TileShared &ts = *reinterpret_cast<TileShared *>(smem);
-  double4 *sq = reinterpret_cast<double4 *>(smem + tile_shared_offset());
-  const int tile = ta.tile_order ? ta.tile_order[ta.tile_base + blockIdx.x] : (int)blockIdx.x;
-  tile_setup(ts, tile, ta.g, c, ta.cell_start, ta.gcell_start);
-  const int gfw0 = ta.tile_fw0[tile];
-  tile_stage_rows(ts, gfw0, fw_off, fw_len);
-  tile_stage_tma(ts, q, ta.gitems, sq);
-  tile_stage_wait(ts);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  // row block of this warp: max_chunks x 32 words
-  uint2 *rb = reinterpret_cast<uint2 *>(sq + ta.cap + 1) + (size_t)wid * max_chunks * 32;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint2 *rb = reinterpret_cast<uint2 *>(smem) + (size_t)wid * max_chunks * 32;  // row block of this warp
   unsigned short *rb16 = reinterpret_cast<unsigned short *>(rb);
-  const int n_int = ts.n_int;
-  const int nfw = (n_int + kPW - 1) / kPW;
-  const unsigned sent = (unsigned)ts.n_all;
-  const uint2 sent2 = make_uint2(sent | (sent << 16), sent | (sent << 16));
   const int c4 = lane & 3, glane0 = lane & ~3;
-  // contiguous rows per warp, as in the force kernel
-  const int rbase = nfw / nwarps, rrem = nfw - rbase * nwarps;
-  const int r0 = wid * rbase + min(wid, rrem), r1 = r0 + rbase + (wid < rrem ? 1 : 0);
   constexpr int NB = 8;  // chunks held in registers (rows of up to 32 steps; longer rows take another trip)
-  for (int fw = r0; fw < r1; fw++) {
-    const int a = fw * kPW + (lane >> 2);
-    const bool act = a < n_int;       // the last force-warp of a tile may own fewer than 8 locals
-    const double4 qa = sq[act ? a : ts.n_all];
-    const int steps = ts.row_len[fw];
-    const uint2 *__restrict__ lp = list + ts.row_base + ts.row_off[fw] + lane;
-    if (fw + 1 < r1) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(lp - lane + ts.row_off[fw + 1] - ts.row_off[fw]) + 128 * lane));
+  const long long nw = (long long)gridDim.x * (REDEAL_TPB / 32);
+  for (long long gfw = (long long)blockIdx.x * (REDEAL_TPB / 32) + wid; gfw < nfw; gfw += nw) {
+    const int steps = fw_len[gfw];
     const int nchunk = (steps + 3) >> 2;
-    // ---- pass A: which of this lane's entries stay (bit 4 c + s of the mask: step 4 c + s), how many per class
+    const unsigned sent = (unsigned)fw_sent[gfw];
+    const uint2 sent2 = make_uint2(sent | (sent << 16), sent | (sent << 16));
+    uint2 *__restrict__ lp = list + fw_off[gfw] + lane;
+    // ---- pass A: the real entries of this lane (bit 4 c + s of the mask: step 4 c + s), how many per class
     unsigned long long keep = 0ull;   // rows of at most 16 chunks = 64 steps = 256 entries (derive_inner checks)
     unsigned kcnt = 0u;
     uint2 w[NB];
 #pragma unroll 1
     for (int cb = 0; cb < nchunk; cb += NB) {
 #pragma unroll
-      for (int i = 0; i < NB; i++) w[i] = (cb + i < nchunk) ? __ldg(lp + 32 * (cb + i)) : sent2;  // all in flight together
+      for (int i = 0; i < NB; i++) w[i] = (cb + i < nchunk) ? lp[32 * (cb + i)] : sent2;  // all in flight together
 #pragma unroll
       for (int i = 0; i < NB; i++) {
         const int ch = cb + i;
@@ -322,10 +304,7 @@ k_tile_derive(TileArgs ta, Consts c, const double4 *__restrict__ q, const uint2 
 #pragma unroll
           for (int s2 = 0; s2 < 4; s2++) {
             const unsigned j = ((s2 < 2 ? w[i].x : w[i].y) >> (16 * (s2 & 1))) & 0xffffu;
-            const double4 qj = sq[j];
-            const double dx = qj.x - qa.x, dy = qj.y - qa.y, dz = qj.z - qa.z;
-            const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-            if (act && r2 <= keep2 && 4 * ch + s2 < steps) { m |= 1u << s2; kcnt += 1u << (8 * (j & 3u)); }
+            if (j != sent && 4 * ch + s2 < steps) { m |= 1u << s2; kcnt += 1u << (8 * (j & 3u)); }
           }
           keep |= (unsigned long long)m << (4 * ch);
         }
@@ -340,20 +319,20 @@ k_tile_derive(TileArgs ta, Consts c, const double4 *__restrict__ q, const uint2 
     const unsigned tot = __shfl_sync(0xffffffffu, incl, kG - 1, kG);  // class totals of the local
     unsigned run = incl - kcnt;                                        // first ordinals of this lane's entries
     const int nk = (int)((tot & 0xFFu) + ((tot >> 8) & 0xFFu) + ((tot >> 16) & 0xFFu) + (tot >> 24));
-    int steps_in = (nk + kG - 1) / kG;
+    int steps_out = (nk + kG - 1) / kG;
 #pragma unroll
-    for (int o = kG; o < 32; o <<= 1) steps_in = max(steps_in, __shfl_xor_sync(0xffffffffu, steps_in, o));
-    steps_in = (steps_in + 1) & ~1;
-    const int nchunk_in = (steps_in + 3) >> 2;
-    // ---- row block <- sentinel, then the kept entries at their rainbow positions
-    for (int i = lane; i < nchunk_in * 32; i += 32) rb[i] = sent2;
+    for (int o = kG; o < 32; o <<= 1) steps_out = max(steps_out, __shfl_xor_sync(0xffffffffu, steps_out, o));
+    steps_out = (steps_out + 1) & ~1;
+    const int nchunk_out = (steps_out + 3) >> 2;
+    // ---- row block <- sentinel, then the entries at their rainbow positions
+    for (int i = lane; i < nchunk_out * 32; i += 32) rb[i] = sent2;
     __syncwarp();
     const int m = rainbow_min(tot);
 #pragma unroll 1
     for (int cb = 0; cb < nchunk; cb += NB) {
       if (nchunk > NB) {  // long row: the words of this trip again (the short ones are still in registers)
 #pragma unroll
-        for (int i = 0; i < NB; i++) w[i] = (cb + i < nchunk) ? __ldg(lp + 32 * (cb + i)) : sent2;
+        for (int i = 0; i < NB; i++) w[i] = (cb + i < nchunk) ? lp[32 * (cb + i)] : sent2;
       }
 #pragma unroll
       for (int i = 0; i < NB; i++) {
@@ -374,15 +353,15 @@ k_tile_derive(TileArgs ta, Consts c, const double4 *__restrict__ q, const uint2 
       }
     }
     __syncwarp();
-    uint2 *__restrict__ dst = list_in + ts.row_base + ts.row_off[fw];
-    for (int i = lane; i < nchunk_in * 32; i += 32) dst[i] = rb[i];
-    if (lane == 0) fw_len_in[gfw0 + fw] = steps_in;
+    // written back in place: every word of the row was read above
+    for (int i = lane; i < nchunk_out * 32; i += 32) lp[i - lane] = rb[i];
+    if (lane == 0) fw_len[gfw] = steps_out;
     __syncwarp();
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// The periodic derivation: per-lane compaction of the RE-DEALT outer list.  Once per rebuild k_tile_derive re-deals
+// The periodic derivation: per-lane compaction of the RE-DEALT outer list.  Once per rebuild k_redeal re-deals
 // the outer list in place into rainbow order (keep = everything); after that a lane's column already holds the
 // partners of "its" class, so deriving the inner list is a filter that needs no exchange between lanes: every lane
 // walks its own column, keeps the entries with r2 <= keep2 and packs them into output words held in registers; the
@@ -532,44 +511,40 @@ static int set_smem(K kernel, size_t bytes) {
   return MDB200_OK;
 }
 
-// k_tile_derive launch: in -> out (in place when they are the same list), entries within keep2
-static int launch_redeal(Unit *u, const uint2 *in, const int *in_len, uint2 *out, int *out_len, double keep2) {
+// k_redeal launch: the outer list into rainbow order, in place
+static int launch_redeal(Unit *u) {
   const int max_steps = (((u->max_row + kG - 1) / kG) + 1) & ~1;
   const int max_chunks = (max_steps + 3) >> 2;
   if (max_chunks > 16) { set_error("rows of %d entries are too long for the inner-list derivation", u->max_row); return MDB200_ECAPACITY; }
-  // as many warps as the row blocks leave room for beside the staged tile (at least 4: tile_setup needs 125 threads)
-  const size_t base = tile_smem_bytes_f64(u->tile_cap), per_warp = (size_t)max_chunks * 256, limit = 227 * 1024;
-  int warps = DERIVE_TPB / 32;
-  while (warps > 4 && base + warps * per_warp > limit) warps--;
-  const size_t sm = base + warps * per_warp;
-  if (sm > limit) { set_error("tile of %d records leaves no shared memory for the inner-list derivation", u->tile_cap); return MDB200_ECAPACITY; }
-  MDB_TRY(set_smem(k_tile_derive<0>, sm));
-  k_tile_derive<0><<<u->ntiles, warps * 32, sm, u->stream>>>(make_ta(u, 0), u->c, u->q.ptr, in, u->fw_off.ptr, in_len, out, out_len,
-                                                             keep2, max_chunks);
+  const size_t sm = (size_t)(REDEAL_TPB / 32) * max_chunks * 256;
+  MDB_TRY(set_smem(k_redeal<0>, sm));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, u->device);
+  const long long want = (u->nfw + REDEAL_TPB / 32 - 1) / (REDEAL_TPB / 32);
+  const unsigned grid = (unsigned)std::min<long long>(want, (long long)sms * 64);
+  k_redeal<0><<<grid, REDEAL_TPB, sm, u->stream>>>(u->fw_off.ptr, u->fw_len.ptr, u->fw_sent.ptr, u->list.ptr, u->nfw, max_chunks);
   u->launches++;
   MDB_CUDA(cudaGetLastError());
   return MDB200_OK;
 }
 
 // Inner list = the outer entries within keep_len of the CURRENT positions.  The first call after a rebuild re-deals the
-// outer list in place into rainbow order (k_tile_derive with keep = everything but the sentinel padding); every call
+// outer list in place into rainbow order (k_redeal); every call
 // then filters it lane by lane (k_tile_compact).  keep_len >= search length: the inner list IS the outer list.
 int derive_inner(Unit *u, double keep_len) {
   u->inner_valid = false;
   u->inner_is_outer = false;
   if (u->pn == 0 || u->ntiles == 0) { u->inner_valid = true; u->inner_keep = keep_len; return MDB200_OK; }
-  static const bool slow = getenv("MDB200_DERIVE_REDEAL") != nullptr;  // diagnostic: every derivation a full re-deal
-  const bool can_compact = !slow;
   static const bool dbg = getenv("MDB200_DEBUG") != nullptr;
   if (dbg) fprintf(stderr, "[mdb200] derive: keep %.4f, longest row <= %d entries, %s%s\n", keep_len, u->max_row,
-                   u->outer_rainbow ? "" : "re-deal + ", keep_len >= u->c.SL ? "walk the outer list" : (can_compact ? "compaction" : "full re-deal"));
+                   u->outer_rainbow ? "" : "re-deal + ", keep_len >= u->c.SL ? "walk the outer list" : "compaction");
   if (!u->outer_rainbow) {
-    MDB_TRY(launch_redeal(u, u->list.ptr, u->fw_len.ptr, u->list.ptr, u->fw_len.ptr, 1.0e15));
+    MDB_TRY(launch_redeal(u));
     u->outer_rainbow = true;
   }
   if (keep_len >= u->c.SL) {
     u->inner_is_outer = true;
-  } else if (can_compact) {
+  } else {
     MDB_TRY(u->list_in.ensure(u->list.cap));
     const size_t sm = tile_smem_bytes_f64(u->tile_cap);
     MDB_TRY(set_smem(k_tile_compact<0>, sm));
@@ -577,9 +552,6 @@ int derive_inner(Unit *u, double keep_len) {
                                                                u->list_in.ptr, u->fw_len_in.ptr, keep_len * keep_len);
     u->launches++;
     MDB_CUDA(cudaGetLastError());
-  } else {
-    MDB_TRY(u->list_in.ensure(u->list.cap));
-    MDB_TRY(launch_redeal(u, u->list.ptr, u->fw_len.ptr, u->list_in.ptr, u->fw_len_in.ptr, keep_len * keep_len));
   }
   u->inner_valid = true;
   u->inner_keep = keep_len;

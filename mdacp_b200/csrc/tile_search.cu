@@ -17,7 +17,7 @@
 //   pass 2 (k_tile_search<true>): the same tests again, every lane appends its hits to a 32-byte staging
 //          sector in shared memory and writes whole sectors of its row (16 entries of 16 bits, layout in unit.h).
 // The OUTER list written here is in arrival order; the force kernel walks the INNER list that
-// force.cu:k_tile_derive re-deals from it.
+// force.cu re-deals (k_redeal) and filters (k_tile_compact) it.
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
@@ -87,7 +87,7 @@ template <bool FILL>
 __global__ void __launch_bounds__(TPB, 3)
 k_tile_search(TileGrid g, Consts c, const double4 *__restrict__ q, const int *__restrict__ cell_start,
               const int *__restrict__ gcell_start, const int *__restrict__ gitems, const int *__restrict__ tile_fw0,
-              int *__restrict__ row_count, int *__restrict__ fw_len, int *__restrict__ fw_store,
+              int *__restrict__ row_count, int *__restrict__ fw_len, int *__restrict__ fw_store, int *__restrict__ fw_sent,
               const long long *__restrict__ fw_off, uint2 *__restrict__ list, int cap, int maxint, Ctrl *ctrl) {
   extern __shared__ __align__(128) unsigned char smem[];
   TileShared &ts = *reinterpret_cast<TileShared *>(smem);
@@ -298,6 +298,7 @@ k_tile_search(TileGrid g, Consts c, const double4 *__restrict__ q, const int *__
       mx = (mx + 1) & ~1;
       fw_len[gfw0 + fw] = mx;
       fw_store[gfw0 + fw] = store_steps(mx) * 8;  // uint2 words of the row block
+      fw_sent[gfw0 + fw] = sentinel;
     }
   } else {
     // lanes of the last force-warp that own no local: sentinel rows
@@ -424,6 +425,7 @@ int build_pair_list(Unit *u) {
   MDB_TRY(u->row_count.ensure((size_t)pn + 32));
   MDB_TRY(u->fw_len.ensure((size_t)nfw + 2));
   MDB_TRY(u->fw_len_in.ensure((size_t)nfw + 2));
+  MDB_TRY(u->fw_sent.ensure((size_t)nfw + 2));
   MDB_TRY(u->fw_off.ensure((size_t)nfw + 2));
   MDB_TRY(u->scan.ensure((size_t)nfw + 2));
   MDB_TRY(u->scan_ws64.ensure(scan_workspace_ints(nfw + 2)));
@@ -433,7 +435,7 @@ int build_pair_list(Unit *u) {
   MDB_CUDA(cudaFuncSetAttribute(k_tile_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
   k_tile_search<false><<<u->ntiles, TPB, sm1, u->stream>>>(tile_grid(u), u->c, u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr,
                                                            u->gcell_items.ptr, u->tile_fw0.ptr, u->row_count.ptr, u->fw_len.ptr,
-                                                           u->scan.ptr, u->fw_off.ptr, u->list.ptr, u->tile_cap, u->tile_maxint, u->ctrl);
+                                                           u->scan.ptr, u->fw_sent.ptr, u->fw_off.ptr, u->list.ptr, u->tile_cap, u->tile_maxint, u->ctrl);
   u->launches++;
   MDB_CUDA(cudaGetLastError());
   MDB_TRY(exclusive_scan_i32_to_i64(u->scan.ptr, u->fw_off.ptr, nfw, u->scan_ws64.ptr, u->stream, &u->launches, 1));
@@ -459,7 +461,7 @@ int build_pair_list(Unit *u) {
   // ---- pass 2: rows
   k_tile_search<true><<<u->ntiles, TPB, sm2, u->stream>>>(tile_grid(u), u->c, u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr,
                                                           u->gcell_items.ptr, u->tile_fw0.ptr, u->row_count.ptr, u->fw_len.ptr,
-                                                          u->scan.ptr, u->fw_off.ptr, u->list.ptr, u->tile_cap, u->tile_maxint, u->ctrl);
+                                                          u->scan.ptr, u->fw_sent.ptr, u->fw_off.ptr, u->list.ptr, u->tile_cap, u->tile_maxint, u->ctrl);
   u->launches++;
   MDB_CUDA(cudaGetLastError());
   // the reference-style pair count (exact: counted by the fill pass); the caller synchronises anyway

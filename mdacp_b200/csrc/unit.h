@@ -188,6 +188,7 @@ struct Unit {
   long long nfw = 0;              // force-warps of the unit = sum over tiles of ceil(interior locals / 8)
   DevBuf<int> row_count;          // outer entries per local slot
   DevBuf<int> fw_len, fw_len_in;  // steps per force-warp (even)
+  DevBuf<int> fw_sent;            // staged index of the sentinel record of the force-warp's tile (k_redeal)
   DevBuf<long long> fw_off;       // first uint2 word of the force-warp's row block (both lists)
   DevBuf<uint2> list, list_in;
   bool inner_valid = false;
