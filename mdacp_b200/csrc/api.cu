@@ -751,6 +751,7 @@ int mdb200_upload(mdb200_unit *h, const double (*q)[4], const double (*p)[4], co
   u->predrifted = 0;
   u->inner_valid = false;
   u->max_row = 0;
+  u->max_row_exact = 0;
   u->npairs = 0;
   u->list_entries = 0;
   for (int d = 0; d < 6; d++) { u->n_border[d] = 0; u->recv_cnt[d] = 0; u->recv_off[d] = pn; }

@@ -82,13 +82,18 @@ struct SearchShared {
   int pad;
 };
 
-// smem: TileShared | SearchShared | float4 sf[cap + 1] | int row_n[maxint + 8] | (FILL) ushort stg[threads][16]
-template <bool FILL>
+// PASS 0 = count (row lengths), 1 = fill (rows at the offsets the host scanned from the counts), 2 = ONE PASS: every
+// row block has the same capacity of cap_chunks chunks (sized from the previous build), so the offsets are known up
+// front and the tests run once; a row longer than that raises ctrl->scratch[6] and the host falls back to 0 + 1.
+// smem: TileShared | SearchShared | float4 sf[cap + 1] | int row_n[maxint + 8] | (fill) ushort stg[threads][16]
+template <int PASS>
 __global__ void __launch_bounds__(TPB, 3)
 k_tile_search(TileGrid g, Consts c, const double4 *__restrict__ q, const int *__restrict__ cell_start,
               const int *__restrict__ gcell_start, const int *__restrict__ gitems, const int *__restrict__ tile_fw0,
               int *__restrict__ row_count, int *__restrict__ fw_len, int *__restrict__ fw_store, int *__restrict__ fw_sent,
-              const long long *__restrict__ fw_off, uint2 *__restrict__ list, int cap, int maxint, Ctrl *ctrl) {
+              long long *__restrict__ fw_off, uint2 *__restrict__ list, int cap, int maxint, int cap_chunks, Ctrl *ctrl) {
+  constexpr bool FILL = PASS != 0;
+  constexpr bool ONEPASS = PASS == 2;
   extern __shared__ __align__(128) unsigned char smem[];
   TileShared &ts = *reinterpret_cast<TileShared *>(smem);
   SearchShared &ss = *reinterpret_cast<SearchShared *>(smem + tile_shared_offset());
@@ -176,8 +181,13 @@ k_tile_search(TileGrid g, Consts c, const double4 *__restrict__ q, const int *__
       unsigned short *my = stg + threadIdx.x * 16;
       if (FILL && act) {
         const int gfw = gfw0 + (a >> 3);
-        rowp = reinterpret_cast<uint4 *>(list + fw_off[gfw] + 4 * (a & 7));
-        store_chunks = store_steps(fw_len[gfw]) >> 2;
+        if (ONEPASS) {
+          rowp = reinterpret_cast<uint4 *>(list + (long long)gfw * cap_chunks * 32 + 4 * (a & 7));
+          store_chunks = cap_chunks;
+        } else {
+          rowp = reinterpret_cast<uint4 *>(list + fw_off[gfw] + 4 * (a & 7));
+          store_chunks = store_steps(fw_len[gfw]) >> 2;
+        }
       }
 #pragma unroll 1
       for (int nb = 0; nb < 54; nb++) {
@@ -235,6 +245,7 @@ k_tile_search(TileGrid g, Consts c, const double4 *__restrict__ q, const int *__
                 if (!within_search(q[own.src_l + l], q[gj], c.SL2)) continue;
               }
               n++;
+              if (ONEPASS && e >= 16 * store_chunks) continue;  // row longer than its block: counted, reported below
               my[sector_byte(e) >> 1] = (unsigned short)j;
               e++;
               if ((e & 15) == 0) {
@@ -268,6 +279,11 @@ k_tile_search(TileGrid g, Consts c, const double4 *__restrict__ q, const int *__
         if (act) {
           row_count[own.src_l + l] = n;   // exact
           nref += (unsigned long long)(nloc + 2 * (n - nloc));
+          if (ONEPASS) {
+            row_n[a] = n;
+            mrow = max(mrow, n);
+            if (n > 16 * store_chunks) ctrl->scratch[6] = 1;
+          }
         }
       } else {
         if (act) {
@@ -282,7 +298,7 @@ k_tile_search(TileGrid g, Consts c, const double4 *__restrict__ q, const int *__
     for (int o = 16; o > 0; o >>= 1) nref += __shfl_xor_sync(0xffffffffu, nref, o);
     if (lane == 0 && nref) atomicAdd(&ctrl->npairs, nref);
   }
-  if (!FILL) {
+  if (!FILL || ONEPASS) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mrow = max(mrow, __shfl_xor_sync(0xffffffffu, mrow, o));
     if (lane == 0 && mrow > *(volatile int *)&ctrl->max_row) atomicMax(&ctrl->max_row, mrow);
@@ -296,18 +312,22 @@ k_tile_search(TileGrid g, Consts c, const double4 *__restrict__ q, const int *__
         if (a < ts.n_int) mx = max(mx, (row_n[a] + kG - 1) / kG);
       }
       mx = (mx + 1) & ~1;
+      if (ONEPASS) mx = min(mx, 4 * cap_chunks);
       fw_len[gfw0 + fw] = mx;
-      fw_store[gfw0 + fw] = store_steps(mx) * 8;  // uint2 words of the row block
+      if (ONEPASS) fw_off[gfw0 + fw] = (long long)(gfw0 + fw) * cap_chunks * 32;
+      else fw_store[gfw0 + fw] = store_steps(mx) * 8;  // uint2 words of the row block
       fw_sent[gfw0 + fw] = sentinel;
     }
-  } else {
+  }
+  if (FILL) {
     // lanes of the last force-warp that own no local: sentinel rows
     const int nfw_t = (ts.n_int + kPW - 1) / kPW;
     const int a = ts.n_int + threadIdx.x;
     if (a < nfw_t * kPW) {
       const int gfw = gfw0 + (a >> 3);
-      uint4 *rowp = reinterpret_cast<uint4 *>(list + fw_off[gfw] + 4 * (a & 7));
-      const int store_chunks = store_steps(fw_len[gfw]) >> 2;
+      uint4 *rowp = ONEPASS ? reinterpret_cast<uint4 *>(list + (long long)gfw * cap_chunks * 32 + 4 * (a & 7))
+                            : reinterpret_cast<uint4 *>(list + fw_off[gfw] + 4 * (a & 7));
+      const int store_chunks = ONEPASS ? cap_chunks : store_steps(fw_len[gfw]) >> 2;
       const unsigned sw = (unsigned)sentinel | ((unsigned)sentinel << 16);
       const uint4 s4 = make_uint4(sw, sw, sw, sw);
       for (int ch = 0; ch < store_chunks; ch++) {
@@ -429,41 +449,79 @@ int build_pair_list(Unit *u) {
   MDB_TRY(u->fw_off.ensure((size_t)nfw + 2));
   MDB_TRY(u->scan.ensure((size_t)nfw + 2));
   MDB_TRY(u->scan_ws64.ensure(scan_workspace_ints(nfw + 2)));
-  // ---- pass 1: row lengths
   const size_t sm1 = search_smem_bytes(u->tile_cap, u->tile_maxint, false), sm2 = search_smem_bytes(u->tile_cap, u->tile_maxint, true);
-  MDB_CUDA(cudaFuncSetAttribute(k_tile_search<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
-  MDB_CUDA(cudaFuncSetAttribute(k_tile_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
-  k_tile_search<false><<<u->ntiles, TPB, sm1, u->stream>>>(tile_grid(u), u->c, u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr,
-                                                           u->gcell_items.ptr, u->tile_fw0.ptr, u->row_count.ptr, u->fw_len.ptr,
-                                                           u->scan.ptr, u->fw_sent.ptr, u->fw_off.ptr, u->list.ptr, u->tile_cap, u->tile_maxint, u->ctrl);
-  u->launches++;
-  MDB_CUDA(cudaGetLastError());
-  MDB_TRY(exclusive_scan_i32_to_i64(u->scan.ptr, u->fw_off.ptr, nfw, u->scan_ws64.ptr, u->stream, &u->launches, 1));
-  MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->scratch[4], u->fw_off.ptr + nfw, sizeof(long long), cudaMemcpyDeviceToHost, u->stream));
-  MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->max_row, &u->ctrl->max_row, sizeof(int), cudaMemcpyDeviceToHost, u->stream));
-  MDB_CUDA(cudaStreamSynchronize(u->stream));
-  long long words;
-  memcpy(&words, &u->ctrl_host->scratch[4], sizeof(long long));
-  u->list_entries = words * 4;
-  u->max_row = u->ctrl_host->max_row;   // upper bound of the longest row (sizes the derivation's row buffers)
-  if (u->max_row > 252) {
-    set_error("a particle has %d partners within the search length: rows above 252 entries are not supported", u->max_row);
-    return MDB200_ECAPACITY;
+  MDB_CUDA(cudaFuncSetAttribute(k_tile_search<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+  MDB_CUDA(cudaFuncSetAttribute(k_tile_search<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+  MDB_CUDA(cudaFuncSetAttribute(k_tile_search<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+#define SEARCH_ARGS(CAPCH) tile_grid(u), u->c, u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr, u->gcell_items.ptr, u->tile_fw0.ptr, \
+                           u->row_count.ptr, u->fw_len.ptr, u->scan.ptr, u->fw_sent.ptr, u->fw_off.ptr, u->list.ptr, u->tile_cap,   \
+                           u->tile_maxint, CAPCH, u->ctrl
+  bool built = false;
+  // ---- one pass with row blocks of fixed capacity, sized from the longest row of the previous build (every rebuild
+  //      but the first): the distance tests run once
+  static const bool no_onepass = getenv("MDB200_NO_ONEPASS") != nullptr;
+  if (u->max_row_exact > 0 && !no_onepass) {
+    const int cap_steps = ((u->max_row_exact + u->max_row_exact / 8 + 8 + kG - 1) / kG + 1) & ~1;  // + 12 % + 8 entries
+    const int cap_chunks = (cap_steps + 3) >> 2;
+    if (cap_chunks <= 16) {
+      const size_t need = (size_t)nfw * cap_chunks * 32 + 8192;
+      if (need > u->list.cap) {
+        if (getenv("MDB200_DEBUG")) fprintf(stderr, "[mdb200] list grows: %zu words > capacity %zu\n", need, u->list.cap);
+        MDB_TRY(u->list.ensure(need + need / 10));
+      }
+      MDB_TRY(u->list_in.ensure(u->list.cap));
+      MDB_CUDA(cudaMemsetAsync(&u->ctrl->scratch[6], 0, sizeof(int), u->stream));
+      k_tile_search<2><<<u->ntiles, TPB, sm2, u->stream>>>(SEARCH_ARGS(cap_chunks));
+      u->launches++;
+      MDB_CUDA(cudaGetLastError());
+      MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->scratch[6], &u->ctrl->scratch[6], sizeof(int), cudaMemcpyDeviceToHost, u->stream));
+      MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->max_row, &u->ctrl->max_row, sizeof(int), cudaMemcpyDeviceToHost, u->stream));
+      MDB_CUDA(cudaStreamSynchronize(u->stream));
+      if (u->ctrl_host->scratch[6] == 0) {
+        built = true;
+        u->max_row = u->ctrl_host->max_row;
+        u->max_row_exact = u->max_row;
+        u->list_entries = (long long)nfw * cap_chunks * 128;
+      } else {
+        if (getenv("MDB200_DEBUG")) fprintf(stderr, "[mdb200] one-pass list build: a row outgrew %d chunks; two passes\n", cap_chunks);
+        u->max_row_exact = std::max(u->max_row_exact, u->ctrl_host->max_row);
+        MDB_CUDA(cudaMemsetAsync(&u->ctrl->npairs, 0, sizeof(unsigned long long), u->stream));
+        MDB_CUDA(cudaMemsetAsync(&u->ctrl->max_row, 0, sizeof(int), u->stream));
+      }
+    }
   }
-  // Head-room: rows of a freshly generated lattice grow by ~20 % once it thermalises, and re-allocating a multi-GB
-  // list inside the step loop stalls for hundreds of ms; the walk reads one chunk past a row block, hence the slack.
-  const size_t need = (size_t)words + 8192;
-  if (need > u->list.cap) {
-    if (getenv("MDB200_DEBUG")) fprintf(stderr, "[mdb200] list grows: %zu words > capacity %zu\n", need, u->list.cap);
-    MDB_TRY(u->list.ensure(need + need * 3 / 10));
+  if (!built) {
+    // ---- pass 1: row lengths
+    k_tile_search<0><<<u->ntiles, TPB, sm1, u->stream>>>(SEARCH_ARGS(0));
+    u->launches++;
+    MDB_CUDA(cudaGetLastError());
+    MDB_TRY(exclusive_scan_i32_to_i64(u->scan.ptr, u->fw_off.ptr, nfw, u->scan_ws64.ptr, u->stream, &u->launches, 1));
+    MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->scratch[4], u->fw_off.ptr + nfw, sizeof(long long), cudaMemcpyDeviceToHost, u->stream));
+    MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->max_row, &u->ctrl->max_row, sizeof(int), cudaMemcpyDeviceToHost, u->stream));
+    MDB_CUDA(cudaStreamSynchronize(u->stream));
+    long long words;
+    memcpy(&words, &u->ctrl_host->scratch[4], sizeof(long long));
+    u->list_entries = words * 4;
+    u->max_row = u->ctrl_host->max_row;   // upper bound of the longest row
+    u->max_row_exact = u->max_row;        // (the count pass counts a superset: good enough to size the next one-pass build)
+    if (u->max_row > 252) {
+      set_error("a particle has %d partners within the search length: rows above 252 entries are not supported", u->max_row);
+      return MDB200_ECAPACITY;
+    }
+    // Head-room: rows of a freshly generated lattice grow by ~20 % once it thermalises, and re-allocating a multi-GB
+    // list inside the step loop stalls for hundreds of ms; the walk reads chunks past a row block, hence the slack.
+    const size_t need = (size_t)words + 8192;
+    if (need > u->list.cap) {
+      if (getenv("MDB200_DEBUG")) fprintf(stderr, "[mdb200] list grows: %zu words > capacity %zu\n", need, u->list.cap);
+      MDB_TRY(u->list.ensure(need + need * 6 / 10));
+    }
+    MDB_TRY(u->list_in.ensure(u->list.cap));
+    // ---- pass 2: rows
+    k_tile_search<1><<<u->ntiles, TPB, sm2, u->stream>>>(SEARCH_ARGS(0));
+    u->launches++;
+    MDB_CUDA(cudaGetLastError());
   }
-  MDB_TRY(u->list_in.ensure(u->list.cap));
-  // ---- pass 2: rows
-  k_tile_search<true><<<u->ntiles, TPB, sm2, u->stream>>>(tile_grid(u), u->c, u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr,
-                                                          u->gcell_items.ptr, u->tile_fw0.ptr, u->row_count.ptr, u->fw_len.ptr,
-                                                          u->scan.ptr, u->fw_sent.ptr, u->fw_off.ptr, u->list.ptr, u->tile_cap, u->tile_maxint, u->ctrl);
-  u->launches++;
-  MDB_CUDA(cudaGetLastError());
+#undef SEARCH_ARGS
   // the reference-style pair count (exact: counted by the fill pass); the caller synchronises anyway
   MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->npairs, &u->ctrl->npairs, sizeof(unsigned long long), cudaMemcpyDeviceToHost, u->stream));
   MDB_CUDA(cudaStreamSynchronize(u->stream));

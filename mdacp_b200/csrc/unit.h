@@ -198,7 +198,8 @@ struct Unit {
   double inner_keep = 0.0;        // radius the present inner list was derived with
   long long list_entries = 0;     // stored 16-bit entries (padded)
   long long npairs = 0;           // reference-style count of listed pairs (meshlist.cc:309)
-  int max_row = 0;
+  int max_row = 0;                // longest row (upper bound after a two-pass build)
+  int max_row_exact = 0;          // longest row seen so far (sizes the fixed-capacity row blocks of the next build)
 
   // expiry check
   DevBuf<double> disp;            // PairList::disp
