@@ -54,6 +54,7 @@ struct ForceConsts {
   // FORCE_KICK_LANGEVIN: ForceCalculator::Langevin (fcalculator.cc:765-778) in the epilogue
   double dt, gamma, amp;
   unsigned key0, key1, step_lo, step_hi;
+  double keep2;   // DERIVE: (cutoff + delta)^2
 };
 
 __device__ __forceinline__ void lds128(unsigned a, double &x, double &y) {
@@ -76,8 +77,8 @@ __device__ __forceinline__ double fast_rcp(double x) {
 
 // one listed entry: o0 / o1 = shared-memory addresses of the record's first / second half as this lane reads it
 template <bool EXACT>
-__device__ __forceinline__ void pair_kick(unsigned o0, unsigned o1, double a0, double a1, double a2, const ForceConsts &fc,
-                                          double &f0, double &f1, double &f2) {
+__device__ __forceinline__ double pair_kick(unsigned o0, unsigned o1, double a0, double a1, double a2, const ForceConsts &fc,
+                                            double &f0, double &f1, double &f2) {
   double j0, j1;
   lds128(o0, j0, j1);
   const double j2 = lds64(o1);
@@ -98,6 +99,7 @@ __device__ __forceinline__ void pair_kick(unsigned o0, unsigned o1, double a0, d
   f0 = fma(df, d0, f0);
   f1 = fma(df, d1, f1);
   f2 = fma(df, d2, f2);
+  return r2;
 }
 
 // MODE 0: impulses to fout (parity probe).  MODE 1: kick, p += F dt (ForceCalculator::CalculateForce).
@@ -123,11 +125,15 @@ struct TileArgs {
   int cap;           // staged-record capacity the shared memory was sized for
 };
 
-template <int MODE, bool EXACT>
+// DERIVE: the launch walks the (re-dealt) OUTER list and, on the side, writes the inner list: every lane packs the
+// entries of its column with r2 <= fc.keep2 into words of list_out (same row offsets) -- the compaction of
+// k_tile_compact for the price of the longer walk, since r2 is computed here anyway.
+template <int MODE, bool EXACT, bool DERIVE>
 __global__ void __launch_bounds__(FORCE_TPB, 2)
 k_tile_force(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__restrict__ p, double *__restrict__ fout,
              const uint2 *__restrict__ list, const long long *__restrict__ fw_off, const int *__restrict__ fw_len,
-             const int *__restrict__ ref_of_slot, double4 *__restrict__ q_out, Ctrl *ctrl, ForceConsts fc) {
+             const int *__restrict__ ref_of_slot, double4 *__restrict__ q_out, Ctrl *ctrl, ForceConsts fc,
+             uint2 *__restrict__ list_out, int *__restrict__ len_out) {
   extern __shared__ __align__(128) unsigned char smem[];
   TileShared &ts = *reinterpret_cast<TileShared *>(smem);
   double4 *sq = reinterpret_cast<double4 *>(smem + tile_shared_offset());
@@ -172,17 +178,36 @@ k_tile_force(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__re
     // miss to HBM ~1000.  Two named buffers, reloaded in place (rotating one into the other makes the copy wait for
     // the younger load: ncu showed 14 % of all stall samples there).  The allocation is padded: loading three chunks
     // past the last row is harmless.
+#define KEEP_ENTRY(R2, E)                                                         \
+  do {                                                                            \
+    if (DERIVE && (R2) <= fc.keep2) {                                             \
+      acc |= (unsigned long long)((E) >> 5) << (16 * (nk & 3));                   \
+      nk++;                                                                       \
+      if ((nk & 3) == 0) {                                                        \
+        dst[32 * ((nk >> 2) - 1)] = acc;                                          \
+        acc = 0ull;                                                               \
+      }                                                                           \
+    }                                                                             \
+  } while (0)
 #define WALK_CHUNK(W, K)                                                          \
   do {                                                                            \
     const unsigned e0 = ((W).x & 0xffffu) << 5, e1 = ((W).x >> 16) << 5;          \
     const unsigned e2 = ((W).y & 0xffffu) << 5, e3 = ((W).y >> 16) << 5;          \
-    pair_kick<EXACT>(e0 + hx, e0 + hx2, a0, a1, a2, fc, f0, f1, f2);              \
-    pair_kick<EXACT>(e1 + hx, e1 + hx2, a0, a1, a2, fc, f0, f1, f2);              \
+    const double r0 = pair_kick<EXACT>(e0 + hx, e0 + hx2, a0, a1, a2, fc, f0, f1, f2); \
+    KEEP_ENTRY(r0, e0);                                                           \
+    const double r1 = pair_kick<EXACT>(e1 + hx, e1 + hx2, a0, a1, a2, fc, f0, f1, f2); \
+    KEEP_ENTRY(r1, e1);                                                           \
     if ((K) + 2 < steps) {                                                        \
-      pair_kick<EXACT>(e2 + hx, e2 + hx2, a0, a1, a2, fc, f0, f1, f2);            \
-      pair_kick<EXACT>(e3 + hx, e3 + hx2, a0, a1, a2, fc, f0, f1, f2);            \
+      const double r2 = pair_kick<EXACT>(e2 + hx, e2 + hx2, a0, a1, a2, fc, f0, f1, f2); \
+      KEEP_ENTRY(r2, e2);                                                         \
+      const double r3 = pair_kick<EXACT>(e3 + hx, e3 + hx2, a0, a1, a2, fc, f0, f1, f2); \
+      KEEP_ENTRY(r3, e3);                                                         \
     }                                                                             \
   } while (0)
+    unsigned long long acc = 0ull;   // DERIVE: the output word being filled, kept entries of this lane
+    int nk = 0;
+    unsigned long long *__restrict__ dst =
+        DERIVE ? reinterpret_cast<unsigned long long *>(list_out + ts.row_base + ts.row_off[fw]) + lane : nullptr;
     // The next row: its first two chunks are requested before the last trip of this row, so that they travel while it
     // is finished, reduced and written back.  (The rows of the inner list keep the row offsets of the outer list,
     // i.e. they are NOT packed back to back: the stream cannot simply run on.)
@@ -207,6 +232,24 @@ k_tile_force(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__re
       lp += 64;
     }
 #undef WALK_CHUNK
+#undef KEEP_ENTRY
+    if (DERIVE) {
+      int steps_in = nk;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) steps_in = max(steps_in, __shfl_xor_sync(0xffffffffu, steps_in, o));
+      steps_in = (steps_in + 1) & ~1;
+      const int nchunk_in = (steps_in + 3) >> 2;
+      // the word in progress, topped up with the sentinel, and sentinel words up to the row's length
+      const unsigned long long sent = (unsigned long long)ts.n_all;
+      const unsigned long long sent4 = sent | (sent << 16) | (sent << 32) | (sent << 48);
+      int wi = nk >> 2;
+      if (nk & 3) {
+        dst[32 * wi] = acc | (sent4 & (~0ull << (16 * (nk & 3))));
+        wi++;
+      }
+      for (; wi < nchunk_in; wi++) dst[32 * wi] = sent4;
+      if (lane == 0) len_out[gfw0 + fw] = steps_in;
+    }
     if (steps <= 0) {
       na = __ldg(nlp);
       nb = __ldg(nlp + 32);
@@ -559,35 +602,59 @@ int derive_inner(Unit *u, double keep_len) {
 }
 
 // part: 0 = every tile, 1 = interior tiles only, 2 = boundary tiles only
-static int force_launch(Unit *u, int mode, double *fout, int part = 0) {
+// derive_keep > 0 (fused modes only): the launch walks the re-dealt OUTER list and writes the inner list of the
+// entries within derive_keep on the side (k_tile_force<.., DERIVE>); 0: it walks the current inner list.
+static int force_launch(Unit *u, int mode, double *fout, int part = 0, double derive_keep = 0.0) {
   const int ntl = (part == 0) ? u->ntiles : (part == 1 ? u->n_interior_tiles : u->ntiles - u->n_interior_tiles);
   if (ntl <= 0) return MDB200_OK;
-  if (!u->inner_valid) MDB_TRY(derive_inner(u, u->c.SL));  // no budgeted inner list: a full one
-  const ForceConsts fc = make_fc(u);
+  const bool derive = derive_keep > 0.0 && derive_keep < u->c.SL;
+  if (derive) {
+    if (!u->outer_rainbow) {
+      MDB_TRY(launch_redeal(u));
+      u->outer_rainbow = true;
+    }
+    MDB_TRY(u->list_in.ensure(u->list.cap));
+  } else if (!u->inner_valid) {
+    MDB_TRY(derive_inner(u, u->c.SL));  // no budgeted inner list: a full one
+  }
+  ForceConsts fc = make_fc(u);
+  fc.keep2 = derive_keep * derive_keep;
   const TileArgs ta = make_ta(u, part);
   const size_t sm = tile_smem_bytes_f64(u->tile_cap);
-  const uint2 *walk_list = u->inner_is_outer ? u->list.ptr : u->list_in.ptr;
-  const int *walk_len = u->inner_is_outer ? u->fw_len.ptr : u->fw_len_in.ptr;
-#define KLAUNCH(M, E)                                                                                               \
+  const bool outer = derive || u->inner_is_outer;
+  const uint2 *walk_list = outer ? u->list.ptr : u->list_in.ptr;
+  const int *walk_len = outer ? u->fw_len.ptr : u->fw_len_in.ptr;
+#define KLAUNCH(M, E, D)                                                                                            \
   do {                                                                                                              \
-    MDB_TRY(set_smem(k_tile_force<M, E>, sm));                                                                      \
-    k_tile_force<M, E><<<ntl, FORCE_TPB, sm, u->stream>>>(ta, u->c, u->q.ptr, u->p.ptr, fout, walk_list, u->fw_off.ptr, \
-                                                          walk_len, u->ref_of_slot.ptr, u->q_alt.ptr, u->ctrl, fc); \
+    MDB_TRY(set_smem(k_tile_force<M, E, D>, sm));                                                                   \
+    k_tile_force<M, E, D><<<ntl, FORCE_TPB, sm, u->stream>>>(ta, u->c, u->q.ptr, u->p.ptr, fout, walk_list, u->fw_off.ptr, \
+                                                             walk_len, u->ref_of_slot.ptr, u->q_alt.ptr, u->ctrl, fc, \
+                                                             u->list_in.ptr, u->fw_len_in.ptr);                     \
   } while (0)
-#define LAUNCH(E)                                          \
-  do {                                                     \
-    if (mode == FORCE_IMPULSE) KLAUNCH(FORCE_IMPULSE, E);  \
-    else if (mode == FORCE_KICK) KLAUNCH(FORCE_KICK, E);   \
-    else if (mode == FORCE_KICK_DRIFT) KLAUNCH(FORCE_KICK_DRIFT, E); \
-    else if (mode == FORCE_KICK_LANGEVIN) KLAUNCH(FORCE_KICK_LANGEVIN, E); \
-    else KLAUNCH(FORCE_KICK_DRIFT2, E);                    \
+#define LAUNCH(E)                                                 \
+  do {                                                            \
+    if (mode == FORCE_IMPULSE) KLAUNCH(FORCE_IMPULSE, E, false);  \
+    else if (mode == FORCE_KICK) KLAUNCH(FORCE_KICK, E, false);   \
+    else if (mode == FORCE_KICK_DRIFT && derive) KLAUNCH(FORCE_KICK_DRIFT, E, true); \
+    else if (mode == FORCE_KICK_DRIFT) KLAUNCH(FORCE_KICK_DRIFT, E, false); \
+    else if (mode == FORCE_KICK_LANGEVIN && derive) KLAUNCH(FORCE_KICK_LANGEVIN, E, true); \
+    else if (mode == FORCE_KICK_LANGEVIN) KLAUNCH(FORCE_KICK_LANGEVIN, E, false); \
+    else if (derive) KLAUNCH(FORCE_KICK_DRIFT2, E, true);         \
+    else KLAUNCH(FORCE_KICK_DRIFT2, E, false);                    \
   } while (0)
+  if (derive && (mode == FORCE_IMPULSE || mode == FORCE_KICK)) { set_error("deriving launch needs a fused mode"); return MDB200_EINVAL; }
   if (fc.exact_cut) LAUNCH(true);
   else LAUNCH(false);
 #undef LAUNCH
 #undef KLAUNCH
   u->launches++;
   MDB_CUDA(cudaGetLastError());
+  if (derive && part != 1) {
+    // (the interior launch of a split step derives the interior tiles' rows, the boundary launch the rest)
+    u->inner_valid = true;
+    u->inner_is_outer = false;
+    u->inner_keep = derive_keep;
+  }
   return MDB200_OK;
 }
 
@@ -602,12 +669,12 @@ int force_kick(Unit *u) {
 // predrift = also the first half drift of the next step (MODE 3; the caller sets u->predrifted).
 // part 0 = every tile; 1 = interior tiles only (no ghost staged: may run before the ghost exchange has
 // finished); 2 = boundary tiles.  The buffers swap after part 0 or 2.
-int force_kick_drift(Unit *u, bool predrift, int part) {
+int force_kick_drift(Unit *u, bool predrift, int part, double derive_keep) {
   if (u->pn == 0 || u->ntiles == 0) return MDB200_OK;
   static const bool dbg = getenv("MDB200_DEBUG_FORCE") != nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (dbg) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, u->stream); }
-  MDB_TRY(force_launch(u, predrift ? FORCE_KICK_DRIFT2 : FORCE_KICK_DRIFT, nullptr, part));
+  MDB_TRY(force_launch(u, predrift ? FORCE_KICK_DRIFT2 : FORCE_KICK_DRIFT, nullptr, part, derive_keep));
   if (dbg) {
     cudaEventRecord(e1, u->stream);
     cudaEventSynchronize(e1);
@@ -626,9 +693,9 @@ int force_kick_drift(Unit *u, bool predrift, int part) {
 // MDManager::CalculateLangevin (mdmanager.cc:186-192) in one kernel: kick, Langevin update of the momenta and --
 // speculatively -- the next step's first half drift (the caller sets u->predrifted = 2: the end-of-step positions
 // are the untouched input buffer).  Swaps q / q_alt.
-int force_kick_langevin(Unit *u) {
+int force_kick_langevin(Unit *u, double derive_keep) {
   if (u->pn == 0 || u->ntiles == 0) return MDB200_OK;
-  MDB_TRY(force_launch(u, FORCE_KICK_LANGEVIN, nullptr, 0));
+  MDB_TRY(force_launch(u, FORCE_KICK_LANGEVIN, nullptr, 0, derive_keep));
   std::swap(u->q, u->q_alt);  // ghosts live in both buffers (exchange.cu)
   u->vmax_ready = true;
   return MDB200_OK;
