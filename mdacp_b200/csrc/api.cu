@@ -510,18 +510,10 @@ static int calculate(Unit **us, int n) {
     for (auto *x : tm) delete x;
     MDB_TRY(r);
   }
-  // Where the step's force launch is a fused one (NVE, Langevin) and the list is to be pruned, that launch derives the
-  // inner list itself (force.cu, DERIVE): it computes every r2 anyway.  Otherwise (Nose-Hoover, pruning off, the
-  // diagnostic switches) the separate derivation runs here, once the ghosts of this step are in.
-  // (measured at 16 M particles: the deriving launch costs 7.4 ms against 3.2 ms for a walk plus 3.3 ms for the separate
-  // compaction -- spills and the longer rows eat what the shared gather saves -- so the fused variant is opt-in)
-  static const bool no_fused_derive = getenv("MDB200_FUSED_DERIVE") == nullptr;
-  const bool nose_hoover = ct && us[0]->prm.heatbath_type == MDB200_HT_NOSEHOOVER;
-  double fused_keep = 0.0;
-  if (derive && !nose_hoover && !no_fused_derive && !no_predrift && keep_len < us[0]->c.SL) {
-    fused_keep = keep_len;
-    for (int i = 0; i < n; i++) us[i]->derive_launches++;
-  } else if (derive) {
+  // the inner list for the velocity budget decided above, once the ghosts of this step are in.  (Deriving it inside the
+  // force launch, which computes every r2 anyway, was measured and dropped: at 16 M particles the deriving launch cost
+  // 7.4 ms against 3.2 ms for a walk plus 3.3 ms for the separate compaction.)
+  if (derive) {
     for (int i = 0; i < n; i++) {
       Unit *u = us[i];
       DeviceGuard g(u->device);
@@ -563,7 +555,7 @@ static int calculate(Unit **us, int n) {
         MDB_TRY(langevin_kick(us[i]));
       } else {
         // kick, Langevin update and the next step's first half drift in one launch (force.cu)
-        MDB_TRY(force_kick_langevin(us[i], fused_keep));
+        MDB_TRY(force_kick_langevin(us[i]));
         us[i]->predrifted = 2;
       }
       force_timer_end(us[i]);
@@ -574,9 +566,9 @@ static int calculate(Unit **us, int n) {
     Unit *u = us[0];
     DeviceGuard g(u->device);
     force_timer_begin(u);
-    MDB_TRY(force_kick_drift(u, predrift, 1, fused_keep));
+    MDB_TRY(force_kick_drift(u, predrift, 1));
     MDB_CUDA(cudaStreamWaitEvent(u->stream, u->ev_ghost, 0));
-    MDB_TRY(force_kick_drift(u, predrift, 2, fused_keep));
+    MDB_TRY(force_kick_drift(u, predrift, 2));
     force_timer_end(u);
     u->predrifted = predrift ? 1 : 0;
   } else {
@@ -588,10 +580,10 @@ static int calculate(Unit **us, int n) {
         PhaseTimer t(us[i], PH_FORCE);
         force_timer_begin(us[i]);
         if (split_test) {  // test hook: the interior / boundary launches of the overlapped path, back to back
-          MDB_TRY(force_kick_drift(us[i], predrift, 1, fused_keep));
-          MDB_TRY(force_kick_drift(us[i], predrift, 2, fused_keep));
+          MDB_TRY(force_kick_drift(us[i], predrift, 1));
+          MDB_TRY(force_kick_drift(us[i], predrift, 2));
         } else {
-          MDB_TRY(force_kick_drift(us[i], predrift, 0, fused_keep));
+          MDB_TRY(force_kick_drift(us[i], predrift, 0));
         }
         force_timer_end(us[i]);
         us[i]->predrifted = predrift ? 1 : 0;

@@ -54,7 +54,6 @@ struct ForceConsts {
   // FORCE_KICK_LANGEVIN: ForceCalculator::Langevin (fcalculator.cc:765-778) in the epilogue
   double dt, gamma, amp;
   unsigned key0, key1, step_lo, step_hi;
-  double keep2;   // DERIVE: (cutoff + delta)^2
 };
 
 __device__ __forceinline__ void lds128(unsigned a, double &x, double &y) {
@@ -125,15 +124,122 @@ struct TileArgs {
   int cap;           // staged-record capacity the shared memory was sized for
 };
 
-// DERIVE: the launch walks the (re-dealt) OUTER list and, on the side, writes the inner list: every lane packs the
-// entries of its column with r2 <= fc.keep2 into words of list_out (same row offsets) -- the compaction of
-// k_tile_compact for the price of the longer walk, since r2 is computed here anyway.
-template <int MODE, bool EXACT, bool DERIVE>
+// The list words of a row two chunks (8 steps) ahead of their use: a chunk takes a warp ~500 clk at 8 warps per
+// scheduler, a miss to HBM ~1000.  Two named buffers, reloaded in place (rotating one into the other makes the copy wait
+// for the younger load: ncu showed 14 % of all stall samples there).  The allocation is padded: loading three chunks
+// past the last row is harmless.
+struct RowStream {
+  const uint2 *lp;   // this lane's word of the row's first chunk not yet in wa / wb ... - 64
+  uint2 wa, wb;
+};
+__device__ __forceinline__ void row_stream_open(RowStream &rs, const uint2 *lp) {
+  rs.lp = lp;
+  rs.wa = __ldg(lp);
+  rs.wb = __ldg(lp + 32);
+}
+
+// Walks `steps` steps of the row rs points at, 4 lanes per local, and leaves rs at the row whose first word (of this
+// lane) is nlp: its first two chunks are requested before the last trip of this row, so that they travel while it is
+// finished, reduced and written back.  (The rows of the inner list keep the row offsets of the outer list, i.e. they
+// are NOT packed back to back: the stream cannot simply run on.)
+template <bool EXACT>
+__device__ __forceinline__ void walk_row(RowStream &rs, const uint2 *__restrict__ nlp, int steps, unsigned hx, unsigned hx2, double a0,
+                                         double a1, double a2, const ForceConsts &fc, double &f0, double &f1, double &f2) {
+#define WALK_CHUNK(W, HALF_ONLY)                                                  \
+  do {                                                                            \
+    const unsigned e0 = ((W).x & 0xffffu) << 5, e1 = ((W).x >> 16) << 5;          \
+    const unsigned e2 = ((W).y & 0xffffu) << 5, e3 = ((W).y >> 16) << 5;          \
+    pair_kick<EXACT>(e0 + hx, e0 + hx2, a0, a1, a2, fc, f0, f1, f2);              \
+    pair_kick<EXACT>(e1 + hx, e1 + hx2, a0, a1, a2, fc, f0, f1, f2);              \
+    if (!(HALF_ONLY)) {                                                           \
+      pair_kick<EXACT>(e2 + hx, e2 + hx2, a0, a1, a2, fc, f0, f1, f2);            \
+      pair_kick<EXACT>(e3 + hx, e3 + hx2, a0, a1, a2, fc, f0, f1, f2);            \
+    }                                                                             \
+  } while (0)
+  const uint2 *__restrict__ lp = rs.lp;
+  uint2 wa = rs.wa, wb = rs.wb;
+  // rem = steps still to walk (even)
+#pragma unroll 1
+  for (int rem = steps; rem > 0; rem -= 8) {
+    // the last trip reloads the buffers with the first two chunks of the next row instead of words past this one
+    const uint2 *__restrict__ src = (rem <= 8) ? nlp - 64 : lp;
+    {
+      const uint2 w = wa;
+      wa = __ldg(src + 64);
+      WALK_CHUNK(w, rem <= 2);
+    }
+    {
+      const uint2 w = wb;
+      wb = __ldg(src + 96);
+      if (rem > 4) WALK_CHUNK(w, rem <= 6);
+    }
+    lp += 64;
+  }
+#undef WALK_CHUNK
+  if (steps <= 0) {
+    wa = __ldg(nlp);
+    wb = __ldg(nlp + 32);
+  }
+  rs.lp = nlp;
+  rs.wa = wa;
+  rs.wb = wb;
+}
+
+// End of a row: the four lanes of a local add up, the writer lane (lane & 3 == 0) applies the MODE's update to the local
+// with staged index a / slot `slot` (see the MODE list above).  pa = the writer lane's momentum, loaded by the caller.
+template <int MODE>
+__device__ __forceinline__ void finish_row(double f0, double f1, double f2, bool writer, unsigned gp, int a, int slot, double4 pa,
+                                           const double4 *sq, double4 *__restrict__ p, double *__restrict__ fout,
+                                           const int *__restrict__ ref_of_slot, double4 *__restrict__ q_out, const ForceConsts &fc,
+                                           double &v2max) {
+#pragma unroll
+  for (int o = kG / 2; o > 0; o >>= 1) {
+    f0 += __shfl_xor_sync(0xffffffffu, f0, o);
+    f1 += __shfl_xor_sync(0xffffffffu, f1, o);
+    f2 += __shfl_xor_sync(0xffffffffu, f2, o);
+  }
+  if (!writer) return;
+  const double fx = gp ? f2 : f0, fy = f1, fz = gp ? f0 : f2;
+  if (MODE == FORCE_IMPULSE) {
+    const long long ra = ref_of_slot[slot];
+    fout[3 * ra + 0] = fx; fout[3 * ra + 1] = fy; fout[3 * ra + 2] = fz;
+    return;
+  }
+  pa.x += fx; pa.y += fy; pa.z += fz;
+  if (MODE == FORCE_KICK_LANGEVIN)
+    langevin_update(pa, (unsigned)ref_of_slot[slot], fc.gamma, fc.amp, fc.dt, fc.key0, fc.key1, fc.step_lo, fc.step_hi);
+  p[slot] = pa;
+  if (MODE == FORCE_KICK_DRIFT || MODE == FORCE_KICK_DRIFT2 || MODE == FORCE_KICK_LANGEVIN) {
+    const double4 qa = sq[a];
+    // fcalculator.cc:22-32, no FMA contraction: identical to k_drift_half
+    const double sx = __dmul_rn(pa.x, fc.dt2), sy = __dmul_rn(pa.y, fc.dt2), sz = __dmul_rn(pa.z, fc.dt2);
+    double nx = __dadd_rn(qa.x, sx), ny = __dadd_rn(qa.y, sy), nz = __dadd_rn(qa.z, sz);
+    if (MODE == FORCE_KICK_DRIFT2) { nx = __dadd_rn(nx, sx); ny = __dadd_rn(ny, sy); nz = __dadd_rn(nz, sz); }
+    q_out[slot] = make_double4(nx, ny, nz, ny);  // lane 3 repeats y (tile.cuh)
+    v2max = fmax(v2max, __dadd_rn(__dadd_rn(__dmul_rn(pa.x, pa.x), __dmul_rn(pa.y, pa.y)), __dmul_rn(pa.z, pa.z)));
+  }
+}
+
+// max |p|^2 of the launch for the next step's velocity-budget test
+__device__ __forceinline__ void publish_v2max(double v2max, int lane, Ctrl *ctrl) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v2max = fmax(v2max, __shfl_xor_sync(0xffffffffu, v2max, o));
+  if (lane == 0) {
+    // non-negative doubles order like their bit patterns; the maximum settles after a few blocks, so the
+    // plain read filters out almost every atomic
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v2max);
+    if (b > *(volatile unsigned long long *)&ctrl->vmax2_bits) atomicMax(&ctrl->vmax2_bits, b);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// One block per tile (two blocks of 512 threads per SM): small units, tiles too large for two staged copies.
+// ---------------------------------------------------------------------------------------------------------
+template <int MODE, bool EXACT>
 __global__ void __launch_bounds__(FORCE_TPB, 2)
 k_tile_force(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__restrict__ p, double *__restrict__ fout,
              const uint2 *__restrict__ list, const long long *__restrict__ fw_off, const int *__restrict__ fw_len,
-             const int *__restrict__ ref_of_slot, double4 *__restrict__ q_out, Ctrl *ctrl, ForceConsts fc,
-             uint2 *__restrict__ list_out, int *__restrict__ len_out) {
+             const int *__restrict__ ref_of_slot, double4 *__restrict__ q_out, Ctrl *ctrl, ForceConsts fc) {
   extern __shared__ __align__(128) unsigned char smem[];
   TileShared &ts = *reinterpret_cast<TileShared *>(smem);
   double4 *sq = reinterpret_cast<double4 *>(smem + tile_shared_offset());
@@ -144,12 +250,11 @@ k_tile_force(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__re
   const int n_int = ts.n_int;
   const int nfw = (n_int + kPW - 1) / kPW;
   // A warp walks a CONTIGUOUS range of the tile's rows (neighbouring row blocks: one L2 prefetch covers what comes
-  // next); the list words are loaded two chunks ahead.  The first two chunks are requested here, before the tile is
-  // staged.
+  // next).  The first two chunks are requested here, before the tile is staged.
   const int rbase = nfw / nwarps, rrem = nfw - rbase * nwarps;
   const int r0 = wid * rbase + min(wid, rrem), r1 = r0 + rbase + (wid < rrem ? 1 : 0);
-  const uint2 *__restrict__ lp = list + (r0 < r1 ? fw_off[gfw0 + r0] : fw_off[gfw0]) + lane;
-  uint2 wa = __ldg(lp), wb = __ldg(lp + 32);
+  RowStream rs;
+  row_stream_open(rs, list + (r0 < r1 ? fw_off[gfw0 + r0] : fw_off[gfw0]) + lane);
   tile_stage_rows(ts, gfw0, fw_off, fw_len);
   tile_stage_tma(ts, q, ta.gitems, sq);
   tile_stage_wait(ts);
@@ -159,7 +264,10 @@ k_tile_force(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__re
   double v2max = 0.0;
   for (int fw = r0; fw < r1; fw++) {
     // keep the stream ahead in L2: the row block two rows further on (one instruction, a 128-byte line per lane)
-    if (fw + 2 < r1) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(list + ts.row_base + ts.row_off[fw + 2]) + 128 * lane));
+    if (fw + 2 < r1) {
+      const int bytes = ((ts.row_len[fw + 2] + 3) >> 2) * 256;
+      if (128 * lane < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(list + ts.row_base + ts.row_off[fw + 2]) + 128 * lane));
+    }
     const int a = fw * kPW + (lane >> 2);
     const bool act = a < n_int;
     const unsigned ao = (unsigned)(act ? a : ts.n_all) << 5;
@@ -168,135 +276,296 @@ k_tile_force(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__re
     const double a2 = lds64(ao + hx2);
     const int steps = ts.row_len[fw];
     // the writer lane's momentum is needed at the end of the row: pull its line (and the next row's) towards the SM
+    const bool writer = act && (lane & 3) == 0;
     int slot = 0;
-    if (act && (lane & 3) == 0) {
+    if (writer) {
       slot = tile_interior_slot(ts, a);
       if (MODE != FORCE_IMPULSE) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + slot + kPW));
     }
     double f0 = 0.0, f1 = 0.0, f2 = 0.0;
-    // List words two chunks (8 steps) ahead of their use: a chunk takes a warp ~500 clk at 8 warps per scheduler, a
-    // miss to HBM ~1000.  Two named buffers, reloaded in place (rotating one into the other makes the copy wait for
-    // the younger load: ncu showed 14 % of all stall samples there).  The allocation is padded: loading three chunks
-    // past the last row is harmless.
-#define KEEP_ENTRY(R2, E)                                                         \
-  do {                                                                            \
-    if (DERIVE && (R2) <= fc.keep2) {                                             \
-      acc |= (unsigned long long)((E) >> 5) << (16 * (nk & 3));                   \
-      nk++;                                                                       \
-      if ((nk & 3) == 0) {                                                        \
-        dst[32 * ((nk >> 2) - 1)] = acc;                                          \
-        acc = 0ull;                                                               \
-      }                                                                           \
-    }                                                                             \
-  } while (0)
-#define WALK_CHUNK(W, K)                                                          \
-  do {                                                                            \
-    const unsigned e0 = ((W).x & 0xffffu) << 5, e1 = ((W).x >> 16) << 5;          \
-    const unsigned e2 = ((W).y & 0xffffu) << 5, e3 = ((W).y >> 16) << 5;          \
-    const double r0 = pair_kick<EXACT>(e0 + hx, e0 + hx2, a0, a1, a2, fc, f0, f1, f2); \
-    KEEP_ENTRY(r0, e0);                                                           \
-    const double r1 = pair_kick<EXACT>(e1 + hx, e1 + hx2, a0, a1, a2, fc, f0, f1, f2); \
-    KEEP_ENTRY(r1, e1);                                                           \
-    if ((K) + 2 < steps) {                                                        \
-      const double r2 = pair_kick<EXACT>(e2 + hx, e2 + hx2, a0, a1, a2, fc, f0, f1, f2); \
-      KEEP_ENTRY(r2, e2);                                                         \
-      const double r3 = pair_kick<EXACT>(e3 + hx, e3 + hx2, a0, a1, a2, fc, f0, f1, f2); \
-      KEEP_ENTRY(r3, e3);                                                         \
-    }                                                                             \
-  } while (0)
-    unsigned long long acc = 0ull;   // DERIVE: the output word being filled, kept entries of this lane
-    int nk = 0;
-    unsigned long long *__restrict__ dst =
-        DERIVE ? reinterpret_cast<unsigned long long *>(list_out + ts.row_base + ts.row_off[fw]) + lane : nullptr;
-    // The next row: its first two chunks are requested before the last trip of this row, so that they travel while it
-    // is finished, reduced and written back.  (The rows of the inner list keep the row offsets of the outer list,
-    // i.e. they are NOT packed back to back: the stream cannot simply run on.)
-    const uint2 *__restrict__ nlp = (fw + 1 < r1) ? list + ts.row_base + ts.row_off[fw + 1] + lane : lp;
-    uint2 na = wa, nb = wb;
-#pragma unroll 1
-    for (int k = 0; k < steps; k += 8) {
-      if (k + 8 >= steps) {
-        na = __ldg(nlp);
-        nb = __ldg(nlp + 32);
-      }
-      {
-        const uint2 w = wa;
-        wa = __ldg(lp + 64);
-        WALK_CHUNK(w, k);
-      }
-      if (k + 4 < steps) {
-        const uint2 w = wb;
-        wb = __ldg(lp + 96);
-        WALK_CHUNK(w, k + 4);
-      }
-      lp += 64;
-    }
-#undef WALK_CHUNK
-#undef KEEP_ENTRY
-    if (DERIVE) {
-      int steps_in = nk;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) steps_in = max(steps_in, __shfl_xor_sync(0xffffffffu, steps_in, o));
-      steps_in = (steps_in + 1) & ~1;
-      const int nchunk_in = (steps_in + 3) >> 2;
-      // the word in progress, topped up with the sentinel, and sentinel words up to the row's length
-      const unsigned long long sent = (unsigned long long)ts.n_all;
-      const unsigned long long sent4 = sent | (sent << 16) | (sent << 32) | (sent << 48);
-      int wi = nk >> 2;
-      if (nk & 3) {
-        dst[32 * wi] = acc | (sent4 & (~0ull << (16 * (nk & 3))));
-        wi++;
-      }
-      for (; wi < nchunk_in; wi++) dst[32 * wi] = sent4;
-      if (lane == 0) len_out[gfw0 + fw] = steps_in;
-    }
-    if (steps <= 0) {
-      na = __ldg(nlp);
-      nb = __ldg(nlp + 32);
-    }
-    lp = nlp;
-    wa = na;
-    wb = nb;
-    // the writer lane's momentum: requested before the reduction below needs it
+    const uint2 *__restrict__ nlp = (fw + 1 < r1) ? list + ts.row_base + ts.row_off[fw + 1] + lane : rs.lp;
+    walk_row<EXACT>(rs, nlp, steps, hx, hx2, a0, a1, a2, fc, f0, f1, f2);
     double4 pa = make_double4(0.0, 0.0, 0.0, 0.0);
-    if (MODE != FORCE_IMPULSE && act && (lane & 3) == 0) pa = p[slot];
-#pragma unroll
-    for (int o = kG / 2; o > 0; o >>= 1) {
-      f0 += __shfl_xor_sync(0xffffffffu, f0, o);
-      f1 += __shfl_xor_sync(0xffffffffu, f1, o);
-      f2 += __shfl_xor_sync(0xffffffffu, f2, o);
+    if (MODE != FORCE_IMPULSE && writer) pa = p[slot];   // requested before the reduction needs it
+    finish_row<MODE>(f0, f1, f2, writer, gp, a, slot, pa, sq, p, fout, ref_of_slot, q_out, fc, v2max);
+  }
+  if (MODE == FORCE_KICK_DRIFT || MODE == FORCE_KICK_DRIFT2 || MODE == FORCE_KICK_LANGEVIN) publish_v2max(v2max, lane, ctrl);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Persistent variant: one block per SM walks a strided sequence of tiles through TWO staged copies.
+//
+// With one block per tile a third of the block's life is not walking: the tile set-up and the staging (every warp
+// waits), and the wait for the slowest warp at the end (84 rows over 16 warps: a warp has 5 or 6).  Here the rows of
+// consecutive tiles are one stream of TICKETS handed out by a shared-memory counter: a walker warp that has finished a
+// row takes the next ticket, whichever tile it belongs to, and only waits if that tile is not published yet.  One extra
+// warp is the PRODUCER: it sets tile n + 2 up (cell table, prefix sums, row table: TileShared has three slots) while
+// tiles n and n + 1 are being walked; as soon as every row of tile n is done it issues the bulk copies of tile n + 2
+// into the buffer tile n occupied, gathers the ghosts, waits for the copies and publishes the tile with a release
+// store.  Nobody waits at a block barrier, and the last rows of a tile overlap the first of the next.
+// ---------------------------------------------------------------------------------------------------------
+// timing of the persistent kernel's phases (MDB200_DEBUG_FORCE prints them): clocks summed over blocks
+__device__ unsigned long long g_persist_clk[8];
+
+constexpr int kPersistWalkers = 24;                       // walker warps
+constexpr int kPersistProducers = 3;                      // producer warps: producer j sets up the tiles seq = j, j + 3, ...
+constexpr int kPersistThreads = 32 * (kPersistWalkers + kPersistProducers);
+struct PersistShared {
+  int staged;        // tiles of this block published so far (st.release / ld.acquire)
+  int ticket;        // next row ticket
+  int my_tiles;      // tiles of this block
+  int pad0;
+  int tile_done[4];  // ring: seq + 1 once every row of tile seq is done (its buffer and its TileShared slot are free)
+  int row_begin[4];  // ring over the tile sequence number: first ticket of the tile, one past its last
+  int row_end[4];
+  unsigned long long v2max_bits;   // max |p|^2 over the block's locals
+  unsigned long long mbar[2];      // mbarrier of the bulk copies into buffer 0 / 1
+  unsigned long long clk[4];       // producer: set-up, wait for the buffer, copies; walkers: wait for a tile
+  // what the producer needs (a copy of the kernel's arguments: persist_producer is not inlined, so that its registers
+  // and the walk's are allocated separately)
+  TileArgs ta;
+  TileDims dims;
+  const double4 *q;
+  const uint2 *list;
+  const long long *fw_off;
+  const int *fw_len;
+};
+constexpr size_t kPersistShared = 256;
+static_assert(sizeof(PersistShared) <= kPersistShared, "PersistShared outgrew its slot");
+__host__ __device__ inline size_t persist_head_bytes() { return 3 * tile_shared_offset() + kPersistShared; }
+static size_t persist_smem_bytes(int cap_records) { return persist_head_bytes() + 2 * (size_t)(cap_records + 1) * 32; }
+
+__device__ __forceinline__ int ld_acquire_shared(const int *p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_shared(int *p, int v) {
+  asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+// slot of the block's tile number seq in the ring of three TileShared
+__device__ __forceinline__ int persist_slot(int seq) { return seq - 3 * ((seq * 21846) >> 16); }   // seq % 3, seq < 32768
+
+// a producer warp: the tiles seq = first, first + kPersistProducers, ... of the block.  A set-up takes a warp longer than
+// the walkers need for a tile, so three of them work on consecutive tiles; they publish in order.
+__device__ __noinline__ void persist_producer(unsigned char *smem, int first) {
+  PersistShared &ps = *reinterpret_cast<PersistShared *>(smem + 3 * tile_shared_offset());
+  const TileArgs &ta = ps.ta;
+  const double4 *__restrict__ q = ps.q;
+  const long long *__restrict__ fw_off = ps.fw_off;
+  const int *__restrict__ fw_len = ps.fw_len;
+  const int lane = threadIdx.x & 31;
+  const int my_tiles = ps.my_tiles;
+  static_assert(kPersistProducers == 3, "producer j owns TileShared slot j");
+  TileShared &ts = *reinterpret_cast<TileShared *>(smem + first * tile_shared_offset());
+  for (int seq = first; seq < my_tiles; seq += kPersistProducers) {
+    double4 *sq = reinterpret_cast<double4 *>(smem + persist_head_bytes() + (seq & 1) * ((size_t)(ta.cap + 1) * 32));
+    const long long t0 = clock64();
+    // (1) set-up: needs the TileShared slot, which tile seq - 3 occupied
+    if (seq >= 3)
+      while (ld_acquire_shared(&ps.tile_done[(seq - 3) & 3]) != seq - 2) __nanosleep(32);
+    const int ti = (int)blockIdx.x + seq * (int)gridDim.x;
+    const int tile = ta.tile_order ? ta.tile_order[ta.tile_base + ti] : ti;
+    const int gfw0 = ta.tile_fw0[tile];
+    tile_setup_warp(ts, tile, ta.g, ps.dims, ta.cell_start, ta.gcell_start);
+    const int ncells = ts.ncells, n_loc = ts.n_loc, n_all = ts.n_all;
+    const int nfw = (ts.n_int + kPW - 1) / kPW;
+    const long long base = fw_off[gfw0];
+    for (int r = lane; r < nfw; r += 32) {
+      ts.row_off[r] = (int)(fw_off[gfw0 + r] - base);
+      ts.row_len[r] = (unsigned short)fw_len[gfw0 + r];
     }
-    if (act && (lane & 3) == 0) {
-      const double fx = gp ? f2 : f0, fy = f1, fz = gp ? f0 : f2;
-      if (MODE == FORCE_IMPULSE) {
-        const long long ra = ref_of_slot[slot];
-        fout[3 * ra + 0] = fx; fout[3 * ra + 1] = fy; fout[3 * ra + 2] = fz;
-      } else {
-        pa.x += fx; pa.y += fy; pa.z += fz;
-        if (MODE == FORCE_KICK_LANGEVIN)
-          langevin_update(pa, (unsigned)ref_of_slot[slot], fc.gamma, fc.amp, fc.dt, fc.key0, fc.key1, fc.step_lo, fc.step_hi);
-        p[slot] = pa;
-        if (MODE == FORCE_KICK_DRIFT || MODE == FORCE_KICK_DRIFT2 || MODE == FORCE_KICK_LANGEVIN) {
-          const double4 qa = sq[a];
-          // fcalculator.cc:22-32, no FMA contraction: identical to k_drift_half
-          const double sx = __dmul_rn(pa.x, fc.dt2), sy = __dmul_rn(pa.y, fc.dt2), sz = __dmul_rn(pa.z, fc.dt2);
-          double nx = __dadd_rn(qa.x, sx), ny = __dadd_rn(qa.y, sy), nz = __dadd_rn(qa.z, sz);
-          if (MODE == FORCE_KICK_DRIFT2) { nx = __dadd_rn(nx, sx); ny = __dadd_rn(ny, sy); nz = __dadd_rn(nz, sz); }
-          q_out[slot] = make_double4(nx, ny, nz, ny);  // lane 3 repeats y (tile.cuh)
-          v2max = fmax(v2max, __dadd_rn(__dadd_rn(__dmul_rn(pa.x, pa.x), __dmul_rn(pa.y, pa.y)), __dmul_rn(pa.z, pa.z)));
+    if (lane == 0) {
+      ts.row_base = base;
+      ts.rows_done = 0;
+    }
+    // (2) the buffer: free once every row of tile seq - 2 is done
+    const long long t1 = clock64();
+    if (seq >= 2)
+      while (ld_acquire_shared(&ps.tile_done[(seq - 2) & 3]) != seq - 1) __nanosleep(32);
+    const long long t2 = clock64();
+    // the generic-proxy accesses above (and the walkers' reads of the buffer's previous tile) before the bulk copies
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    unsigned long long *bar = &ps.mbar[seq & 1];
+    if (lane == 0) mbar_arrive_expect_tx(bar, (unsigned)n_loc * 32u);
+    __syncwarp();
+    for (int k = lane; k < ncells; k += 32) {
+      const int nl = ts.cell[k].n_l;
+      if (nl > 0) bulk_copy_g2s(sq + ts.cell[k].off_l, q + ts.cell[k].src_l, (unsigned)nl * 32u, bar);
+    }
+    // the first rows of the tile towards L2
+    if (nfw > 0) {
+      const int head = ts.row_off[min(nfw, 2 * kPersistWalkers) - 1];   // words before the last of them
+      for (long long b = 128ll * lane; b <= (long long)head * 8; b += 4096)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(ps.list + base) + b));
+    }
+    // ghosts (boundary tiles): staged index -> cell by binary search over the cells' ghost offsets
+    for (int i0 = n_loc; i0 < n_all; i0 += 128) {
+      int s[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int i = i0 + 32 * u + lane;
+        s[u] = -1;
+        if (i < n_all) {
+          int k = 0;
+#pragma unroll
+          for (int st = 64; st > 0; st >>= 1)
+            if (k + st < ncells && ts.cell[k + st].off_g <= i) k += st;
+          s[u] = ta.gitems[ts.cell[k].src_g + (i - ts.cell[k].off_g)];
         }
       }
+      double4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (s[u] >= 0) v[u] = ld_q256(q + s[u]);
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (s[u] >= 0) sq[i0 + 32 * u + lane] = v[u];
+    }
+    if (lane == 0) sq[n_all] = make_double4(1.0e8, 1.0e8, 1.0e8, 1.0e8);
+    mbar_wait(bar, (unsigned)(seq >> 1) & 1u);   // the buffer's mbarrier completes one phase per tile
+    const long long t3 = clock64();
+    // publish, in order
+    while (ld_acquire_shared(&ps.staged) != seq) __nanosleep(32);
+    __syncwarp();
+    if (lane == 0) {
+      const int begin = seq ? ps.row_end[(seq - 1) & 3] : 0;
+      ps.row_begin[seq & 3] = begin;
+      ps.row_end[seq & 3] = begin + nfw;
+      if (nfw == 0) ps.tile_done[seq & 3] = seq + 1;   // nobody walks it
+      st_release_shared(&ps.staged, seq + 1);
+      atomicAdd(&ps.clk[0], (unsigned long long)(t1 - t0));
+      atomicAdd(&ps.clk[1], (unsigned long long)(t2 - t1));
+      atomicAdd(&ps.clk[2], (unsigned long long)(t3 - t2));
+    }
+    __syncwarp();
+  }
+}
+
+template <int MODE, bool EXACT>
+__global__ void __launch_bounds__(kPersistThreads, 1)
+k_tile_force_p(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__restrict__ p, double *__restrict__ fout,
+               const uint2 *__restrict__ list, const long long *__restrict__ fw_off, const int *__restrict__ fw_len,
+               const int *__restrict__ ref_of_slot, double4 *__restrict__ q_out, Ctrl *ctrl, ForceConsts fc, int ntiles) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  PersistShared &ps = *reinterpret_cast<PersistShared *>(smem + 3 * tile_shared_offset());
+  const int lane = threadIdx.x & 31;
+#define TS_OF(SEQ) (*reinterpret_cast<TileShared *>(smem + persist_slot(SEQ) * tile_shared_offset()))
+#define SQ_OF(SEQ) (reinterpret_cast<double4 *>(smem + persist_head_bytes() + ((SEQ) & 1) * ((size_t)(ta.cap + 1) * 32)))
+  if (threadIdx.x == 0) {
+    ps.staged = 0;
+    ps.ticket = 0;
+    ps.my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles blockIdx.x + k gridDim.x
+    ps.v2max_bits = 0ull;
+    ps.clk[0] = ps.clk[1] = ps.clk[2] = ps.clk[3] = 0ull;
+    ps.tile_done[0] = ps.tile_done[1] = ps.tile_done[2] = ps.tile_done[3] = 0;
+    ps.ta = ta;
+#pragma unroll
+    for (int d = 0; d < 3; d++) { ps.dims.m[d] = c.m[d]; ps.dims.ms[d] = c.ms[d]; }
+    ps.q = q;
+    ps.list = list;
+    ps.fw_off = fw_off;
+    ps.fw_len = fw_len;
+    mbar_init(&ps.mbar[0], 1);
+    mbar_init(&ps.mbar[1], 1);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x >= 32 * kPersistWalkers) {
+    persist_producer(smem, (int)(threadIdx.x >> 5) - kPersistWalkers);
+  } else {
+    int cur = 0;
+    int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(&ps.ticket, 1);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    RowStream rs;
+    rs.lp = nullptr;   // not open at any row
+    rs.wa = rs.wb = make_uint2(0u, 0u);
+    const int my_tiles = ps.my_tiles;
+    while (cur < my_tiles) {
+      // the tile the ticket belongs to
+      if (ld_acquire_shared(&ps.staged) <= cur) {
+        const long long w0 = clock64();
+        while (ld_acquire_shared(&ps.staged) <= cur) __nanosleep(32);
+        if (lane == 0) atomicAdd(&ps.clk[3], (unsigned long long)(clock64() - w0));
+      }
+      if (ticket >= ps.row_end[cur & 3]) {
+        cur++;
+        continue;
+      }
+      // the next ticket now: its row's first chunks are requested before this row ends
+      int tnext = 0;
+      if (lane == 0) tnext = atomicAdd(&ps.ticket, 1);
+      tnext = __shfl_sync(0xffffffffu, tnext, 0);
+      double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+      {
+        const TileShared &ts = TS_OF(cur);
+        const int begin = ps.row_begin[cur & 3], nrows = ps.row_end[cur & 3] - begin;
+        const int fw = ticket - begin;
+        const uint2 *tl = list + ts.row_base;
+        // (the buffers hold the words at rs.lp and rs.lp + 32: the stream is open at this row if the walk before left it here)
+        if (rs.lp != tl + ts.row_off[fw] + lane) row_stream_open(rs, tl + ts.row_off[fw] + lane);
+        // keep the stream ahead in L2: the row a warp will take about two rows' time from now
+        if (fw + 2 * kPersistWalkers < nrows) {
+          const int bytes = ((ts.row_len[fw + 2 * kPersistWalkers] + 3) >> 2) * 256;
+          if (128 * lane < bytes)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(tl + ts.row_off[fw + 2 * kPersistWalkers]) + 128 * lane));
+        }
+        const unsigned gp = (lane >> 2) & 1u;                                // odd groups: x and z exchanged
+        const unsigned sbase = (unsigned)__cvta_generic_to_shared(SQ_OF(cur));
+        const unsigned hx = sbase + (gp << 4), hx2 = sbase + ((gp ^ 1u) << 4);
+        const int a = fw * kPW + (lane >> 2);
+        const unsigned ao = (unsigned)(a < ts.n_int ? a : ts.n_all) << 5;
+        double a0, a1;
+        lds128(ao + hx, a0, a1);
+        const double a2 = lds64(ao + hx2);
+        // the writer lane's momentum is needed at the end of the row: pull its line towards the SM
+        if (MODE != FORCE_IMPULSE && a < ts.n_int && (lane & 3) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + tile_interior_slot(ts, a)));
+        const bool more = tnext - begin < nrows;
+        const uint2 *__restrict__ nlp = more ? tl + ts.row_off[tnext - begin] + lane : rs.lp;
+        walk_row<EXACT>(rs, nlp, (int)ts.row_len[fw], hx, hx2, a0, a1, a2, fc, f0, f1, f2);
+      }
+      // (nothing read from shared memory above is to be kept in a register across the walk: it is read again below)
+      asm volatile("" ::: "memory");
+      {
+        const TileShared &ts = TS_OF(cur);
+        const int a = (ticket - ps.row_begin[cur & 3]) * kPW + (lane >> 2);
+        const bool writer = a < ts.n_int && (lane & 3) == 0;
+        int slot = 0;
+        double4 pa = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (writer) {
+          slot = tile_interior_slot(ts, a);
+          if (MODE != FORCE_IMPULSE) pa = p[slot];
+        }
+        double v2 = 0.0;
+        finish_row<MODE>(f0, f1, f2, writer, (lane >> 2) & 1u, a, slot, pa, SQ_OF(cur), p, fout, ref_of_slot, q_out, fc, v2);
+        if (MODE == FORCE_KICK_DRIFT || MODE == FORCE_KICK_DRIFT2 || MODE == FORCE_KICK_LANGEVIN) {
+          // non-negative doubles order like their bit patterns
+          const unsigned long long b = (unsigned long long)__double_as_longlong(v2);
+          if (writer && b > *(volatile unsigned long long *)&ps.v2max_bits) atomicMax(&ps.v2max_bits, b);
+        }
+        // This warp has read everything it needs from the tile's buffer (its loads have returned: their values were
+        // used above), so no fence: a fence would also wait for the row's global stores.
+        __syncwarp();
+        if (lane == 0) {
+          const int nrows = ps.row_end[cur & 3] - ps.row_begin[cur & 3];
+          if (atomicAdd(const_cast<int *>(&ts.rows_done), 1) == nrows - 1) st_release_shared(&ps.tile_done[cur & 3], cur + 1);
+        }
+      }
+      ticket = tnext;
     }
   }
-  if (MODE == FORCE_KICK_DRIFT || MODE == FORCE_KICK_DRIFT2 || MODE == FORCE_KICK_LANGEVIN) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v2max = fmax(v2max, __shfl_xor_sync(0xffffffffu, v2max, o));
-    if (lane == 0) {
-      // non-negative doubles order like their bit patterns; the maximum settles after a few blocks, so the
-      // plain read filters out almost every atomic
-      const unsigned long long b = (unsigned long long)__double_as_longlong(v2max);
+#undef TS_OF
+#undef SQ_OF
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (MODE == FORCE_KICK_DRIFT || MODE == FORCE_KICK_DRIFT2 || MODE == FORCE_KICK_LANGEVIN) {
+      // the maximum settles after a few blocks, so the plain read filters out almost every atomic
+      const unsigned long long b = ps.v2max_bits;
       if (b > *(volatile unsigned long long *)&ctrl->vmax2_bits) atomicMax(&ctrl->vmax2_bits, b);
     }
+    for (int i = 0; i < 4; i++) atomicAdd(&g_persist_clk[i], ps.clk[i]);
+    atomicAdd(&g_persist_clk[4], (unsigned long long)ps.my_tiles);
   }
 }
 
@@ -602,59 +871,52 @@ int derive_inner(Unit *u, double keep_len) {
 }
 
 // part: 0 = every tile, 1 = interior tiles only, 2 = boundary tiles only
-// derive_keep > 0 (fused modes only): the launch walks the re-dealt OUTER list and writes the inner list of the
-// entries within derive_keep on the side (k_tile_force<.., DERIVE>); 0: it walks the current inner list.
-static int force_launch(Unit *u, int mode, double *fout, int part = 0, double derive_keep = 0.0) {
+static int force_launch(Unit *u, int mode, double *fout, int part = 0) {
   const int ntl = (part == 0) ? u->ntiles : (part == 1 ? u->n_interior_tiles : u->ntiles - u->n_interior_tiles);
   if (ntl <= 0) return MDB200_OK;
-  const bool derive = derive_keep > 0.0 && derive_keep < u->c.SL;
-  if (derive) {
-    if (!u->outer_rainbow) {
-      MDB_TRY(launch_redeal(u));
-      u->outer_rainbow = true;
-    }
-    MDB_TRY(u->list_in.ensure(u->list.cap));
-  } else if (!u->inner_valid) {
-    MDB_TRY(derive_inner(u, u->c.SL));  // no budgeted inner list: a full one
-  }
-  ForceConsts fc = make_fc(u);
-  fc.keep2 = derive_keep * derive_keep;
+  if (!u->inner_valid) MDB_TRY(derive_inner(u, u->c.SL));  // no budgeted inner list: a full one
+  const ForceConsts fc = make_fc(u);
   const TileArgs ta = make_ta(u, part);
-  const size_t sm = tile_smem_bytes_f64(u->tile_cap);
-  const bool outer = derive || u->inner_is_outer;
+  const bool outer = u->inner_is_outer;
   const uint2 *walk_list = outer ? u->list.ptr : u->list_in.ptr;
   const int *walk_len = outer ? u->fw_len.ptr : u->fw_len_in.ptr;
-#define KLAUNCH(M, E, D)                                                                                            \
-  do {                                                                                                              \
-    MDB_TRY(set_smem(k_tile_force<M, E, D>, sm));                                                                   \
-    k_tile_force<M, E, D><<<ntl, FORCE_TPB, sm, u->stream>>>(ta, u->c, u->q.ptr, u->p.ptr, fout, walk_list, u->fw_off.ptr, \
-                                                             walk_len, u->ref_of_slot.ptr, u->q_alt.ptr, u->ctrl, fc, \
-                                                             u->list_in.ptr, u->fw_len_in.ptr);                     \
+  // Persistent kernel (one block per SM, two staged tiles): where two copies of the largest tile fit the SM's shared
+  // memory and a tile has rows enough to keep the walker warps busy; one block per tile otherwise
+  // (MDB200_FORCE_PERSIST=0/1 overrides the second condition; read at every launch so that tests can switch it).
+  const char *persist_env = getenv("MDB200_FORCE_PERSIST");
+  int sms = 148, smem_max = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, u->device);
+  cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, u->device);
+  const size_t psm = persist_smem_bytes(u->tile_cap);
+  bool persist = psm <= (size_t)smem_max && u->tile_maxint >= kPersistWalkers * kPW * 2 && ntl >= 2 * sms;
+  if (persist_env) persist = psm <= (size_t)smem_max && atoi(persist_env) != 0;
+  const size_t sm = tile_smem_bytes_f64(u->tile_cap);
+#define KLAUNCH(M, E)                                                                                                       \
+  do {                                                                                                                      \
+    if (persist) {                                                                                                          \
+      MDB_TRY(set_smem(k_tile_force_p<M, E>, psm));                                                                         \
+      k_tile_force_p<M, E><<<std::min(ntl, sms), kPersistThreads, psm, u->stream>>>(                                        \
+          ta, u->c, u->q.ptr, u->p.ptr, fout, walk_list, u->fw_off.ptr, walk_len, u->ref_of_slot.ptr, u->q_alt.ptr, u->ctrl, fc, ntl); \
+    } else {                                                                                                                \
+      MDB_TRY(set_smem(k_tile_force<M, E>, sm));                                                                            \
+      k_tile_force<M, E><<<ntl, FORCE_TPB, sm, u->stream>>>(ta, u->c, u->q.ptr, u->p.ptr, fout, walk_list, u->fw_off.ptr,   \
+                                                            walk_len, u->ref_of_slot.ptr, u->q_alt.ptr, u->ctrl, fc);       \
+    }                                                                                                                       \
   } while (0)
-#define LAUNCH(E)                                                 \
-  do {                                                            \
-    if (mode == FORCE_IMPULSE) KLAUNCH(FORCE_IMPULSE, E, false);  \
-    else if (mode == FORCE_KICK) KLAUNCH(FORCE_KICK, E, false);   \
-    else if (mode == FORCE_KICK_DRIFT && derive) KLAUNCH(FORCE_KICK_DRIFT, E, true); \
-    else if (mode == FORCE_KICK_DRIFT) KLAUNCH(FORCE_KICK_DRIFT, E, false); \
-    else if (mode == FORCE_KICK_LANGEVIN && derive) KLAUNCH(FORCE_KICK_LANGEVIN, E, true); \
-    else if (mode == FORCE_KICK_LANGEVIN) KLAUNCH(FORCE_KICK_LANGEVIN, E, false); \
-    else if (derive) KLAUNCH(FORCE_KICK_DRIFT2, E, true);         \
-    else KLAUNCH(FORCE_KICK_DRIFT2, E, false);                    \
+#define LAUNCH(E)                                                           \
+  do {                                                                      \
+    if (mode == FORCE_IMPULSE) KLAUNCH(FORCE_IMPULSE, E);                   \
+    else if (mode == FORCE_KICK) KLAUNCH(FORCE_KICK, E);                    \
+    else if (mode == FORCE_KICK_DRIFT) KLAUNCH(FORCE_KICK_DRIFT, E);        \
+    else if (mode == FORCE_KICK_LANGEVIN) KLAUNCH(FORCE_KICK_LANGEVIN, E);  \
+    else KLAUNCH(FORCE_KICK_DRIFT2, E);                                     \
   } while (0)
-  if (derive && (mode == FORCE_IMPULSE || mode == FORCE_KICK)) { set_error("deriving launch needs a fused mode"); return MDB200_EINVAL; }
   if (fc.exact_cut) LAUNCH(true);
   else LAUNCH(false);
 #undef LAUNCH
 #undef KLAUNCH
   u->launches++;
   MDB_CUDA(cudaGetLastError());
-  if (derive && part != 1) {
-    // (the interior launch of a split step derives the interior tiles' rows, the boundary launch the rest)
-    u->inner_valid = true;
-    u->inner_is_outer = false;
-    u->inner_keep = derive_keep;
-  }
   return MDB200_OK;
 }
 
@@ -669,18 +931,25 @@ int force_kick(Unit *u) {
 // predrift = also the first half drift of the next step (MODE 3; the caller sets u->predrifted).
 // part 0 = every tile; 1 = interior tiles only (no ghost staged: may run before the ghost exchange has
 // finished); 2 = boundary tiles.  The buffers swap after part 0 or 2.
-int force_kick_drift(Unit *u, bool predrift, int part, double derive_keep) {
+int force_kick_drift(Unit *u, bool predrift, int part) {
   if (u->pn == 0 || u->ntiles == 0) return MDB200_OK;
   static const bool dbg = getenv("MDB200_DEBUG_FORCE") != nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (dbg) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, u->stream); }
-  MDB_TRY(force_launch(u, predrift ? FORCE_KICK_DRIFT2 : FORCE_KICK_DRIFT, nullptr, part, derive_keep));
+  MDB_TRY(force_launch(u, predrift ? FORCE_KICK_DRIFT2 : FORCE_KICK_DRIFT, nullptr, part));
   if (dbg) {
     cudaEventRecord(e1, u->stream);
     cudaEventSynchronize(e1);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
     fprintf(stderr, "[mdb200] force launch: part %d keep %.4f  %.3f ms\n", part, u->inner_keep, ms);
+    unsigned long long h[8] = {0};
+    if (cudaMemcpyFromSymbol(h, g_persist_clk, sizeof(h)) == cudaSuccess && h[4]) {
+      fprintf(stderr, "[mdb200]   persistent: per tile: set-up %.0f clk, wait for the buffer %.0f, copies %.0f; walkers waited %.0f warp-clk per tile (%llu tiles)\n",
+              (double)h[0] / h[4], (double)h[1] / h[4], (double)h[2] / h[4], (double)h[3] / h[4], h[4]);
+      memset(h, 0, sizeof(h));
+      cudaMemcpyToSymbol(g_persist_clk, h, sizeof(h));
+    }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
   }
   if (part != 1) {
@@ -693,9 +962,9 @@ int force_kick_drift(Unit *u, bool predrift, int part, double derive_keep) {
 // MDManager::CalculateLangevin (mdmanager.cc:186-192) in one kernel: kick, Langevin update of the momenta and --
 // speculatively -- the next step's first half drift (the caller sets u->predrifted = 2: the end-of-step positions
 // are the untouched input buffer).  Swaps q / q_alt.
-int force_kick_langevin(Unit *u, double derive_keep) {
+int force_kick_langevin(Unit *u) {
   if (u->pn == 0 || u->ntiles == 0) return MDB200_OK;
-  MDB_TRY(force_launch(u, FORCE_KICK_LANGEVIN, nullptr, 0, derive_keep));
+  MDB_TRY(force_launch(u, FORCE_KICK_LANGEVIN, nullptr, 0));
   std::swap(u->q, u->q_alt);  // ghosts live in both buffers (exchange.cu)
   u->vmax_ready = true;
   return MDB200_OK;

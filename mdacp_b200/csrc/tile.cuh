@@ -47,6 +47,7 @@ struct TileShared {          // per-block bookkeeping in shared memory
   int n_all;                 // staged records:         [0, n_all); the sentinel sits at n_all
   int nicell;                // interior cells
   int next_row;              // work counter (dynamic row hand-out)
+  int rows_done;             // persistent force kernel: rows of the tile finished so far (the buffer is free at all of them)
   TileCell cell[kTileMaxCells];
   int icell_off[kTileMaxInterior + 1];  // staged offset of interior cell i (ascending)
   int icell_src[kTileMaxInterior];      // its first slot
@@ -95,16 +96,66 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 __device__ __forceinline__ int small_magic(int n) { return (int)__fdividef(65536.0f, (float)n) + 2; }
 __device__ __forceinline__ int small_div(int k, int magic) { return (k * magic) >> 16; }
 
-// Fills ts for tile `tile`.  Called by every thread of the block (blockDim.x >= 128); ends with a barrier.
-__device__ __forceinline__ void tile_setup(TileShared &ts, int tile, const TileGrid &g, const Consts &c,
-                                           const int *__restrict__ cell_start, const int *__restrict__ gcell_start) {
-  const int tid = threadIdx.x;
+// second half of the set-up, one warp: exclusive prefix sums per category (interior locals / halo locals / ghosts) in
+// cell order over the cell table the first half filled
+__device__ __forceinline__ void tile_setup_scan(TileShared &ts, int tid, int ncells) {
+  int base_a = 0, base_b = 0, base_c = 0, base_i = 0;
+  for (int k0 = 0; k0 < ncells; k0 += 32) {
+    const int k = k0 + tid;
+    const bool valid = k < ncells;
+    const bool inter = valid && ts.interior[k];
+    const int nl = valid ? ts.cell[k].n_l : 0, ng = valid ? ts.cell[k].n_g : 0;
+    int a = inter ? nl : 0, b = inter ? 0 : nl, cg = ng, fi = inter ? 1 : 0;
+    int sa = a, sb = b, sc = cg, si = fi;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int ta = __shfl_up_sync(0xffffffffu, sa, o), tb = __shfl_up_sync(0xffffffffu, sb, o);
+      const int tc = __shfl_up_sync(0xffffffffu, sc, o), ti = __shfl_up_sync(0xffffffffu, si, o);
+      if (tid >= o) { sa += ta; sb += tb; sc += tc; si += ti; }
+    }
+    if (valid) {
+      ts.cell[k].off_l = (unsigned short)(inter ? base_a + sa - a : base_b + sb - b);  // halo locals: n_int added below
+      ts.cell[k].off_g = (unsigned short)(base_c + sc - cg);                            // n_loc added below
+      if (inter) {
+        const int i = base_i + si - 1;
+        ts.icell_off[i] = base_a + sa - a;
+        ts.icell_src[i] = ts.cell[k].src_l;
+        ts.icell_k[i] = k;
+      }
+    }
+    base_a += __shfl_sync(0xffffffffu, sa, 31);
+    base_b += __shfl_sync(0xffffffffu, sb, 31);
+    base_c += __shfl_sync(0xffffffffu, sc, 31);
+    base_i += __shfl_sync(0xffffffffu, si, 31);
+  }
+  __syncwarp();
+  for (int k = tid; k < ncells; k += 32) {
+    if (!ts.interior[k]) ts.cell[k].off_l = (unsigned short)(ts.cell[k].off_l + base_a);
+    ts.cell[k].off_g = (unsigned short)(ts.cell[k].off_g + base_a + base_b);
+  }
+  if (tid == 0) {
+    ts.n_int = base_a;
+    ts.n_loc = base_a + base_b;
+    ts.n_all = base_a + base_b + base_c;
+    ts.nicell = base_i;
+    ts.icell_off[base_i] = base_a;
+  }
+}
+
+// what the tile set-up needs of Consts (the persistent force kernel keeps a copy in shared memory)
+struct TileDims {
+  int m[3];    // cells per axis including the ghost layers
+  int ms[3];   // the unit's own cells per axis
+};
+
+// halo box of tile `tile`: first cell and cells per axis
+template <class C>
+__device__ __forceinline__ void tile_box(int tile, const TileGrid &g, const C &c, int (&lo)[3], int (&n)[3]) {
   int T[3];
   T[2] = tile / (g.nt[0] * g.nt[1]);
   const int rem = tile - T[2] * (g.nt[0] * g.nt[1]);
   T[1] = rem / g.nt[0];
   T[0] = rem - T[1] * g.nt[0];
-  int lo[3], n[3];
 #pragma unroll
   for (int d = 0; d < 3; d++) {
     const int first = 1 + T[d] * g.t[d];                  // first interior cell (cells 1..ms are the unit's own)
@@ -112,6 +163,64 @@ __device__ __forceinline__ void tile_setup(TileShared &ts, int tile, const TileG
     lo[d] = first - 1;
     n[d] = last - first + 2;
   }
+}
+
+// The set-up by ONE warp (persistent force kernel: warp 0 sets the next tile up while the others walk): fills ts like
+// tile_setup except for the mbarrier, which that kernel initialises once.  Ends with __syncwarp.
+template <class C>
+__device__ __forceinline__ void tile_setup_warp(TileShared &ts, int tile, const TileGrid &g, const C &c,
+                                                const int *__restrict__ cell_start, const int *__restrict__ gcell_start) {
+  const int lane = threadIdx.x & 31;
+  int lo[3], n[3];
+  tile_box(tile, g, c, lo, n);
+  const int n01 = n[0] * n[1];
+  const int ncells = n01 * n[2];
+  if (lane == 0) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) { ts.lo[d] = lo[d]; ts.n[d] = n[d]; }
+    ts.ncells = ncells;
+  }
+  constexpr int kTrips = (kTileMaxCells + 31) / 32;
+  const int m01 = small_magic(n01), m0 = small_magic(n[0]);
+  int l0[kTrips], l1[kTrips], g0[kTrips], g1[kTrips];
+  // all the loads first: four dependent round trips to L2 otherwise
+#pragma unroll
+  for (int u = 0; u < kTrips; u++) {
+    const int k = lane + 32 * u;
+    if (k < ncells) {
+      const int kz = small_div(k, m01), r = k - kz * n01, ky = small_div(r, m0), kx = r - ky * n[0];
+      const int gc = (lo[0] + kx) + c.m[0] * ((lo[1] + ky) + c.m[1] * (lo[2] + kz));
+      l0[u] = __ldg(cell_start + gc); l1[u] = __ldg(cell_start + gc + 1);
+      g0[u] = __ldg(gcell_start + gc); g1[u] = __ldg(gcell_start + gc + 1);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kTrips; u++) {
+    const int k = lane + 32 * u;
+    if (k < ncells) {
+      const int kz = small_div(k, m01), r = k - kz * n01, ky = small_div(r, m0), kx = r - ky * n[0];
+      TileCell tc;
+      tc.src_l = l0[u];
+      tc.n_l = (unsigned short)min(l1[u] - l0[u], 65535);
+      tc.src_g = g0[u];
+      tc.n_g = (unsigned short)min(g1[u] - g0[u], 65535);
+      tc.off_l = 0;
+      tc.off_g = 0;
+      ts.interior[k] = (kx >= 1 && kx <= n[0] - 2 && ky >= 1 && ky <= n[1] - 2 && kz >= 1 && kz <= n[2] - 2) ? 1 : 0;
+      ts.cell[k] = tc;
+    }
+  }
+  __syncwarp();
+  tile_setup_scan(ts, lane, ncells);
+  __syncwarp();
+}
+
+// Fills ts for tile `tile`.  Called by every thread of the block (blockDim.x >= 128); ends with a barrier.
+__device__ __forceinline__ void tile_setup(TileShared &ts, int tile, const TileGrid &g, const Consts &c,
+                                           const int *__restrict__ cell_start, const int *__restrict__ gcell_start) {
+  const int tid = threadIdx.x;
+  int lo[3], n[3];
+  tile_box(tile, g, c, lo, n);
   const int n01 = n[0] * n[1];
   const int ncells = n01 * n[2];
   if (tid == 0) {
@@ -135,50 +244,7 @@ __device__ __forceinline__ void tile_setup(TileShared &ts, int tile, const TileG
     ts.cell[tid] = tc;
   }
   __syncthreads();
-  if (tid < 32) {
-    // exclusive prefix sums per category (interior locals / halo locals / ghosts) in cell order
-    int base_a = 0, base_b = 0, base_c = 0, base_i = 0;
-    for (int k0 = 0; k0 < ncells; k0 += 32) {
-      const int k = k0 + tid;
-      const bool valid = k < ncells;
-      const bool inter = valid && ts.interior[k];
-      const int nl = valid ? ts.cell[k].n_l : 0, ng = valid ? ts.cell[k].n_g : 0;
-      int a = inter ? nl : 0, b = inter ? 0 : nl, cg = ng, fi = inter ? 1 : 0;
-      int sa = a, sb = b, sc = cg, si = fi;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int ta = __shfl_up_sync(0xffffffffu, sa, o), tb = __shfl_up_sync(0xffffffffu, sb, o);
-        const int tc = __shfl_up_sync(0xffffffffu, sc, o), ti = __shfl_up_sync(0xffffffffu, si, o);
-        if (tid >= o) { sa += ta; sb += tb; sc += tc; si += ti; }
-      }
-      if (valid) {
-        ts.cell[k].off_l = (unsigned short)(inter ? base_a + sa - a : base_b + sb - b);  // halo locals: n_int added below
-        ts.cell[k].off_g = (unsigned short)(base_c + sc - cg);                            // n_loc added below
-        if (inter) {
-          const int i = base_i + si - 1;
-          ts.icell_off[i] = base_a + sa - a;
-          ts.icell_src[i] = ts.cell[k].src_l;
-          ts.icell_k[i] = k;
-        }
-      }
-      base_a += __shfl_sync(0xffffffffu, sa, 31);
-      base_b += __shfl_sync(0xffffffffu, sb, 31);
-      base_c += __shfl_sync(0xffffffffu, sc, 31);
-      base_i += __shfl_sync(0xffffffffu, si, 31);
-    }
-    __syncwarp();
-    for (int k = tid; k < ncells; k += 32) {
-      if (!ts.interior[k]) ts.cell[k].off_l = (unsigned short)(ts.cell[k].off_l + base_a);
-      ts.cell[k].off_g = (unsigned short)(ts.cell[k].off_g + base_a + base_b);
-    }
-    if (tid == 0) {
-      ts.n_int = base_a;
-      ts.n_loc = base_a + base_b;
-      ts.n_all = base_a + base_b + base_c;
-      ts.nicell = base_i;
-      ts.icell_off[base_i] = base_a;
-    }
-  }
+  if (tid < 32) tile_setup_scan(ts, tid, ncells);
   __syncthreads();
 }
 

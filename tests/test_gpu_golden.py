@@ -27,6 +27,22 @@ def test_multi_cell_tiles(name, shape, monkeypatch):
     the benchmark sizes use (up to 3 x 3 x 3 cells: several rows per warp, halo cells of neighbouring rows, edge
     tiles narrower than the rest) are forced here through MDB200_TILE."""
     monkeypatch.setenv("MDB200_TILE", shape)
+    monkeypatch.delenv("MDB200_FORCE_PERSIST", raising=False)
+    rec, cfg, steps, init_build = load_golden(name)
+    seed = int(cfg["Seed"]) if cfg.get("DumpInit") == "Langevin" else None
+    check_cuda_against_records(rec, steps, init_build, seed)
+
+
+@pytest.mark.parametrize("shape", [None, "3,3,3", "2,3,1"])
+@pytest.mark.parametrize("name", ["bench1", "bench8", "collision8", "langevinT0", "nosehoover8", "scale8"])
+def test_persistent_force_kernel(name, shape, monkeypatch):
+    """The persistent force kernel (one block per SM, producer warps staging the next tiles while the others walk)
+    is what the benchmark sizes run; the library would not pick it for systems this small, so it is forced here:
+    with one-cell tiles a block goes through hundreds of tiles of three or four rows each (tickets, buffer reuse and
+    the publication order all under stress), with 3 x 3 x 3 tiles through a few large ones."""
+    monkeypatch.setenv("MDB200_FORCE_PERSIST", "1")
+    if shape:
+        monkeypatch.setenv("MDB200_TILE", shape)
     rec, cfg, steps, init_build = load_golden(name)
     seed = int(cfg["Seed"]) if cfg.get("DumpInit") == "Langevin" else None
     check_cuda_against_records(rec, steps, init_build, seed)
