@@ -352,6 +352,13 @@ static int make_pairlist(Unit **us, int n) {
     MDB_TRY(stage_barrier(us, n));
   }
   MDB_TRY(comm_p2p_update(us, n));  // ghost windows of the neighbour processes for the per-step peer-to-peer refresh
+  for (int i = 0; i < n; i++) {
+    us[i]->ghost_composed = false;
+    if (n == 1) {
+      DeviceGuard g(us[i]->device);
+      MDB_TRY(ghost_compose(us[i]));  // a periodic box on one GPU: the per-step refresh becomes one launch
+    }
+  }
   dbg.lap("border lists + ghosts");
   // --- per unit MDUnit::MakePairList (mdunit.cc:194-198)
   for (int i = 0; i < n; i++) {
@@ -374,6 +381,10 @@ static int make_pairlist(Unit **us, int n) {
 
 // MDManager::SendBorderParticles (mdmanager.cc:283-292)
 static int send_border_particles(Unit **us, int n) {
+  if (n == 1 && us[0]->ghost_composed) {
+    DeviceGuard g(us[0]->device);
+    return ghost_refresh_composed(us[0], us[0]->stream);
+  }
   MDB_TRY(comm_refresh_begin(us, n, false));
   for (int dir = 0; dir < 6; dir++) {
     MDB_TRY(comm_border_refresh(us, n, dir));
@@ -408,6 +419,7 @@ static int any_expired(Unit **us, int n, int *expired) {
     for (int i = 0; i < n; i++) {
       DeviceGuard g(us[i]->device);
       MDB_CUDA(cudaStreamSynchronize(us[i]->stream));
+      MDB_TRY(expiry_check_finish(us[i]));
       force_timer_resolve(us[i]);
       MDB_TRY(check_device_error(us[i]));
       ex |= us[i]->ctrl_host->expired;
@@ -684,6 +696,8 @@ int mdb200_destroy(mdb200_unit *h) {
   u->cell_items.release(); u->gcell_count.release(); u->gcell_start.release(); u->gcell_cursor.release();
   u->gcell_items.release();
   for (int d = 0; d < 6; d++) u->border[d].release();
+  u->ghost_src.release();
+  u->ghost_shift.release();
   u->send_buf.release(); u->mig_send_q.release(); u->mig_send_p.release(); u->mig_recv_q.release();
   u->mig_recv_p.release(); u->mig_send_t.release(); u->mig_recv_t.release();
   u->row_count.release(); u->list_in.release(); u->fw_len_in.release(); u->tile_fw0.release(); u->tile_flag.release(); u->tile_order.release();
@@ -750,6 +764,7 @@ int mdb200_upload(mdb200_unit *h, const double (*q)[4], const double (*p)[4], co
   u->tn = pn;
   u->scratch_tail = pn;
   u->list_initialized = false;
+  u->ghost_composed = false;
   u->vmax_ready = false;
   u->predrifted = 0;
   u->inner_valid = false;

@@ -12,6 +12,9 @@
 // All kernels are HBM-bound streams: 64 B read + 32 B written per particle for the drift.
 #include <math.h>
 #include "rng.cuh"
+#include <stddef.h>
+#include <stdlib.h>
+#include <string.h>
 #include "unit.h"
 
 namespace mdb {
@@ -261,19 +264,11 @@ __global__ void k_expiry_cand(const double4 *__restrict__ q, const double4 *__re
   if (threadIdx.x == 0) ctrl->expired = hit ? 1 : 0;
 }
 
-int expiry_check_launch(Unit *u) {
-  const int grid_p = (int)((u->pn + TPB - 1) / TPB) < 1 ? 1 : (int)(((u->pn + TPB - 1) / TPB) > 1184 ? 1184 : ((u->pn + TPB - 1) / TPB));
+// the displacement test of the step (stages 2 and 3); both kernels return at once unless ctrl->phase is set
+static int expiry_disp_launch(Unit *u) {
   const int grid_t = (int)((u->tn + TPB - 1) / TPB) < 1 ? 1 : (int)(((u->tn + TPB - 1) / TPB) > 1184 ? 1184 : ((u->tn + TPB - 1) / TPB));
   const int cll = u->prm.check_list_length;
   const int Nl = (u->tn > cll) ? cll : (int)u->tn;  // pairlist.cc:85
-  MDB_TRY(u->cand.ensure((size_t)(cll > 0 ? cll : 1) + 1));
-  MDB_TRY(u->disp.ensure((size_t)u->cap_t + 1));
-  u->lifetime++;
-  if (u->vmax_ready)
-    k_expiry_budget<<<1, 1, 0, u->stream>>>(u->ctrl, u->c.dt, u->c.BL);
-  else
-    k_expiry_vmax<<<grid_p, TPB, 0, u->stream>>>(u->p.ptr, (int)u->pn, u->ctrl, u->c.dt, u->c.BL);
-  u->vmax_ready = false;
   const double4 *qprev = u->predrifted ? u->q_alt.ptr : nullptr;
   // pre-drifted after a Langevin step (predrifted == 2): the end-of-step positions are the previous buffer as it
   // is, i.e. "previous + p * 0" (adding +-0 is exact)
@@ -282,18 +277,57 @@ int expiry_check_launch(Unit *u) {
                                                (int)u->tn, u->ctrl, u->c.BL);
   k_expiry_cand<<<grid_t, TPB, 0, u->stream>>>(u->q.ptr, qprev, u->p.ptr, (int)u->pn, dt2, u->q0.ptr, u->disp.ptr,
                                                u->cand.ptr, (int)u->tn, Nl, u->ctrl, u->c.SL2, u->c.CL2);
-  u->launches += 3;
+  u->launches += 2;
   MDB_CUDA(cudaGetLastError());
-  MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->expired, &u->ctrl->expired, 2 * sizeof(int), cudaMemcpyDeviceToHost,
-                           u->stream));  // expired + err (adjacent)
-  MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->last_vmax2_bits, &u->ctrl->last_vmax2_bits, sizeof(unsigned long long),
-                           cudaMemcpyDeviceToHost, u->stream));
+  return MDB200_OK;
+}
+// buffer_length ... err of Ctrl (one copy): what the host needs of a check
+static int expiry_pull(Unit *u) {
+  static_assert(offsetof(Ctrl, err) + sizeof(int) - offsetof(Ctrl, buffer_length) <= 64, "Ctrl head");
+  MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->buffer_length, &u->ctrl->buffer_length,
+                           offsetof(Ctrl, err) + sizeof(int) - offsetof(Ctrl, buffer_length), cudaMemcpyDeviceToHost, u->stream));
   return MDB200_OK;
 }
 
+// The displacement kernels only act once the velocity budget is used up (ctrl->phase), a few steps before a rebuild.
+// While the budget the host saw after the previous step still covers TWICE the decrement of that step they are not even
+// launched (two launches of the five a small system's step has); should the device find the budget exhausted all the
+// same, expiry_check_finish launches them after the synchronisation.
+int expiry_check_launch(Unit *u) {
+  const int grid_p = (int)((u->pn + TPB - 1) / TPB) < 1 ? 1 : (int)(((u->pn + TPB - 1) / TPB) > 1184 ? 1184 : ((u->pn + TPB - 1) / TPB));
+  const int cll = u->prm.check_list_length;
+  MDB_TRY(u->cand.ensure((size_t)(cll > 0 ? cll : 1) + 1));
+  MDB_TRY(u->disp.ensure((size_t)u->cap_t + 1));
+  u->lifetime++;
+  if (u->vmax_ready)
+    k_expiry_budget<<<1, 1, 0, u->stream>>>(u->ctrl, u->c.dt, u->c.BL);
+  else
+    k_expiry_vmax<<<grid_p, TPB, 0, u->stream>>>(u->p.ptr, (int)u->pn, u->ctrl, u->c.dt, u->c.BL);
+  u->launches++;
+  u->vmax_ready = false;
+  static const bool always = getenv("MDB200_EXPIRY_ALWAYS") != nullptr;
+  double v2;
+  memcpy(&v2, &u->ctrl_host->last_vmax2_bits, sizeof(double));
+  const double dec = 2.0 * sqrt(v2) * u->c.dt;
+  // lifetime 1 = first check of a list: ctrl_host still describes the previous one
+  u->expiry_disp_skipped = !always && u->lifetime > 1 && u->ctrl_host->buffer_length > 0.0 && dec == dec &&
+                           u->ctrl_host->buffer_length - 2.0 * dec > 0.0;
+  if (!u->expiry_disp_skipped) MDB_TRY(expiry_disp_launch(u));
+  MDB_CUDA(cudaGetLastError());
+  return expiry_pull(u);
+}
+int expiry_check_finish(Unit *u) {
+  if (!u->expiry_disp_skipped || u->ctrl_host->phase == 0) return MDB200_OK;
+  u->expiry_disp_skipped = false;
+  MDB_TRY(expiry_disp_launch(u));
+  MDB_TRY(expiry_pull(u));
+  MDB_CUDA(cudaStreamSynchronize(u->stream));
+  return MDB200_OK;
+}
 int expiry_check_local(Unit *u, int *expired) {
   MDB_TRY(expiry_check_launch(u));
   MDB_CUDA(cudaStreamSynchronize(u->stream));
+  MDB_TRY(expiry_check_finish(u));
   *expired = u->ctrl_host->expired;
   return MDB200_OK;
 }

@@ -93,6 +93,7 @@ struct Ctrl {
   double c_d2;                   // (BufferLength - sqrt(dr2_max))^2, pairlist.cc:88-89
   unsigned long long vmax2_bits; // max |p|^2 as ordered bits
   unsigned long long dr2max_bits;
+  unsigned long long last_vmax2_bits;  // max |p|^2 the last expiry test saw (host: inner-list budget)
   int phase;                     // 1 = displacement check active in this call
   int cand_count;
   int expired;
@@ -104,7 +105,6 @@ struct Ctrl {
   double obs[4];                 // K,U,W scratch
   double zeta;                   // Variables::Zeta (variables.h:19)
   int scratch[8];
-  unsigned long long last_vmax2_bits;  // max |p|^2 the last expiry test saw (host: inner-list budget)
 };
 
 struct Unit {
@@ -152,6 +152,12 @@ struct Unit {
   DevBuf<int> border[6];
   long long n_border[6] = {0, 0, 0, 0, 0, 0};
   long long recv_off[6] = {0, 0, 0, 0, 0, 0}, recv_cnt[6] = {0, 0, 0, 0, 0, 0};
+  // one-unit periodic box: every ghost traced back to the LOCAL it is an image of (exchange.cu:ghost_compose), so that
+  // the per-step refresh is one launch instead of six dependent ones
+  DevBuf<int> ghost_src;          // per ghost (index - pn): source local slot
+  DevBuf<double4> ghost_shift;    // per ghost: the sum of the periodic shifts on its way (one per axis at most)
+  bool ghost_composed = false;
+  bool expiry_disp_skipped = false;  // the last expiry_check_launch left the displacement kernels out (integrate.cu)
   double shift[6][3];             // mdunit.cc:141-163
   DevBuf<double4> send_buf;       // pack buffer for off-device neighbours
   DevBuf<double4> mig_send_q, mig_send_p, mig_recv_q, mig_recv_p;
@@ -268,6 +274,8 @@ int migrate_compact_pack(Unit *u, int dir, long long n_leave);           // keep
 int migrate_unpack(Unit *dst, const double4 *rq, const double4 *rp, const int *rt, long long n);
 int wrap_periodic(Unit *u);
 int cell_sort_locals(Unit *u);
+int ghost_compose(Unit *u);          // after the six border set-ups of a rebuild (one unit that is all its own neighbours)
+int ghost_refresh_composed(Unit *u, cudaStream_t st);
 int find_border(Unit *u, int dir, long long *n_border);                  // sync
 int bin_ghosts(Unit *u);
 int snapshot_positions(Unit *u);
@@ -285,6 +293,7 @@ int drift_half(Unit *u);
 int drift_half_buffer(Unit *u, double4 *qbuf);                           // the same on a given position buffer
 int heatbath_momenta(Unit *u);
 int langevin_kick(Unit *u);
+int expiry_check_finish(Unit *u);   // after the stream synchronisation that follows expiry_check_launch
 int expiry_check_local(Unit *u, int *expired);                           // sync
 
 // force.cu
