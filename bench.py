@@ -534,7 +534,10 @@ def run_ours(args):
         fp64_src = "measured here: DFMA loop, 16 chains per thread (mdb200_measure_fp64_peak)"
     except Exception:
         fp64_peak, fp64_src = 37.0, "nominal B200 FP64 (measurement failed)"
-    roofline = {"bound": "hbm", "kernel": "k_tile_force (LJ force kick + half drifts)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "k_tile_force_p (persistent LJ force kick + half drifts)", "achieved": achieved, "peak": peak,
+                "limiter": "the kernel is not HBM-bound: ncu has the SM's shared-memory data pipe at 83 % of its peak (the "
+                           "partner gathers, 11 wavefronts per warp-step of which 5 are bank conflicts) and FP64 at 47 % "
+                           "(profiles/r02_force_persistent_ncu.txt, DESIGN.md section 5)",
                 "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
                 "traffic_source": traffic_src,
                 "peak_source": peak_src, "ms_per_launch": f_ms, "launches_timed": tm["force_launches"],
