@@ -208,14 +208,14 @@ __device__ __forceinline__ void finish_row(double f0, double f1, double f2, bool
   pa.x += fx; pa.y += fy; pa.z += fz;
   if (MODE == FORCE_KICK_LANGEVIN)
     langevin_update(pa, (unsigned)ref_of_slot[slot], fc.gamma, fc.amp, fc.dt, fc.key0, fc.key1, fc.step_lo, fc.step_hi);
-  p[slot] = pa;
+  st_256(p + slot, pa);
   if (MODE == FORCE_KICK_DRIFT || MODE == FORCE_KICK_DRIFT2 || MODE == FORCE_KICK_LANGEVIN) {
     const double4 qa = sq[a];
     // fcalculator.cc:22-32, no FMA contraction: identical to k_drift_half
     const double sx = __dmul_rn(pa.x, fc.dt2), sy = __dmul_rn(pa.y, fc.dt2), sz = __dmul_rn(pa.z, fc.dt2);
     double nx = __dadd_rn(qa.x, sx), ny = __dadd_rn(qa.y, sy), nz = __dadd_rn(qa.z, sz);
     if (MODE == FORCE_KICK_DRIFT2) { nx = __dadd_rn(nx, sx); ny = __dadd_rn(ny, sy); nz = __dadd_rn(nz, sz); }
-    q_out[slot] = make_double4(nx, ny, nz, ny);  // lane 3 repeats y (tile.cuh)
+    st_256(q_out + slot, make_double4(nx, ny, nz, ny));  // lane 3 repeats y (tile.cuh)
     v2max = fmax(v2max, __dadd_rn(__dadd_rn(__dmul_rn(pa.x, pa.x), __dmul_rn(pa.y, pa.y)), __dmul_rn(pa.z, pa.z)));
   }
 }
@@ -286,7 +286,7 @@ k_tile_force(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__re
     const uint2 *__restrict__ nlp = (fw + 1 < r1) ? list + ts.row_base + ts.row_off[fw + 1] + lane : rs.lp;
     walk_row<EXACT>(rs, nlp, steps, hx, hx2, a0, a1, a2, fc, f0, f1, f2);
     double4 pa = make_double4(0.0, 0.0, 0.0, 0.0);
-    if (MODE != FORCE_IMPULSE && writer) pa = p[slot];   // requested before the reduction needs it
+    if (MODE != FORCE_IMPULSE && writer) pa = ld_256(p + slot);   // requested before the reduction needs it
     finish_row<MODE>(f0, f1, f2, writer, gp, a, slot, pa, sq, p, fout, ref_of_slot, q_out, fc, v2max);
   }
   if (MODE == FORCE_KICK_DRIFT || MODE == FORCE_KICK_DRIFT2 || MODE == FORCE_KICK_LANGEVIN) publish_v2max(v2max, lane, ctrl);
@@ -374,6 +374,7 @@ __device__ __noinline__ void persist_producer(unsigned char *smem, int first) {
     for (int r = lane; r < nfw; r += 32) {
       ts.row_off[r] = (int)(fw_off[gfw0 + r] - base);
       ts.row_len[r] = (unsigned short)fw_len[gfw0 + r];
+      ts.row_cell[r] = (unsigned char)tile_interior_cell(ts, r * kPW);
     }
     if (lane == 0) {
       ts.row_base = base;
@@ -482,12 +483,16 @@ k_tile_force_p(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__
     rs.lp = nullptr;   // not open at any row
     rs.wa = rs.wb = make_uint2(0u, 0u);
     const int my_tiles = ps.my_tiles;
+    int staged = 0;   // tiles known to be published
     while (cur < my_tiles) {
       // the tile the ticket belongs to
-      if (ld_acquire_shared(&ps.staged) <= cur) {
-        const long long w0 = clock64();
-        while (ld_acquire_shared(&ps.staged) <= cur) __nanosleep(32);
-        if (lane == 0) atomicAdd(&ps.clk[3], (unsigned long long)(clock64() - w0));
+      if (staged <= cur) {
+        staged = ld_acquire_shared(&ps.staged);
+        if (staged <= cur) {
+          const long long w0 = clock64();
+          while ((staged = ld_acquire_shared(&ps.staged)) <= cur) __nanosleep(32);
+          if (lane == 0) atomicAdd(&ps.clk[3], (unsigned long long)(clock64() - w0));
+        }
       }
       if (ticket >= ps.row_end[cur & 3]) {
         cur++;
@@ -498,6 +503,7 @@ k_tile_force_p(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__
       if (lane == 0) tnext = atomicAdd(&ps.ticket, 1);
       tnext = __shfl_sync(0xffffffffu, tnext, 0);
       double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+      int slot = 0;
       {
         const TileShared &ts = TS_OF(cur);
         const int begin = ps.row_begin[cur & 3], nrows = ps.row_end[cur & 3] - begin;
@@ -505,12 +511,6 @@ k_tile_force_p(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__
         const uint2 *tl = list + ts.row_base;
         // (the buffers hold the words at rs.lp and rs.lp + 32: the stream is open at this row if the walk before left it here)
         if (rs.lp != tl + ts.row_off[fw] + lane) row_stream_open(rs, tl + ts.row_off[fw] + lane);
-        // keep the stream ahead in L2: the row a warp will take about two rows' time from now
-        if (fw + 2 * kPersistWalkers < nrows) {
-          const int bytes = ((ts.row_len[fw + 2 * kPersistWalkers] + 3) >> 2) * 256;
-          if (128 * lane < bytes)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(tl + ts.row_off[fw + 2 * kPersistWalkers]) + 128 * lane));
-        }
         const unsigned gp = (lane >> 2) & 1u;                                // odd groups: x and z exchanged
         const unsigned sbase = (unsigned)__cvta_generic_to_shared(SQ_OF(cur));
         const unsigned hx = sbase + (gp << 4), hx2 = sbase + ((gp ^ 1u) << 4);
@@ -520,7 +520,10 @@ k_tile_force_p(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__
         lds128(ao + hx, a0, a1);
         const double a2 = lds64(ao + hx2);
         // the writer lane's momentum is needed at the end of the row: pull its line towards the SM
-        if (MODE != FORCE_IMPULSE && a < ts.n_int && (lane & 3) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + tile_interior_slot(ts, a)));
+        if (a < ts.n_int && (lane & 3) == 0) {
+          slot = tile_interior_slot_from(ts, a, ts.row_cell[fw]);
+          if (MODE != FORCE_IMPULSE) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + slot));
+        }
         const bool more = tnext - begin < nrows;
         const uint2 *__restrict__ nlp = more ? tl + ts.row_off[tnext - begin] + lane : rs.lp;
         walk_row<EXACT>(rs, nlp, (int)ts.row_len[fw], hx, hx2, a0, a1, a2, fc, f0, f1, f2);
@@ -531,12 +534,8 @@ k_tile_force_p(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__
         const TileShared &ts = TS_OF(cur);
         const int a = (ticket - ps.row_begin[cur & 3]) * kPW + (lane >> 2);
         const bool writer = a < ts.n_int && (lane & 3) == 0;
-        int slot = 0;
         double4 pa = make_double4(0.0, 0.0, 0.0, 0.0);
-        if (writer) {
-          slot = tile_interior_slot(ts, a);
-          if (MODE != FORCE_IMPULSE) pa = p[slot];
-        }
+        if (MODE != FORCE_IMPULSE && writer) pa = ld_256(p + slot);
         double v2 = 0.0;
         finish_row<MODE>(f0, f1, f2, writer, (lane >> 2) & 1u, a, slot, pa, SQ_OF(cur), p, fout, ref_of_slot, q_out, fc, v2);
         if (MODE == FORCE_KICK_DRIFT || MODE == FORCE_KICK_DRIFT2 || MODE == FORCE_KICK_LANGEVIN) {

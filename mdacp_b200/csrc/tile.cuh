@@ -59,6 +59,7 @@ struct TileShared {          // per-block bookkeeping in shared memory
   unsigned long long mbar;              // mbarrier of the bulk copies that stage the tile (tile_stage_tma)
   int row_off[kTileMaxRows];
   unsigned short row_len[kTileMaxRows];
+  unsigned char row_cell[kTileMaxRows];   // interior cell (index into icell_*) of the row's first local (persistent force kernel)
 };
 
 // Shared memory of a kernel that stages FP64 records: bookkeeping + (records + sentinel) x 32 bytes
@@ -248,6 +249,20 @@ __device__ __forceinline__ void tile_setup(TileShared &ts, int tile, const TileG
   __syncthreads();
 }
 
+// the same starting from the interior cell i0 of an earlier local (a row's first): a row of 8 locals spans few cells
+__device__ __forceinline__ int tile_interior_slot_from(const TileShared &ts, int a, int i0) {
+  int i = i0;
+  while (i + 1 < ts.nicell && ts.icell_off[i + 1] <= a) i++;
+  return ts.icell_src[i] + (a - ts.icell_off[i]);
+}
+// interior cell of the interior local with staged index a
+__device__ __forceinline__ int tile_interior_cell(const TileShared &ts, int a) {
+  int i = 0;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1)
+    if (i + s < ts.nicell && ts.icell_off[i + s] <= a) i += s;
+  return i;
+}
 // slot of the interior local with staged index a (binary search over <= 27 interior cells)
 __device__ __forceinline__ int tile_interior_slot(const TileShared &ts, int a) {
   int i = 0;
@@ -257,6 +272,16 @@ __device__ __forceinline__ int tile_interior_slot(const TileShared &ts, int a) {
   return ts.icell_src[i] + (a - ts.icell_off[i]);
 }
 
+// 256-bit global accesses (sm_100): a double4 record is one instruction and, for the 8 consecutive records a force-warp's
+// writer lanes touch, one pass over each 128-byte line instead of two
+__device__ __forceinline__ double4 ld_256(const double4 *p) {
+  double4 v;
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_256(double4 *p, const double4 &v) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
 __device__ __forceinline__ double4 ld_q256(const double4 *p) {
   double4 v;
   asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
