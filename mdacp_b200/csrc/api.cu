@@ -361,6 +361,7 @@ static int make_pairlist(Unit **us, int n) {
   }
   dbg.lap("border lists + ghosts");
   // --- per unit MDUnit::MakePairList (mdunit.cc:194-198)
+  int lerr = MDB200_OK;
   for (int i = 0; i < n; i++) {
     Unit *u = us[i];
     DeviceGuard g(u->device);
@@ -373,9 +374,18 @@ static int make_pairlist(Unit **us, int n) {
     u->lifetime = 0;
     u->list_initialized = true;
     u->nbuilds++;
-    MDB_TRY(pull_error_word(u));
+    const int rc = pull_error_word(u);   // not returned yet: the other ranks must learn of it first
+    if (rc != MDB200_OK && lerr == MDB200_OK) lerr = rc;
   }
   dbg.lap("ghost bins + snapshot + search");
+  // a rank whose rebuild failed must not leave the others waiting in the next collective
+  int gerr = lerr;
+  MDB_TRY(comm_allreduce_or(us, n, &gerr));
+  if (lerr != MDB200_OK) return lerr;
+  if (gerr != MDB200_OK) {
+    set_error("another rank reported error %d while rebuilding the pair list", gerr);
+    return gerr;
+  }
   return MDB200_OK;
 }
 
@@ -403,7 +413,7 @@ static int inner_steps() {           // steps one derivation should last (MDB200
 }
 
 static int any_expired(Unit **us, int n, int *expired) {
-  int ex = 0;
+  int ex = 0, lerr = MDB200_OK;
   bool uninit = false;
   unsigned long long vbits = 0ull;
   for (int i = 0; i < n; i++)
@@ -421,13 +431,20 @@ static int any_expired(Unit **us, int n, int *expired) {
       MDB_CUDA(cudaStreamSynchronize(us[i]->stream));
       MDB_TRY(expiry_check_finish(us[i]));
       force_timer_resolve(us[i]);
-      MDB_TRY(check_device_error(us[i]));
+      const int rc = check_device_error(us[i]);   // not returned yet: the other ranks must learn of it first
+      if (rc != MDB200_OK && lerr == MDB200_OK) lerr = rc;
       ex |= us[i]->ctrl_host->expired;
       vbits = std::max(vbits, us[i]->ctrl_host->last_vmax2_bits);
     }
   }
-  // Communicator::AllReduceBoolean (mdmanager.cc:375); the global max |p|^2 rides along
-  MDB_TRY(comm_allreduce_flag_bits(us, n, &ex, &vbits));
+  // Communicator::AllReduceBoolean (mdmanager.cc:375); the global max |p|^2 and the error code ride along
+  int gerr = lerr;
+  MDB_TRY(comm_allreduce_flag_bits(us, n, &ex, &gerr, &vbits));
+  if (lerr != MDB200_OK) return lerr;
+  if (gerr != MDB200_OK) {
+    set_error("another rank reported error %d in this step", gerr);
+    return gerr;
+  }
   *expired = ex;
   // every particle (also the neighbours' that we see as ghosts) moves at most vmax dt per step, a pair
   // distance changes by at most twice that
@@ -674,9 +691,19 @@ int mdb200_create(const mdb200_params *params, int device, mdb200_unit **out) {
     u->stream = it->second;
     u->own_stream = false;
   }
-  MDB_CUDA(cudaMalloc(&u->ctrl, sizeof(Ctrl)));
-  MDB_CUDA(cudaMallocHost(&u->ctrl_host, sizeof(Ctrl)));
-  MDB_TRY(reset_ctrl(u, false));
+  // (no MDB_CUDA / MDB_TRY early returns from here on: what has been allocated is released on failure)
+  int rc = MDB200_OK;
+  if (cudaMalloc(&u->ctrl, sizeof(Ctrl)) != cudaSuccess || cudaMallocHost(&u->ctrl_host, sizeof(Ctrl)) != cudaSuccess) {
+    set_error("CUDA: %s (control block of unit %d)", cudaGetErrorString(cudaGetLastError()), params->unit_id);
+    rc = MDB200_ECUDA;
+  }
+  if (rc == MDB200_OK) rc = reset_ctrl(u, false);
+  if (rc != MDB200_OK) {
+    if (u->ctrl) cudaFree(u->ctrl);
+    if (u->ctrl_host) cudaFreeHost(u->ctrl_host);
+    delete h;
+    return rc;
+  }
   for (int d = 0; d < 6; d++) { u->nbr[d] = nullptr; u->src[d] = nullptr; }
   *out = h;
   return MDB200_OK;
@@ -940,6 +967,15 @@ int mdb200_change_scale(mdb200_unit **units, int n, double alpha) {
   std::vector<Unit *> us;
   MDB_TRY(unpack_units(units, n, us));
   if (!(alpha > 0.0)) { set_error("scale factor must be positive"); return MDB200_EINVAL; }
+  // every unit first: a refusal must not leave some units scaled and others not
+  for (int i = 0; i < n; i++)
+    for (int d = 0; d < 3; d++) {
+      const double w = us[i]->c.e[d] * alpha - us[i]->c.s[d] * alpha;
+      if (static_cast<int>(w / us[i]->c.SL) < 1) {
+        set_error("sub-box narrower than the search length along axis %d after scaling", d);
+        return MDB200_EINVAL;
+      }
+    }
   for (int i = 0; i < n; i++) MDB_TRY(materialize(us[i]));
   MDB_TRY(make_pairlist(us.data(), n));
   for (int i = 0; i < n; i++) {
@@ -950,11 +986,6 @@ int mdb200_change_scale(mdb200_unit **units, int n, double alpha) {
       u->c.L[d] = u->prm.L[d];
       u->c.s[d] *= alpha;
       u->c.e[d] *= alpha;
-      const double w = u->c.e[d] - u->c.s[d];
-      if (static_cast<int>(w / u->c.SL) < 1) {
-        set_error("sub-box narrower than the search length along axis %d after scaling", d);
-        return MDB200_EINVAL;
-      }
     }
     setup_cells(u);
     if (u->pn > 0) {

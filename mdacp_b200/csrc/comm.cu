@@ -131,12 +131,19 @@ static int p2p_open(const cudaIpcMemHandle_t &h, void **out, std::string *key_ou
   return MDB200_OK;
 }
 
-// ~10 s at 2 GHz: a neighbour that never shows up raises DE_COMM instead of hanging the device (and once the
-// flag is up nobody waits any more)
+// A neighbour that never shows up raises DE_COMM instead of hanging the device (and once the flag is up nobody waits
+// any more).  The limit is wall time (globaltimer, nanoseconds; MDB200_P2P_TIMEOUT_S, default 30 s, 0 = wait for
+// ever: under a debugger, compute-sanitizer or an oversubscribed host a neighbour may be legitimately slow).
+__device__ unsigned long long g_p2p_timeout_ns = 30000000000ull;
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ bool spin_until(const unsigned long long *flag, unsigned long long want, const Ctrl *ctrl) {
-  const long long t0 = clock64();
+  const unsigned long long t0 = global_ns(), limit = g_p2p_timeout_ns;
   while (*(const volatile unsigned long long *)flag < want) {
-    if ((*(const volatile int *)&ctrl->err & (int)DE_COMM) || clock64() - t0 > 20000000000LL) return false;
+    if ((*(const volatile int *)&ctrl->err & (int)DE_COMM) || (limit && global_ns() - t0 > limit)) return false;
     __nanosleep(64);
   }
   return true;
@@ -242,6 +249,11 @@ static int p2p_init(Unit *u) {
   MDB_CUDA(cudaMemcpyAsync(&ok, g_comm.d_cnt + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
   MDB_CUDA(cudaStreamSynchronize(st));
   g_p2p.enabled = ok != 0;
+  if (const char *ts = getenv("MDB200_P2P_TIMEOUT_S")) {
+    const double sec = atof(ts);
+    const unsigned long long ns = sec <= 0.0 ? 0ull : (unsigned long long)(sec * 1.0e9);
+    MDB_CUDA(cudaMemcpyToSymbol(g_p2p_timeout_ns, &ns, sizeof(ns)));
+  }
   if (g_p2p.enabled) {
     u->q.graveyard = &u->deferred_free;
     u->q_alt.graveyard = &u->deferred_free;
@@ -541,20 +553,24 @@ int comm_allreduce_or(Unit **us, int n, int *flag) {
   return MDB200_OK;
 }
 
-int comm_allreduce_flag_bits(Unit **us, int n, int *flag, unsigned long long *bits) {
+// {expiry flag, error code, max |p|^2 bits}, MAX over the ranks in one collective.  The error code rides along so that a
+// rank whose device reported an error (too fast, invalid position, ...) does not simply leave the step while the others
+// block in the next collective: every rank sees the largest code and returns.
+int comm_allreduce_flag_bits(Unit **us, int n, int *flag, int *err, unsigned long long *bits) {
   (void)n;
   if (g_comm.nranks <= 1 || !g_comm.comm) return MDB200_OK;
   Unit *u = us[0];
   cudaSetDevice(u->device);
   // bit patterns of non-negative doubles order like signed 64-bit integers
-  long long h[2] = {(long long)*flag, (long long)*bits};
+  long long h[3] = {(long long)*flag, (long long)*err, (long long)*bits};
   long long *d = reinterpret_cast<long long *>(g_comm.d_cnt64);
   MDB_CUDA(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, u->stream));
-  MDB_NCCL(g_nccl.AllReduce(d, d, 2, ncclInt64, ncclMax, g_comm.comm, u->stream));
+  MDB_NCCL(g_nccl.AllReduce(d, d, 3, ncclInt64, ncclMax, g_comm.comm, u->stream));
   MDB_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, u->stream));
   MDB_CUDA(cudaStreamSynchronize(u->stream));
   *flag = (int)h[0];
-  *bits = (unsigned long long)h[1];
+  *err = (int)h[1];
+  *bits = (unsigned long long)h[2];
   return MDB200_OK;
 }
 

@@ -26,7 +26,7 @@ bool comm_multi_process();
 int comm_remote_directions(const Unit *u);  // how many of the 6 neighbours live in another process
 int comm_allreduce_or(Unit **us, int n, int *flag);
 // MAX over the processes of {flag, bits}: the expiry flag and the bit pattern of max |p|^2 in one collective
-int comm_allreduce_flag_bits(Unit **us, int n, int *flag, unsigned long long *bits);
+int comm_allreduce_flag_bits(Unit **us, int n, int *flag, int *err, unsigned long long *bits);
 int comm_allreduce_sum(Unit **us, int n, double *v, int cnt);
 
 int ghost_put_to(Unit *s, int dir, double4 *dst, double4 *dst2, cudaStream_t st);

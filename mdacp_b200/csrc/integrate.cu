@@ -301,8 +301,12 @@ int expiry_check_launch(Unit *u) {
   u->lifetime++;
   if (u->vmax_ready)
     k_expiry_budget<<<1, 1, 0, u->stream>>>(u->ctrl, u->c.dt, u->c.BL);
-  else
+  else {
+    // a maximum a fused force launch left behind and nobody consumed (an external rebuild or rescale in between) must
+    // not enter this test: pairlist.cc:48-65 looks at the current locals only
+    MDB_CUDA(cudaMemsetAsync(&u->ctrl->vmax2_bits, 0, sizeof(unsigned long long), u->stream));
     k_expiry_vmax<<<grid_p, TPB, 0, u->stream>>>(u->p.ptr, (int)u->pn, u->ctrl, u->c.dt, u->c.BL);
+  }
   u->launches++;
   u->vmax_ready = false;
   static const bool always = getenv("MDB200_EXPIRY_ALWAYS") != nullptr;

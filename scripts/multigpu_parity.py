@@ -41,7 +41,8 @@ def main():
     dist.broadcast(buf, 0)
     uid = bytes(buf.cpu().numpy().tobytes())
     res = multigpu_parity_lib.run_parity(world, rank, lrank, uid, args.unit_length, args.steps, args.dt, args.v0)
-    print("rank %d/%d: %s" % (rank, world, json.dumps(res)), flush=True)
+    sys.stdout.write("rank %d/%d: %s\n" % (rank, world, json.dumps(res)))   # one write: lines of two ranks do not mix
+    sys.stdout.flush()
     bad = torch.tensor([0 if res["ok"] else 1], device="cuda")
     dist.all_reduce(bad)
     dist.barrier()
