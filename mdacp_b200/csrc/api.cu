@@ -539,16 +539,22 @@ static int calculate(Unit **us, int n) {
     for (auto *x : tm) delete x;
     MDB_TRY(r);
   }
-  // the inner list for the velocity budget decided above, once the ghosts of this step are in.  (Deriving it inside the
-  // force launch, which computes every r2 anyway, was measured and dropped: at 16 M particles the deriving launch cost
-  // 7.4 ms against 3.2 ms for a walk plus 3.3 ms for the separate compaction.)
+  // the inner list for the velocity budget decided above, once the ghosts of this step are in.  Where the whole unit goes
+  // through ONE persistent force launch, that launch derives it on the side (it computes every r2 anyway: the launch walks
+  // the longer outer list once instead of a separate compaction pass); otherwise k_tile_compact does.
+  std::vector<double> fused(n, 0.0);
   if (derive) {
+    const bool fusable_step = !(ct && !langevin) && !(langevin && no_predrift) && !overlap && !split_test;
     for (int i = 0; i < n; i++) {
       Unit *u = us[i];
       DeviceGuard g(u->device);
       if (overlap) MDB_CUDA(cudaStreamWaitEvent(u->stream, u->ev_ghost, 0));  // the derivation reads the ghosts
       derive_timer_begin(u);
-      MDB_TRY(derive_inner(u, keep_len));
+      if (fusable_step && keep_len < u->c.SL) {
+        MDB_TRY(ensure_rainbow(u));
+        if (force_can_derive(u, keep_len)) fused[i] = keep_len;
+      }
+      if (fused[i] == 0.0) MDB_TRY(derive_inner(u, keep_len));
       derive_timer_end(u);
     }
   }
@@ -584,7 +590,7 @@ static int calculate(Unit **us, int n) {
         MDB_TRY(langevin_kick(us[i]));
       } else {
         // kick, Langevin update and the next step's first half drift in one launch (force.cu)
-        MDB_TRY(force_kick_langevin(us[i]));
+        MDB_TRY(force_kick_langevin(us[i], fused[i]));
         us[i]->predrifted = 2;
       }
       force_timer_end(us[i]);
@@ -612,7 +618,7 @@ static int calculate(Unit **us, int n) {
           MDB_TRY(force_kick_drift(us[i], predrift, 1));
           MDB_TRY(force_kick_drift(us[i], predrift, 2));
         } else {
-          MDB_TRY(force_kick_drift(us[i], predrift, 0));
+          MDB_TRY(force_kick_drift(us[i], predrift, 0, fused[i]));
         }
         force_timer_end(us[i]);
         us[i]->predrifted = predrift ? 1 : 0;

@@ -54,6 +54,7 @@ struct ForceConsts {
   // FORCE_KICK_LANGEVIN: ForceCalculator::Langevin (fcalculator.cc:765-778) in the epilogue
   double dt, gamma, amp;
   unsigned key0, key1, step_lo, step_hi;
+  double keep2;   // deriving launch: (cutoff + delta)^2
 };
 
 __device__ __forceinline__ void lds128(unsigned a, double &x, double &y) {
@@ -142,18 +143,45 @@ __device__ __forceinline__ void row_stream_open(RowStream &rs, const uint2 *lp) 
 // lane) is nlp: its first two chunks are requested before the last trip of this row, so that they travel while it is
 // finished, reduced and written back.  (The rows of the inner list keep the row offsets of the outer list, i.e. they
 // are NOT packed back to back: the stream cannot simply run on.)
-template <bool EXACT>
+// What a DERIVING walk keeps per lane (k_tile_force_p<.., DERIVE>): the launch walks the re-dealt OUTER list and, on the
+// side, writes the inner list -- every lane packs the entries of its column with r2 <= fc.keep2 into words of the
+// inner row block (same row offsets): the compaction of k_tile_compact for the price of the longer walk, since r2 is
+// computed here anyway.
+struct DeriveLane {
+  unsigned long long acc;          // the output word being filled
+  int nk;                          // kept entries of this lane
+  bool on;                         // this lane's local exists (the last row of a tile has phantom locals)
+  unsigned long long *dst;         // this lane's word 0 of the inner row block
+};
+
+template <bool EXACT, bool DERIVE>
 __device__ __forceinline__ void walk_row(RowStream &rs, const uint2 *__restrict__ nlp, int steps, unsigned hx, unsigned hx2, double a0,
-                                         double a1, double a2, const ForceConsts &fc, double &f0, double &f1, double &f2) {
+                                         double a1, double a2, const ForceConsts &fc, double &f0, double &f1, double &f2,
+                                         DeriveLane &dl) {
+#define KEEP_ENTRY(R2, E)                                                         \
+  do {                                                                            \
+    if (DERIVE && dl.on && (R2) <= fc.keep2) {                                    \
+      dl.acc |= (unsigned long long)((E) >> 5) << (16 * (dl.nk & 3));             \
+      dl.nk++;                                                                    \
+      if ((dl.nk & 3) == 0) {                                                     \
+        dl.dst[32 * ((dl.nk >> 2) - 1)] = dl.acc;                                 \
+        dl.acc = 0ull;                                                            \
+      }                                                                           \
+    }                                                                             \
+  } while (0)
 #define WALK_CHUNK(W, HALF_ONLY)                                                  \
   do {                                                                            \
     const unsigned e0 = ((W).x & 0xffffu) << 5, e1 = ((W).x >> 16) << 5;          \
     const unsigned e2 = ((W).y & 0xffffu) << 5, e3 = ((W).y >> 16) << 5;          \
-    pair_kick<EXACT>(e0 + hx, e0 + hx2, a0, a1, a2, fc, f0, f1, f2);              \
-    pair_kick<EXACT>(e1 + hx, e1 + hx2, a0, a1, a2, fc, f0, f1, f2);              \
+    const double r0 = pair_kick<EXACT>(e0 + hx, e0 + hx2, a0, a1, a2, fc, f0, f1, f2); \
+    KEEP_ENTRY(r0, e0);                                                           \
+    const double r1 = pair_kick<EXACT>(e1 + hx, e1 + hx2, a0, a1, a2, fc, f0, f1, f2); \
+    KEEP_ENTRY(r1, e1);                                                           \
     if (!(HALF_ONLY)) {                                                           \
-      pair_kick<EXACT>(e2 + hx, e2 + hx2, a0, a1, a2, fc, f0, f1, f2);            \
-      pair_kick<EXACT>(e3 + hx, e3 + hx2, a0, a1, a2, fc, f0, f1, f2);            \
+      const double r2 = pair_kick<EXACT>(e2 + hx, e2 + hx2, a0, a1, a2, fc, f0, f1, f2); \
+      KEEP_ENTRY(r2, e2);                                                         \
+      const double r3 = pair_kick<EXACT>(e3 + hx, e3 + hx2, a0, a1, a2, fc, f0, f1, f2); \
+      KEEP_ENTRY(r3, e3);                                                         \
     }                                                                             \
   } while (0)
   const uint2 *__restrict__ lp = rs.lp;
@@ -176,6 +204,7 @@ __device__ __forceinline__ void walk_row(RowStream &rs, const uint2 *__restrict_
     lp += 64;
   }
 #undef WALK_CHUNK
+#undef KEEP_ENTRY
   if (steps <= 0) {
     wa = __ldg(nlp);
     wb = __ldg(nlp + 32);
@@ -183,6 +212,25 @@ __device__ __forceinline__ void walk_row(RowStream &rs, const uint2 *__restrict_
   rs.lp = nlp;
   rs.wa = wa;
   rs.wb = wb;
+}
+
+// end of a deriving row: the word in progress topped up with the sentinel, sentinel words up to the row's new length
+// (the longest column, rounded up to even), which lane 0 records
+__device__ __forceinline__ void derive_finish_row(DeriveLane &dl, int sentinel, int lane, int *len_slot) {
+  int steps_in = dl.nk;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) steps_in = max(steps_in, __shfl_xor_sync(0xffffffffu, steps_in, o));
+  steps_in = (steps_in + 1) & ~1;
+  const int nchunk_in = (steps_in + 3) >> 2;
+  const unsigned long long sent = (unsigned long long)sentinel;
+  const unsigned long long sent4 = sent | (sent << 16) | (sent << 32) | (sent << 48);
+  int wi = dl.nk >> 2;
+  if (dl.nk & 3) {
+    dl.dst[32 * wi] = dl.acc | (sent4 & (~0ull << (16 * (dl.nk & 3))));
+    wi++;
+  }
+  for (; wi < nchunk_in; wi++) dl.dst[32 * wi] = sent4;
+  if (lane == 0) *len_slot = steps_in;
 }
 
 // End of a row: the four lanes of a local add up, the writer lane (lane & 3 == 0) applies the MODE's update to the local
@@ -284,7 +332,8 @@ k_tile_force(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__re
     }
     double f0 = 0.0, f1 = 0.0, f2 = 0.0;
     const uint2 *__restrict__ nlp = (fw + 1 < r1) ? list + ts.row_base + ts.row_off[fw + 1] + lane : rs.lp;
-    walk_row<EXACT>(rs, nlp, steps, hx, hx2, a0, a1, a2, fc, f0, f1, f2);
+    DeriveLane no_dl;
+    walk_row<EXACT, false>(rs, nlp, steps, hx, hx2, a0, a1, a2, fc, f0, f1, f2, no_dl);
     double4 pa = make_double4(0.0, 0.0, 0.0, 0.0);
     if (MODE != FORCE_IMPULSE && writer) pa = ld_256(p + slot);   // requested before the reduction needs it
     finish_row<MODE>(f0, f1, f2, writer, gp, a, slot, pa, sq, p, fout, ref_of_slot, q_out, fc, v2max);
@@ -307,9 +356,11 @@ k_tile_force(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__re
 // timing of the persistent kernel's phases (MDB200_DEBUG_FORCE prints them): clocks summed over blocks
 __device__ unsigned long long g_persist_clk[8];
 
-constexpr int kPersistWalkers = 24;                       // walker warps
+constexpr int kPersistWalkers = 24;                       // walker warps (72 registers)
+constexpr int kPersistWalkersDerive = 24;                 // ... of a deriving launch (same budget: 8-16 bytes spilled)
 constexpr int kPersistProducers = 3;                      // producer warps: producer j sets up the tiles seq = j, j + 3, ...
 constexpr int kPersistThreads = 32 * (kPersistWalkers + kPersistProducers);
+constexpr int kPersistThreadsDerive = 32 * (kPersistWalkersDerive + kPersistProducers);
 struct PersistShared {
   int staged;        // tiles of this block published so far (st.release / ld.acquire)
   int ticket;        // next row ticket
@@ -378,6 +429,7 @@ __device__ __noinline__ void persist_producer(unsigned char *smem, int first) {
     }
     if (lane == 0) {
       ts.row_base = base;
+      ts.gfw0 = gfw0;
       ts.rows_done = 0;
     }
     // (2) the buffer: free once every row of tile seq - 2 is done
@@ -443,11 +495,13 @@ __device__ __noinline__ void persist_producer(unsigned char *smem, int first) {
   }
 }
 
-template <int MODE, bool EXACT>
-__global__ void __launch_bounds__(kPersistThreads, 1)
+template <int MODE, bool EXACT, bool DERIVE>
+__global__ void __launch_bounds__(DERIVE ? kPersistThreadsDerive : kPersistThreads, 1)
 k_tile_force_p(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__restrict__ p, double *__restrict__ fout,
                const uint2 *__restrict__ list, const long long *__restrict__ fw_off, const int *__restrict__ fw_len,
-               const int *__restrict__ ref_of_slot, double4 *__restrict__ q_out, Ctrl *ctrl, ForceConsts fc, int ntiles) {
+               const int *__restrict__ ref_of_slot, double4 *__restrict__ q_out, Ctrl *ctrl, ForceConsts fc, int ntiles,
+               uint2 *__restrict__ list_out, int *__restrict__ len_out) {
+  constexpr int kWalkers = DERIVE ? kPersistWalkersDerive : kPersistWalkers;
   extern __shared__ __align__(128) unsigned char smem[];
   PersistShared &ps = *reinterpret_cast<PersistShared *>(smem + 3 * tile_shared_offset());
   const int lane = threadIdx.x & 31;
@@ -472,8 +526,8 @@ k_tile_force_p(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  if (threadIdx.x >= 32 * kPersistWalkers) {
-    persist_producer(smem, (int)(threadIdx.x >> 5) - kPersistWalkers);
+  if (threadIdx.x >= 32 * kWalkers) {
+    persist_producer(smem, (int)(threadIdx.x >> 5) - kWalkers);
   } else {
     int cur = 0;
     int ticket = 0;
@@ -504,6 +558,7 @@ k_tile_force_p(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__
       tnext = __shfl_sync(0xffffffffu, tnext, 0);
       double f0 = 0.0, f1 = 0.0, f2 = 0.0;
       int slot = 0;
+      DeriveLane dl;
       {
         const TileShared &ts = TS_OF(cur);
         const int begin = ps.row_begin[cur & 3], nrows = ps.row_end[cur & 3] - begin;
@@ -526,12 +581,19 @@ k_tile_force_p(TileArgs ta, Consts c, const double4 *__restrict__ q, double4 *__
         }
         const bool more = tnext - begin < nrows;
         const uint2 *__restrict__ nlp = more ? tl + ts.row_off[tnext - begin] + lane : rs.lp;
-        walk_row<EXACT>(rs, nlp, (int)ts.row_len[fw], hx, hx2, a0, a1, a2, fc, f0, f1, f2);
+        if (DERIVE) {
+          dl.acc = 0ull;
+          dl.nk = 0;
+          dl.on = a < ts.n_int;
+          dl.dst = reinterpret_cast<unsigned long long *>(list_out + ts.row_base + ts.row_off[fw]) + lane;
+        }
+        walk_row<EXACT, DERIVE>(rs, nlp, (int)ts.row_len[fw], hx, hx2, a0, a1, a2, fc, f0, f1, f2, dl);
       }
       // (nothing read from shared memory above is to be kept in a register across the walk: it is read again below)
       asm volatile("" ::: "memory");
       {
         const TileShared &ts = TS_OF(cur);
+        if (DERIVE) derive_finish_row(dl, ts.n_all, lane, len_out + ts.gfw0 + (ticket - ps.row_begin[cur & 3]));
         const int a = (ticket - ps.row_begin[cur & 3]) * kPW + (lane >> 2);
         const bool writer = a < ts.n_int && (lane & 3) == 0;
         double4 pa = make_double4(0.0, 0.0, 0.0, 0.0);
@@ -839,6 +901,14 @@ static int launch_redeal(Unit *u) {
   return MDB200_OK;
 }
 
+// the outer list into rainbow order, once per rebuild (no-op afterwards)
+int ensure_rainbow(Unit *u) {
+  if (u->outer_rainbow || u->pn == 0 || u->ntiles == 0) return MDB200_OK;
+  MDB_TRY(launch_redeal(u));
+  u->outer_rainbow = true;
+  return MDB200_OK;
+}
+
 // Inner list = the outer entries within keep_len of the CURRENT positions.  The first call after a rebuild re-deals the
 // outer list in place into rainbow order (k_redeal); every call
 // then filters it lane by lane (k_tile_compact).  keep_len >= search length: the inner list IS the outer list.
@@ -849,10 +919,7 @@ int derive_inner(Unit *u, double keep_len) {
   static const bool dbg = getenv("MDB200_DEBUG") != nullptr;
   if (dbg) fprintf(stderr, "[mdb200] derive: keep %.4f, longest row <= %d entries, %s%s\n", keep_len, u->max_row,
                    u->outer_rainbow ? "" : "re-deal + ", keep_len >= u->c.SL ? "walk the outer list" : "compaction");
-  if (!u->outer_rainbow) {
-    MDB_TRY(launch_redeal(u));
-    u->outer_rainbow = true;
-  }
+  MDB_TRY(ensure_rainbow(u));
   if (keep_len >= u->c.SL) {
     u->inner_is_outer = true;
   } else {
@@ -869,19 +936,11 @@ int derive_inner(Unit *u, double keep_len) {
   return MDB200_OK;
 }
 
-// part: 0 = every tile, 1 = interior tiles only, 2 = boundary tiles only
-static int force_launch(Unit *u, int mode, double *fout, int part = 0) {
-  const int ntl = (part == 0) ? u->ntiles : (part == 1 ? u->n_interior_tiles : u->ntiles - u->n_interior_tiles);
-  if (ntl <= 0) return MDB200_OK;
-  if (!u->inner_valid) MDB_TRY(derive_inner(u, u->c.SL));  // no budgeted inner list: a full one
-  const ForceConsts fc = make_fc(u);
-  const TileArgs ta = make_ta(u, part);
-  const bool outer = u->inner_is_outer;
-  const uint2 *walk_list = outer ? u->list.ptr : u->list_in.ptr;
-  const int *walk_len = outer ? u->fw_len.ptr : u->fw_len_in.ptr;
-  // Persistent kernel (one block per SM, two staged tiles): where two copies of the largest tile fit the SM's shared
-  // memory and a tile has rows enough to keep the walker warps busy; one block per tile otherwise
-  // (MDB200_FORCE_PERSIST=0/1 overrides the second condition; read at every launch so that tests can switch it).
+// whether a launch over ntl tiles of this unit takes the persistent kernel (one block per SM, two staged tiles): where
+// two copies of the largest tile fit the SM's shared memory and a tile has rows enough to keep the walker warps busy;
+// one block per tile otherwise (MDB200_FORCE_PERSIST=0/1 overrides the second condition; read at every launch so that
+// tests can switch it)
+static bool force_persistent(const Unit *u, int ntl, int *sms_out, size_t *psm_out) {
   const char *persist_env = getenv("MDB200_FORCE_PERSIST");
   int sms = 148, smem_max = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, u->device);
@@ -889,13 +948,53 @@ static int force_launch(Unit *u, int mode, double *fout, int part = 0) {
   const size_t psm = persist_smem_bytes(u->tile_cap);
   bool persist = psm <= (size_t)smem_max && u->tile_maxint >= kPersistWalkers * kPW * 2 && ntl >= 2 * sms;
   if (persist_env) persist = psm <= (size_t)smem_max && atoi(persist_env) != 0;
+  if (sms_out) *sms_out = sms;
+  if (psm_out) *psm_out = psm;
+  return persist;
+}
+
+// A force launch that also derives the inner list for keep_len (k_tile_force_p<.., DERIVE>): possible where the whole
+// unit goes through one persistent launch and the outer list is already in rainbow order (MDB200_FUSED_DERIVE=0: never).
+bool force_can_derive(const Unit *u, double keep_len) {
+  const char *env = getenv("MDB200_FUSED_DERIVE");  // read at every call so that tests can switch it
+  const bool off = env && atoi(env) == 0;
+  if (off || u->pn == 0 || u->ntiles == 0 || !u->outer_rainbow || keep_len >= u->c.SL) return false;
+  return force_persistent(u, u->ntiles, nullptr, nullptr);
+}
+
+// part: 0 = every tile, 1 = interior tiles only, 2 = boundary tiles only
+// derive_keep > 0 (part 0, drifting modes, persistent kernel only: force_can_derive): walk the outer list and write the
+// inner list for that radius on the side
+static int force_launch(Unit *u, int mode, double *fout, int part = 0, double derive_keep = 0.0) {
+  const int ntl = (part == 0) ? u->ntiles : (part == 1 ? u->n_interior_tiles : u->ntiles - u->n_interior_tiles);
+  if (ntl <= 0) return MDB200_OK;
+  const bool deriving = derive_keep > 0.0;
+  if (!deriving && !u->inner_valid) MDB_TRY(derive_inner(u, u->c.SL));  // no budgeted inner list: a full one
+  ForceConsts fc = make_fc(u);
+  fc.keep2 = derive_keep * derive_keep;
+  const TileArgs ta = make_ta(u, part);
+  const bool outer = deriving || u->inner_is_outer;
+  const uint2 *walk_list = outer ? u->list.ptr : u->list_in.ptr;
+  const int *walk_len = outer ? u->fw_len.ptr : u->fw_len_in.ptr;
+  int sms = 148;
+  size_t psm = 0;
+  const bool persist = force_persistent(u, ntl, &sms, &psm);
   const size_t sm = tile_smem_bytes_f64(u->tile_cap);
+  if (deriving) {
+    if (!persist || part != 0 || mode < FORCE_KICK_DRIFT) { set_error("deriving force launch not available here"); return MDB200_EINVAL; }
+    MDB_TRY(u->list_in.ensure(u->list.cap));
+  }
+#define PLAUNCH(M, E, D)                                                                                                    \
+  do {                                                                                                                      \
+    MDB_TRY(set_smem(k_tile_force_p<M, E, D>, psm));                                                                        \
+    k_tile_force_p<M, E, D><<<std::min(ntl, sms), D ? kPersistThreadsDerive : kPersistThreads, psm, u->stream>>>(           \
+        ta, u->c, u->q.ptr, u->p.ptr, fout, walk_list, u->fw_off.ptr, walk_len, u->ref_of_slot.ptr, u->q_alt.ptr, u->ctrl, fc, \
+        ntl, u->list_in.ptr, u->fw_len_in.ptr);                                                                             \
+  } while (0)
 #define KLAUNCH(M, E)                                                                                                       \
   do {                                                                                                                      \
     if (persist) {                                                                                                          \
-      MDB_TRY(set_smem(k_tile_force_p<M, E>, psm));                                                                         \
-      k_tile_force_p<M, E><<<std::min(ntl, sms), kPersistThreads, psm, u->stream>>>(                                        \
-          ta, u->c, u->q.ptr, u->p.ptr, fout, walk_list, u->fw_off.ptr, walk_len, u->ref_of_slot.ptr, u->q_alt.ptr, u->ctrl, fc, ntl); \
+      PLAUNCH(M, E, false);                                                                                                 \
     } else {                                                                                                                \
       MDB_TRY(set_smem(k_tile_force<M, E>, sm));                                                                            \
       k_tile_force<M, E><<<ntl, FORCE_TPB, sm, u->stream>>>(ta, u->c, u->q.ptr, u->p.ptr, fout, walk_list, u->fw_off.ptr,   \
@@ -904,7 +1003,12 @@ static int force_launch(Unit *u, int mode, double *fout, int part = 0) {
   } while (0)
 #define LAUNCH(E)                                                           \
   do {                                                                      \
-    if (mode == FORCE_IMPULSE) KLAUNCH(FORCE_IMPULSE, E);                   \
+    if (deriving) {                                                         \
+      if (mode == FORCE_KICK_DRIFT) PLAUNCH(FORCE_KICK_DRIFT, E, true);     \
+      else if (mode == FORCE_KICK_LANGEVIN) PLAUNCH(FORCE_KICK_LANGEVIN, E, true); \
+      else PLAUNCH(FORCE_KICK_DRIFT2, E, true);                             \
+    }                                                                       \
+    else if (mode == FORCE_IMPULSE) KLAUNCH(FORCE_IMPULSE, E);              \
     else if (mode == FORCE_KICK) KLAUNCH(FORCE_KICK, E);                    \
     else if (mode == FORCE_KICK_DRIFT) KLAUNCH(FORCE_KICK_DRIFT, E);        \
     else if (mode == FORCE_KICK_LANGEVIN) KLAUNCH(FORCE_KICK_LANGEVIN, E);  \
@@ -914,8 +1018,14 @@ static int force_launch(Unit *u, int mode, double *fout, int part = 0) {
   else LAUNCH(false);
 #undef LAUNCH
 #undef KLAUNCH
+#undef PLAUNCH
   u->launches++;
   MDB_CUDA(cudaGetLastError());
+  if (deriving) {
+    u->inner_valid = true;
+    u->inner_is_outer = false;
+    u->inner_keep = derive_keep;
+  }
   return MDB200_OK;
 }
 
@@ -930,18 +1040,18 @@ int force_kick(Unit *u) {
 // predrift = also the first half drift of the next step (MODE 3; the caller sets u->predrifted).
 // part 0 = every tile; 1 = interior tiles only (no ghost staged: may run before the ghost exchange has
 // finished); 2 = boundary tiles.  The buffers swap after part 0 or 2.
-int force_kick_drift(Unit *u, bool predrift, int part) {
+int force_kick_drift(Unit *u, bool predrift, int part, double derive_keep) {
   if (u->pn == 0 || u->ntiles == 0) return MDB200_OK;
   static const bool dbg = getenv("MDB200_DEBUG_FORCE") != nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (dbg) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, u->stream); }
-  MDB_TRY(force_launch(u, predrift ? FORCE_KICK_DRIFT2 : FORCE_KICK_DRIFT, nullptr, part));
+  MDB_TRY(force_launch(u, predrift ? FORCE_KICK_DRIFT2 : FORCE_KICK_DRIFT, nullptr, part, derive_keep));
   if (dbg) {
     cudaEventRecord(e1, u->stream);
     cudaEventSynchronize(e1);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
-    fprintf(stderr, "[mdb200] force launch: part %d keep %.4f  %.3f ms\n", part, u->inner_keep, ms);
+    fprintf(stderr, "[mdb200] force launch: part %d keep %.4f%s  %.3f ms\n", part, u->inner_keep, derive_keep > 0.0 ? " (deriving)" : "", ms);
     unsigned long long h[8] = {0};
     if (cudaMemcpyFromSymbol(h, g_persist_clk, sizeof(h)) == cudaSuccess && h[4]) {
       fprintf(stderr, "[mdb200]   persistent: per tile: set-up %.0f clk, wait for the buffer %.0f, copies %.0f; walkers waited %.0f warp-clk per tile (%llu tiles)\n",
@@ -961,9 +1071,9 @@ int force_kick_drift(Unit *u, bool predrift, int part) {
 // MDManager::CalculateLangevin (mdmanager.cc:186-192) in one kernel: kick, Langevin update of the momenta and --
 // speculatively -- the next step's first half drift (the caller sets u->predrifted = 2: the end-of-step positions
 // are the untouched input buffer).  Swaps q / q_alt.
-int force_kick_langevin(Unit *u) {
+int force_kick_langevin(Unit *u, double derive_keep) {
   if (u->pn == 0 || u->ntiles == 0) return MDB200_OK;
-  MDB_TRY(force_launch(u, FORCE_KICK_LANGEVIN, nullptr, 0));
+  MDB_TRY(force_launch(u, FORCE_KICK_LANGEVIN, nullptr, 0, derive_keep));
   std::swap(u->q, u->q_alt);  // ghosts live in both buffers (exchange.cu)
   u->vmax_ready = true;
   return MDB200_OK;

@@ -56,6 +56,7 @@ struct TileShared {          // per-block bookkeeping in shared memory
   // row blocks of the tile's force-warps in the list being walked (filled by tile_stage_rows): first uint2 word
   // relative to the tile's first row block, and steps
   long long row_base;
+  int gfw0;                  // first force-warp (row) of the tile in the unit's row arrays
   unsigned long long mbar;              // mbarrier of the bulk copies that stage the tile (tile_stage_tma)
   int row_off[kTileMaxRows];
   unsigned short row_len[kTileMaxRows];

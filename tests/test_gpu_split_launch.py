@@ -41,3 +41,17 @@ def test_outer_list_only_matches_reference_golden(name, monkeypatch):
     monkeypatch.setenv("MDB200_NO_PRUNE", "1")
     rec, cfg, steps, init_build = load_golden(name)
     check_cuda_against_records(rec, steps, init_build, None, observe_every=25)
+
+
+# Where the whole unit goes through one persistent force launch, that launch also derives the inner list (force.cu
+# DERIVE); MDB200_FUSED_DERIVE=0 keeps the separate compaction pass.  Both must meet the same parity, also with rare
+# observations (the pre-drifted state runs through the deriving launches).
+@pytest.mark.parametrize("fused", ["1", "0"])
+@pytest.mark.parametrize("name", ["bench1", "bench8", "collision2", "langevinT0"])
+def test_fused_inner_list_derivation(name, fused, monkeypatch):
+    monkeypatch.setenv("MDB200_FORCE_PERSIST", "1")
+    monkeypatch.setenv("MDB200_FUSED_DERIVE", fused)
+    monkeypatch.setenv("MDB200_TILE", "2,2,2")
+    rec, cfg, steps, init_build = load_golden(name)
+    seed = int(cfg["Seed"]) if cfg.get("DumpInit") == "Langevin" else None
+    check_cuda_against_records(rec, steps, init_build, seed, observe_every=25)
