@@ -195,6 +195,29 @@ int mdb200_event_elapsed_ms(mdb200_unit *u, int slot_a, int slot_b, double *ms);
 /* Block until all work queued for the unit has finished. */
 int mdb200_synchronize(mdb200_unit *u);
 
+/* ---- On-device initial states (mdacp_b200/csrc/generate.cu) -------------------
+ * The reference's configuration makers run on the host, serially per unit, and hand every site to
+ * MDUnit::AddParticle (mdunit.cc:36-49).  These entries do the same on the device: each APPENDS the particles the
+ * maker would add to this unit (the sites inside its box, in the maker's loop order, type 0) to the unit's particle
+ * store, exactly as if the host maker had run and mdb200_upload had followed.  Positions, types and drift
+ * velocities are bit-identical to the host makers'; mdb200_generate_initial_velocity reproduces the reference's
+ * std::mt19937 draws exactly but takes cos / sin from CUDA's libm (a few ulp from glibc's), so it is an ALTERNATIVE
+ * provenance of the initial momenta, not a bit-for-bit one.  A unit that has stepped must be cleared first
+ * (MDB200_EINVAL otherwise).  `added` (may be NULL) receives the number of particles appended. */
+/* Variables::Variables (variables.cc:8-17): empty store, particle_number = 0. */
+int mdb200_clear(mdb200_unit *u);
+/* ExtractConfigurationMaker::Execute (confmaker.cc:174-252), Mode=Benchmark: the unit's own FCC lattice minus
+ * n_full - int(volume * density) vacancies drawn from std::mt19937(unit id). */
+int mdb200_generate_benchmark(mdb200_unit *u, double density, long long *added);
+/* radius <= 0: ConfigurationMaker::Execute (confmaker.cc:9-44), the global FCC lattice of the system box L;
+ * radius > 0: DropletMaker::Execute (burst.cc:30-64), its sites strictly inside the sphere around L[X]/2. */
+int mdb200_generate_lattice(mdb200_unit *u, double density, double radius, long long *added);
+/* BallAdder::Execute (collision.cc:8-51): FCC ball of radius r around c with momentum (xv, 0, 0). */
+int mdb200_generate_ball(mdb200_unit *u, const double c[3], double r, double xv, double density, long long *added);
+/* Variables::SetInitialVelocity (variables.cc:82-108) via MDUnit::SetInitialVelocity (mdunit.h:49, seed = unit id):
+ * |p| = v0, directions uniform on the sphere, centre-of-mass momentum of the unit removed. */
+int mdb200_generate_initial_velocity(mdb200_unit *u, double v0, int seed);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,8 @@ SYMBOLS = [
     "mdb200_observe_unit", "mdb200_get_pairs", "mdb200_get_impulse", "mdb200_timers", "mdb200_set_profiling",
     "mdb200_synchronize", "mdb200_event_record", "mdb200_event_elapsed_ms", "mdb200_list_stats",
     "mdb200_snapshot_begin", "mdb200_snapshot_wait", "mdb200_change_scale", "mdb200_measure_fp64_peak",
+    "mdb200_clear", "mdb200_generate_benchmark", "mdb200_generate_lattice", "mdb200_generate_ball",
+    "mdb200_generate_initial_velocity",
 ]
 
 
@@ -62,6 +64,11 @@ def lib():
         L.mdb200_destroy.argtypes = [vp]
         L.mdb200_get_rect.argtypes = [vp, dp, dp]
         L.mdb200_upload.argtypes = [vp, vp, vp, vp, C.c_longlong]
+        L.mdb200_clear.argtypes = [vp]
+        L.mdb200_generate_benchmark.argtypes = [vp, C.c_double, llp]
+        L.mdb200_generate_lattice.argtypes = [vp, C.c_double, C.c_double, llp]
+        L.mdb200_generate_ball.argtypes = [vp, dp, C.c_double, C.c_double, C.c_double, llp]
+        L.mdb200_generate_initial_velocity.argtypes = [vp, C.c_double, C.c_int]
         L.mdb200_download.argtypes = [vp, vp, vp, vp, C.c_longlong, llp, llp]
         L.mdb200_get_counts.argtypes = [vp, llp, llp, llp, llp]
         L.mdb200_comm_unique_id.argtypes = [vp]
@@ -161,6 +168,29 @@ class Unit:
         """zero-copy variant: C-contiguous (n,4) float64 arrays (may be pinned)."""
         assert q4.dtype == np.float64 and p4.dtype == np.float64 and q4.shape[1] == 4 and p4.shape[1] == 4
         check(lib().mdb200_upload(self.handle, _ptr(q4), _ptr(p4), _ptr(type_), q4.shape[0]))
+
+    # on-device initial states (include/mdacp_b200.h; generate.cu): each returns the number of particles appended
+    def clear(self):
+        check(lib().mdb200_clear(self.handle))
+
+    def generate_benchmark(self, density=0.7):
+        n = C.c_longlong()
+        check(lib().mdb200_generate_benchmark(self.handle, density, C.byref(n)))
+        return n.value
+
+    def generate_lattice(self, density, radius=0.0):
+        n = C.c_longlong()
+        check(lib().mdb200_generate_lattice(self.handle, density, radius, C.byref(n)))
+        return n.value
+
+    def generate_ball(self, c, r, xv, density):
+        n = C.c_longlong()
+        c3 = (C.c_double * 3)(*[float(x) for x in c])
+        check(lib().mdb200_generate_ball(self.handle, c3, r, xv, density, C.byref(n)))
+        return n.value
+
+    def generate_initial_velocity(self, v0, seed):
+        check(lib().mdb200_generate_initial_velocity(self.handle, v0, int(seed)))
 
     def counts(self):
         a, b, c, d = C.c_longlong(), C.c_longlong(), C.c_longlong(), C.c_longlong()

@@ -629,6 +629,46 @@ static int calculate(Unit **us, int n) {
   return MDB200_OK;
 }
 
+// room for pn locals (+ their ghosts) in the particle store, contents kept: locals with head-room for migration, ghosts
+// from the halo-shell volume ratio
+int reserve_store(Unit *u, long long pn) {
+  long long need_p = std::max<long long>(u->prm.pn_capacity, pn);
+  double ratio = 1.0;
+  for (int d = 0; d < 3; d++) {
+    const double w = u->c.e[d] - u->c.s[d];
+    ratio *= (w + 2.0 * u->c.SL) / w;
+  }
+  long long need_t = std::max<long long>(u->prm.tn_capacity, (long long)(need_p * std::min(ratio, 27.0) * 1.05) + 1024);
+  // arrivals of a migration are appended past the ghosts before the cell sort compacts them (cells.cu:
+  // migrate_unpack), so the per-local arrays must reach past tn as well -- matters for small boxes, where the
+  // ghost shell is as large as the box; sized here so that no rebuild re-allocates
+  need_p = std::max<long long>(need_p, need_t - need_p / 4);
+  // test hook (tests/test_gpu_multiprocess.py): start from the bare minimum so that the rebuilds have to grow the
+  // position buffers -- the path that re-exports the peer-to-peer windows and parks replaced allocations
+  static const bool small_cap = getenv("MDB200_DEBUG_SMALL_CAPACITY") != nullptr;
+  if (small_cap) { need_p = pn + 64; need_t = pn + 64; }
+  return ensure_capacity(u, need_p, need_t);
+}
+
+// the store now holds pn particles in reference order (slot = reference index), no ghosts, no pair list
+// (pairlist.h:25: the next step rebuilds first)
+int store_replaced(Unit *u, long long pn) {
+  u->pn = pn;
+  u->tn = pn;
+  u->scratch_tail = pn;
+  u->list_initialized = false;
+  u->ghost_composed = false;
+  u->vmax_ready = false;
+  u->predrifted = 0;
+  u->inner_valid = false;
+  u->max_row = 0;
+  u->max_row_exact = 0;
+  u->npairs = 0;
+  u->list_entries = 0;
+  for (int d = 0; d < 6; d++) { u->n_border[d] = 0; u->recv_cnt[d] = 0; u->recv_off[d] = pn; }
+  return reset_ctrl(u, true);
+}
+
 }  // namespace mdb
 
 using namespace mdb;
@@ -761,23 +801,7 @@ int mdb200_upload(mdb200_unit *h, const double (*q)[4], const double (*p)[4], co
   if (pn > 2000000000LL) { set_error("pn exceeds 32-bit index range"); return MDB200_ECAPACITY; }
   Unit *u = &h->u;
   DeviceGuard g(u->device);
-  // capacity: locals with head-room for migration, ghosts from the halo-shell volume ratio
-  long long need_p = std::max<long long>(u->prm.pn_capacity, pn);
-  double ratio = 1.0;
-  for (int d = 0; d < 3; d++) {
-    const double w = u->c.e[d] - u->c.s[d];
-    ratio *= (w + 2.0 * u->c.SL) / w;
-  }
-  long long need_t = std::max<long long>(u->prm.tn_capacity, (long long)(need_p * std::min(ratio, 27.0) * 1.05) + 1024);
-  // arrivals of a migration are appended past the ghosts before the cell sort compacts them (cells.cu:
-  // migrate_unpack), so the per-local arrays must reach past tn as well -- matters for small boxes, where the
-  // ghost shell is as large as the box; sized here so that no rebuild re-allocates
-  need_p = std::max<long long>(need_p, need_t - need_p / 4);
-  // test hook (tests/test_gpu_multiprocess.py): start from the bare minimum so that the rebuilds have to grow the
-  // position buffers -- the path that re-exports the peer-to-peer windows and parks replaced allocations
-  static const bool small_cap = getenv("MDB200_DEBUG_SMALL_CAPACITY") != nullptr;
-  if (small_cap) { need_p = pn + 64; need_t = pn + 64; }
-  MDB_TRY(ensure_capacity(u, need_p, need_t));
+  MDB_TRY(reserve_store(u, pn));
   if (pn > 0) {
     // stage through the alt buffers (device-side repack keeps lane 3 == 0)
     MDB_CUDA(cudaMemcpyAsync(u->q_alt.ptr, q, sizeof(double) * 4 * (size_t)pn, cudaMemcpyHostToDevice, u->stream));
@@ -793,22 +817,57 @@ int mdb200_upload(mdb200_unit *h, const double (*q)[4], const double (*p)[4], co
     u->launches += 3;
     MDB_CUDA(cudaGetLastError());
   }
-  u->pn = pn;
-  u->tn = pn;
-  u->scratch_tail = pn;
-  u->list_initialized = false;
-  u->ghost_composed = false;
-  u->vmax_ready = false;
-  u->predrifted = 0;
-  u->inner_valid = false;
-  u->max_row = 0;
-  u->max_row_exact = 0;
-  u->npairs = 0;
-  u->list_entries = 0;
-  for (int d = 0; d < 6; d++) { u->n_border[d] = 0; u->recv_cnt[d] = 0; u->recv_off[d] = pn; }
-  MDB_TRY(reset_ctrl(u, true));
+  MDB_TRY(store_replaced(u, pn));
   MDB_CUDA(cudaStreamSynchronize(u->stream));
   return MDB200_OK;
+}
+
+// On-device initial states (generate.cu).  The makers append to the particle store like MDUnit::AddParticle; a store
+// that has been stepped (slot order != reference order) must be cleared first.
+static int gen_guard(mdb200_unit *h) {
+  if (!h) { set_error("null unit"); return MDB200_EINVAL; }
+  if (h->u.list_initialized) {
+    set_error("the generators append to a freshly uploaded / generated store: call mdb200_clear first");
+    return MDB200_EINVAL;
+  }
+  return MDB200_OK;
+}
+int mdb200_clear(mdb200_unit *h) {
+  if (!h) return MDB200_EINVAL;
+  DeviceGuard g(h->u.device);
+  return store_replaced(&h->u, 0);
+}
+int mdb200_generate_benchmark(mdb200_unit *h, double density, long long *added) {
+  MDB_TRY(gen_guard(h));
+  if (!(density > 0.0)) { set_error("density must be positive"); return MDB200_EINVAL; }
+  DeviceGuard g(h->u.device);
+  long long n = 0;
+  MDB_TRY(generate_benchmark(&h->u, density, &n));
+  if (added) *added = n;
+  return MDB200_OK;
+}
+int mdb200_generate_lattice(mdb200_unit *h, double density, double radius, long long *added) {
+  MDB_TRY(gen_guard(h));
+  if (!(density > 0.0)) { set_error("density must be positive"); return MDB200_EINVAL; }
+  DeviceGuard g(h->u.device);
+  long long n = 0;
+  MDB_TRY(generate_lattice(&h->u, density, radius, &n));
+  if (added) *added = n;
+  return MDB200_OK;
+}
+int mdb200_generate_ball(mdb200_unit *h, const double c[3], double r, double xv, double density, long long *added) {
+  MDB_TRY(gen_guard(h));
+  if (!c || !(density > 0.0) || !(r > 0.0)) { set_error("bad ball arguments"); return MDB200_EINVAL; }
+  DeviceGuard g(h->u.device);
+  long long n = 0;
+  MDB_TRY(generate_ball(&h->u, c, r, xv, density, &n));
+  if (added) *added = n;
+  return MDB200_OK;
+}
+int mdb200_generate_initial_velocity(mdb200_unit *h, double v0, int seed) {
+  MDB_TRY(gen_guard(h));
+  DeviceGuard g(h->u.device);
+  return generate_initial_velocity(&h->u, v0, seed);
 }
 
 int mdb200_download(mdb200_unit *h, double (*q)[4], double (*p)[4], int *type, long long cap_rows, long long *pn,

@@ -268,6 +268,14 @@ int exclusive_scan_i32_to_i64(const int *in, long long *out, long long n, long l
 
 // cells.cu
 int ensure_capacity(Unit *u, long long need_p, long long need_t);
+// api.cu: room for pn locals in the particle store (contents kept) / bookkeeping after the store was replaced
+int reserve_store(Unit *u, long long pn);
+int store_replaced(Unit *u, long long pn);
+// generate.cu: on-device initial states (confmaker.cc, collision.cc, burst.cc, variables.cc:82-108)
+int generate_benchmark(Unit *u, double density, long long *added);
+int generate_lattice(Unit *u, double density, double radius, long long *added);
+int generate_ball(Unit *u, const double c[3], double r, double xv, double density, long long *added);
+int generate_initial_velocity(Unit *u, double v0, int seed);
 int rebuild_begin_order(Unit *u);                                        // ord[r] = slot_of_ref[r]
 int migrate_flag_and_count(Unit *u, int dir, long long *n_leave);        // sync
 int migrate_compact_pack(Unit *u, int dir, long long n_leave);           // keepers compacted, leavers packed
