@@ -100,7 +100,8 @@ k_tile_search(TileGrid g, Consts c, const double4 *__restrict__ q, const int *__
   float4 *sf = reinterpret_cast<float4 *>(smem + tile_shared_offset() + 128);
   int *row_n = reinterpret_cast<int *>(sf + cap + 1);
   unsigned short *stg = reinterpret_cast<unsigned short *>(row_n + ((maxint + 8 + 7) & ~7));
-  const int tile = blockIdx.x;
+  // a count pass may visit only every cap_chunks-th tile (the sample that sizes the first one-pass build)
+  const int tile = (PASS == 0 && cap_chunks > 1) ? (int)blockIdx.x * cap_chunks : (int)blockIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   tile_setup(ts, tile, g, c, cell_start, gcell_start);
   if (threadIdx.x == 0) ss.maxrel_bits = 0u;
@@ -457,9 +458,29 @@ int build_pair_list(Unit *u) {
                            u->row_count.ptr, u->fw_len.ptr, u->scan.ptr, u->fw_sent.ptr, u->fw_off.ptr, u->list.ptr, u->tile_cap,   \
                            u->tile_maxint, CAPCH, u->ctrl
   bool built = false;
-  // ---- one pass with row blocks of fixed capacity, sized from the longest row of the previous build (every rebuild
-  //      but the first): the distance tests run once
   static const bool no_onepass = getenv("MDB200_NO_ONEPASS") != nullptr;
+  // ---- first build of a store: no previous longest row to size the row blocks of a one-pass build with.  The count
+  //      pass over every 8th tile gives one (a few entries short of the true maximum at worst: the capacity below adds
+  //      12 % + 8, and a row that outgrows it all the same sends the build through the two passes).  Not worth it for
+  //      small units (MDB200_SAMPLE_TILES = smallest tile count it is done for; tests force it with 1).
+  {
+    const char *e = getenv("MDB200_SAMPLE_TILES");
+    const int min_tiles = e ? atoi(e) : 1024;
+    const int stride = 8;
+    if (u->max_row_exact == 0 && !no_onepass && min_tiles > 0 && u->ntiles >= min_tiles) {
+      k_tile_search<0><<<(u->ntiles + stride - 1) / stride, TPB, sm1, u->stream>>>(SEARCH_ARGS(stride));
+      u->launches++;
+      MDB_CUDA(cudaGetLastError());
+      MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->max_row, &u->ctrl->max_row, sizeof(int), cudaMemcpyDeviceToHost, u->stream));
+      MDB_CUDA(cudaMemsetAsync(&u->ctrl->npairs, 0, sizeof(unsigned long long), u->stream));
+      MDB_CUDA(cudaMemsetAsync(&u->ctrl->max_row, 0, sizeof(int), u->stream));
+      MDB_CUDA(cudaStreamSynchronize(u->stream));
+      u->max_row_exact = u->ctrl_host->max_row;
+      if (getenv("MDB200_DEBUG")) fprintf(stderr, "[mdb200] first build: longest row of the sampled tiles %d\n", u->max_row_exact);
+    }
+  }
+  // ---- one pass with row blocks of fixed capacity, sized from the longest row of the previous build (or of the sample
+  //      above): the distance tests run once
   if (u->max_row_exact > 0 && !no_onepass) {
     const int cap_steps = ((u->max_row_exact + u->max_row_exact / 8 + 8 + kG - 1) / kG + 1) & ~1;  // + 12 % + 8 entries
     const int cap_chunks = (cap_steps + 3) >> 2;
@@ -467,7 +488,8 @@ int build_pair_list(Unit *u) {
       const size_t need = (size_t)nfw * cap_chunks * 32 + 8192;
       if (need > u->list.cap) {
         if (getenv("MDB200_DEBUG")) fprintf(stderr, "[mdb200] list grows: %zu words > capacity %zu\n", need, u->list.cap);
-        MDB_TRY(u->list.ensure(need + need / 10));
+        // a first allocation gets the head-room of the two-pass build below (rows of a lattice grow as it thermalises)
+        MDB_TRY(u->list.ensure(u->list.cap == 0 ? need + need * 6 / 10 : need + need / 10));
       }
       MDB_TRY(u->list_in.ensure(u->list.cap));
       MDB_CUDA(cudaMemsetAsync(&u->ctrl->scratch[6], 0, sizeof(int), u->stream));
@@ -483,7 +505,7 @@ int build_pair_list(Unit *u) {
         u->max_row_exact = u->max_row;
         u->list_entries = (long long)nfw * cap_chunks * 128;
       } else {
-        if (getenv("MDB200_DEBUG")) fprintf(stderr, "[mdb200] one-pass list build: a row outgrew %d chunks; two passes\n", cap_chunks);
+        if (getenv("MDB200_DEBUG")) fprintf(stderr, "[mdb200] one-pass list build: a row of %d entries outgrew %d chunks; two passes\n", u->ctrl_host->max_row, cap_chunks);
         u->max_row_exact = std::max(u->max_row_exact, u->ctrl_host->max_row);
         MDB_CUDA(cudaMemsetAsync(&u->ctrl->npairs, 0, sizeof(unsigned long long), u->stream));
         MDB_CUDA(cudaMemsetAsync(&u->ctrl->max_row, 0, sizeof(int), u->stream));

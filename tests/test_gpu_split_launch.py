@@ -55,3 +55,13 @@ def test_fused_inner_list_derivation(name, fused, monkeypatch):
     rec, cfg, steps, init_build = load_golden(name)
     seed = int(cfg["Seed"]) if cfg.get("DumpInit") == "Langevin" else None
     check_cuda_against_records(rec, steps, init_build, seed, observe_every=25)
+
+
+# The first build of a store has no previous longest row to size a one-pass search with: on large units a count pass over
+# every 8th tile provides one (tile_search.cu).  Forced onto the small fixtures here, where the sample is a handful of
+# tiles: some cases build in one pass from it, others overflow and fall back to the two passes -- same lists either way.
+@pytest.mark.parametrize("name", ["bench1", "bench8", "collision2", "slab2", "bench1_c25"])
+def test_first_build_sized_from_a_tile_sample(name, monkeypatch):
+    monkeypatch.setenv("MDB200_SAMPLE_TILES", "1")
+    rec, cfg, steps, init_build = load_golden(name)
+    check_cuda_against_records(rec, steps, init_build, None, observe_every=25)
