@@ -539,22 +539,25 @@ static int calculate(Unit **us, int n) {
     for (auto *x : tm) delete x;
     MDB_TRY(r);
   }
-  // the inner list for the velocity budget decided above, once the ghosts of this step are in.  Where the whole unit goes
-  // through ONE persistent force launch, that launch derives it on the side (it computes every r2 anyway: the launch walks
-  // the longer outer list once instead of a separate compaction pass); otherwise k_tile_compact does.
+  // the inner list for the velocity budget decided above, once the ghosts of this step are in.  Where the force
+  // launch(es) of this step take the persistent kernel they derive it on the side (they compute every r2 anyway: the
+  // outer list is walked once instead of a separate compaction pass); otherwise k_tile_compact does.
   std::vector<double> fused(n, 0.0);
   if (derive) {
-    const bool fusable_step = !(ct && !langevin) && !(langevin && no_predrift) && !overlap && !split_test;
+    const bool fusable_step = !(ct && !langevin) && !(langevin && no_predrift);
+    const bool split = overlap || (split_test && !ct);
     for (int i = 0; i < n; i++) {
       Unit *u = us[i];
       DeviceGuard g(u->device);
-      if (overlap) MDB_CUDA(cudaStreamWaitEvent(u->stream, u->ev_ghost, 0));  // the derivation reads the ghosts
       derive_timer_begin(u);
       if (fusable_step && keep_len < u->c.SL) {
         MDB_TRY(ensure_rainbow(u));
-        if (force_can_derive(u, keep_len)) fused[i] = keep_len;
+        if (force_can_derive(u, keep_len, split)) fused[i] = keep_len;
       }
-      if (fused[i] == 0.0) MDB_TRY(derive_inner(u, keep_len));
+      if (fused[i] == 0.0) {
+        if (overlap) MDB_CUDA(cudaStreamWaitEvent(u->stream, u->ev_ghost, 0));  // the derivation reads the ghosts
+        MDB_TRY(derive_inner(u, keep_len));
+      }
       derive_timer_end(u);
     }
   }
@@ -601,9 +604,9 @@ static int calculate(Unit **us, int n) {
     Unit *u = us[0];
     DeviceGuard g(u->device);
     force_timer_begin(u);
-    MDB_TRY(force_kick_drift(u, predrift, 1));
+    MDB_TRY(force_kick_drift(u, predrift, 1, fused[0]));
     MDB_CUDA(cudaStreamWaitEvent(u->stream, u->ev_ghost, 0));
-    MDB_TRY(force_kick_drift(u, predrift, 2));
+    MDB_TRY(force_kick_drift(u, predrift, 2, fused[0]));
     force_timer_end(u);
     u->predrifted = predrift ? 1 : 0;
   } else {
@@ -615,8 +618,8 @@ static int calculate(Unit **us, int n) {
         PhaseTimer t(us[i], PH_FORCE);
         force_timer_begin(us[i]);
         if (split_test) {  // test hook: the interior / boundary launches of the overlapped path, back to back
-          MDB_TRY(force_kick_drift(us[i], predrift, 1));
-          MDB_TRY(force_kick_drift(us[i], predrift, 2));
+          MDB_TRY(force_kick_drift(us[i], predrift, 1, fused[i]));
+          MDB_TRY(force_kick_drift(us[i], predrift, 2, fused[i]));
         } else {
           MDB_TRY(force_kick_drift(us[i], predrift, 0, fused[i]));
         }

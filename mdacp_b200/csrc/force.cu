@@ -953,22 +953,29 @@ static bool force_persistent(const Unit *u, int ntl, int *sms_out, size_t *psm_o
   return persist;
 }
 
-// A force launch that also derives the inner list for keep_len (k_tile_force_p<.., DERIVE>): possible where the whole
-// unit goes through one persistent launch and the outer list is already in rainbow order (MDB200_FUSED_DERIVE=0: never).
-bool force_can_derive(const Unit *u, double keep_len) {
+// A force launch that also derives the inner list for keep_len (k_tile_force_p<.., DERIVE>): possible where every launch
+// of the step -- the whole unit, or its interior and its boundary tiles (split) -- takes the persistent kernel and the
+// outer list is already in rainbow order (MDB200_FUSED_DERIVE=0: never).
+bool force_can_derive(const Unit *u, double keep_len, bool split) {
   const char *env = getenv("MDB200_FUSED_DERIVE");  // read at every call so that tests can switch it
   const bool off = env && atoi(env) == 0;
   if (off || u->pn == 0 || u->ntiles == 0 || !u->outer_rainbow || keep_len >= u->c.SL) return false;
-  return force_persistent(u, u->ntiles, nullptr, nullptr);
+  if (!split) return force_persistent(u, u->ntiles, nullptr, nullptr);
+  const int n_in = u->n_interior_tiles, n_bd = u->ntiles - u->n_interior_tiles;
+  // (an empty part launches nothing)
+  return (n_in == 0 || force_persistent(u, n_in, nullptr, nullptr)) && (n_bd == 0 || force_persistent(u, n_bd, nullptr, nullptr));
 }
 
 // part: 0 = every tile, 1 = interior tiles only, 2 = boundary tiles only
-// derive_keep > 0 (part 0, drifting modes, persistent kernel only: force_can_derive): walk the outer list and write the
-// inner list for that radius on the side
+// derive_keep > 0 (drifting modes, persistent kernel only: force_can_derive): walk the outer list and write the inner
+// list for that radius on the side; with split launches BOTH parts must be given the same derive_keep
 static int force_launch(Unit *u, int mode, double *fout, int part = 0, double derive_keep = 0.0) {
   const int ntl = (part == 0) ? u->ntiles : (part == 1 ? u->n_interior_tiles : u->ntiles - u->n_interior_tiles);
-  if (ntl <= 0) return MDB200_OK;
   const bool deriving = derive_keep > 0.0;
+  if (ntl <= 0) {
+    if (deriving && part != 1) { u->inner_valid = true; u->inner_is_outer = false; u->inner_keep = derive_keep; }
+    return MDB200_OK;
+  }
   if (!deriving && !u->inner_valid) MDB_TRY(derive_inner(u, u->c.SL));  // no budgeted inner list: a full one
   ForceConsts fc = make_fc(u);
   fc.keep2 = derive_keep * derive_keep;
@@ -981,7 +988,7 @@ static int force_launch(Unit *u, int mode, double *fout, int part = 0, double de
   const bool persist = force_persistent(u, ntl, &sms, &psm);
   const size_t sm = tile_smem_bytes_f64(u->tile_cap);
   if (deriving) {
-    if (!persist || part != 0 || mode < FORCE_KICK_DRIFT) { set_error("deriving force launch not available here"); return MDB200_EINVAL; }
+    if (!persist || mode < FORCE_KICK_DRIFT) { set_error("deriving force launch not available here"); return MDB200_EINVAL; }
     MDB_TRY(u->list_in.ensure(u->list.cap));
   }
 #define PLAUNCH(M, E, D)                                                                                                    \
@@ -1021,7 +1028,7 @@ static int force_launch(Unit *u, int mode, double *fout, int part = 0, double de
 #undef PLAUNCH
   u->launches++;
   MDB_CUDA(cudaGetLastError());
-  if (deriving) {
+  if (deriving && part != 1) {  // (after the interior part the boundary rows are still to come)
     u->inner_valid = true;
     u->inner_is_outer = false;
     u->inner_keep = derive_keep;

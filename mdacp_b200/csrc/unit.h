@@ -312,7 +312,7 @@ int force_kick(Unit *u);                                                 // deri
 // part: 0 every tile, 1 interior tiles, 2 boundary tiles.  Walks the inner list (derived on demand).
 int force_kick_drift(Unit *u, bool predrift, int part, double derive_keep = 0.0);
 int ensure_rainbow(Unit *u);                          // outer list into rainbow order (once per rebuild)
-bool force_can_derive(const Unit *u, double keep_len);  // a whole-unit force launch can write the inner list on the side
+bool force_can_derive(const Unit *u, double keep_len, bool split);  // the step's force launch(es) can write the inner list on the side
 int force_kick_langevin(Unit *u, double derive_keep = 0.0);                   // fused Langevin step (+ next first half drift)
 int force_impulse(Unit *u, double *f3_host, long long cap_rows);         // sync
 

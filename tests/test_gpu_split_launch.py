@@ -46,11 +46,14 @@ def test_outer_list_only_matches_reference_golden(name, monkeypatch):
 # Where the whole unit goes through one persistent force launch, that launch also derives the inner list (force.cu
 # DERIVE); MDB200_FUSED_DERIVE=0 keeps the separate compaction pass.  Both must meet the same parity, also with rare
 # observations (the pre-drifted state runs through the deriving launches).
+@pytest.mark.parametrize("split", [False, True])
 @pytest.mark.parametrize("fused", ["1", "0"])
 @pytest.mark.parametrize("name", ["bench1", "bench8", "collision2", "langevinT0"])
-def test_fused_inner_list_derivation(name, fused, monkeypatch):
+def test_fused_inner_list_derivation(name, fused, split, monkeypatch):
     monkeypatch.setenv("MDB200_FORCE_PERSIST", "1")
     monkeypatch.setenv("MDB200_FUSED_DERIVE", fused)
+    if split:  # interior and boundary tiles in two launches (the overlapped multi-process step): both derive
+        monkeypatch.setenv("MDB200_FORCE_SPLIT", "1")
     monkeypatch.setenv("MDB200_TILE", "2,2,2")
     rec, cfg, steps, init_build = load_golden(name)
     seed = int(cfg["Seed"]) if cfg.get("DumpInit") == "Langevin" else None
