@@ -776,7 +776,7 @@ int mdb200_destroy(mdb200_unit *h) {
   u->ghost_shift.release();
   u->send_buf.release(); u->mig_send_q.release(); u->mig_send_p.release(); u->mig_recv_q.release();
   u->mig_recv_p.release(); u->mig_send_t.release(); u->mig_recv_t.release();
-  u->row_count.release(); u->list_in.release(); u->fw_len_in.release(); u->tile_fw0.release(); u->tile_flag.release(); u->tile_order.release();
+  u->row_count.release(); u->list_in.release(); u->fw_len_in.release(); u->tile_fw0.release(); u->tile_flag.release(); u->tile_order.release(); u->tile_tmp.release();
   if (u->cstream) { cudaStreamDestroy(u->cstream); cudaEventDestroy(u->ev_drift); cudaEventDestroy(u->ev_ghost); }
   u->fw_len.release(); u->fw_off.release(); u->fw_sent.release(); u->list.release();
   u->disp.release(); u->cand.release(); u->partial.release();

@@ -863,7 +863,7 @@ static TileArgs make_ta(const Unit *u, int part) {
   ta.gcell_start = u->gcell_start.ptr;
   ta.gitems = u->gcell_items.ptr;
   ta.tile_fw0 = u->tile_fw0.ptr;
-  ta.tile_order = part ? u->tile_order.ptr : nullptr;
+  ta.tile_order = u->tile_order.ptr;  // active tiles only (tile_search.cu)
   ta.tile_base = (part == 2) ? u->n_interior_tiles : 0;
   ta.cap = u->tile_cap;
   return ta;
@@ -926,7 +926,7 @@ int derive_inner(Unit *u, double keep_len) {
     MDB_TRY(u->list_in.ensure(u->list.cap));
     const size_t sm = tile_smem_bytes_f64(u->tile_cap);
     MDB_TRY(set_smem(k_tile_compact<0>, sm));
-    k_tile_compact<0><<<u->ntiles, FORCE_TPB, sm, u->stream>>>(make_ta(u, 0), u->c, u->q.ptr, u->list.ptr, u->fw_off.ptr, u->fw_len.ptr,
+    k_tile_compact<0><<<u->n_active_tiles, FORCE_TPB, sm, u->stream>>>(make_ta(u, 0), u->c, u->q.ptr, u->list.ptr, u->fw_off.ptr, u->fw_len.ptr,
                                                                u->list_in.ptr, u->fw_len_in.ptr, keep_len * keep_len);
     u->launches++;
     MDB_CUDA(cudaGetLastError());
@@ -960,8 +960,8 @@ bool force_can_derive(const Unit *u, double keep_len, bool split) {
   const char *env = getenv("MDB200_FUSED_DERIVE");  // read at every call so that tests can switch it
   const bool off = env && atoi(env) == 0;
   if (off || u->pn == 0 || u->ntiles == 0 || !u->outer_rainbow || keep_len >= u->c.SL) return false;
-  if (!split) return force_persistent(u, u->ntiles, nullptr, nullptr);
-  const int n_in = u->n_interior_tiles, n_bd = u->ntiles - u->n_interior_tiles;
+  if (!split) return force_persistent(u, u->n_active_tiles, nullptr, nullptr);
+  const int n_in = u->n_interior_tiles, n_bd = u->n_active_tiles - u->n_interior_tiles;
   // (an empty part launches nothing)
   return (n_in == 0 || force_persistent(u, n_in, nullptr, nullptr)) && (n_bd == 0 || force_persistent(u, n_bd, nullptr, nullptr));
 }
@@ -970,7 +970,7 @@ bool force_can_derive(const Unit *u, double keep_len, bool split) {
 // derive_keep > 0 (drifting modes, persistent kernel only: force_can_derive): walk the outer list and write the inner
 // list for that radius on the side; with split launches BOTH parts must be given the same derive_keep
 static int force_launch(Unit *u, int mode, double *fout, int part = 0, double derive_keep = 0.0) {
-  const int ntl = (part == 0) ? u->ntiles : (part == 1 ? u->n_interior_tiles : u->ntiles - u->n_interior_tiles);
+  const int ntl = (part == 0) ? u->n_active_tiles : (part == 1 ? u->n_interior_tiles : u->n_active_tiles - u->n_interior_tiles);
   const bool deriving = derive_keep > 0.0;
   if (ntl <= 0) {
     if (deriving && part != 1) { u->inner_valid = true; u->inner_is_outer = false; u->inner_keep = derive_keep; }

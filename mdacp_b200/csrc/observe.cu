@@ -62,7 +62,8 @@ __device__ __forceinline__ void pair_uw(double dx, double dy, double dz, double 
 // kG-th entry of the row (unit.h).
 __global__ void __launch_bounds__(TPB, 2)
 k_observe(TileGrid g, Consts c, const int *__restrict__ cell_start, const int *__restrict__ gcell_start,
-          const int *__restrict__ gitems, const int *__restrict__ tile_fw0, const double4 *__restrict__ q,
+          const int *__restrict__ gitems, const int *__restrict__ tile_order, const int *__restrict__ tile_fw0,
+          const double4 *__restrict__ q,
           const double4 *__restrict__ p, const uint2 *__restrict__ list, const long long *__restrict__ fw_off,
           const int *__restrict__ fw_len, int pn, int have_list, double *__restrict__ partial) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -79,7 +80,7 @@ k_observe(TileGrid g, Consts c, const int *__restrict__ cell_start, const int *_
     k += 0.5 * pp.w * pp.w;
   }
   if (have_list) {
-    const int tile = blockIdx.x;
+    const int tile = tile_order[blockIdx.x];  // tiles with interior locals only (tile_search.cu)
     tile_setup(ts, tile, g, c, cell_start, gcell_start);
     tile_stage_tma(ts, q, gitems, sq);
     tile_stage_wait(ts);
@@ -138,13 +139,13 @@ static int observe_impl(Unit *u, double out[4], bool with_list) {
   out[3] = (double)u->pn;
   if (u->pn == 0) return MDB200_OK;
   const bool walk = with_list && u->list_initialized && u->ntiles > 0;
-  long long nb = walk ? u->ntiles : (u->pn + TPB - 1) / TPB;
+  long long nb = walk ? std::max(u->n_active_tiles, 1) : (u->pn + TPB - 1) / TPB;
   if (!walk && nb > MAXBLK) nb = MAXBLK;
   MDB_TRY(u->partial.ensure((size_t)3 * nb + 8));
   const size_t sm = walk ? tile_smem_bytes_f64(u->tile_cap) : tile_shared_offset();
   MDB_CUDA(cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes_f64(walk ? u->tile_cap : 0)));
   k_observe<<<(unsigned)nb, TPB, sm, u->stream>>>(tile_grid(u), u->c, u->cell_start.ptr, u->gcell_start.ptr, u->gcell_items.ptr,
-                                                  u->tile_fw0.ptr, u->q.ptr, u->p.ptr, u->list.ptr, u->fw_off.ptr, u->fw_len.ptr,
+                                                  u->tile_order.ptr, u->tile_fw0.ptr, u->q.ptr, u->p.ptr, u->list.ptr, u->fw_off.ptr, u->fw_len.ptr,
                                                   (int)u->pn, walk ? 1 : 0, u->partial.ptr);
   k_observe_final<<<1, TPB, 0, u->stream>>>(u->partial.ptr, (int)nb, u->ctrl);
   u->launches += 2;

@@ -58,13 +58,22 @@ __global__ void k_tile_census(TileGrid g, Consts c, const int *__restrict__ cell
   atomicMax(&ctrl->scratch[3], n_int);
 }
 
-__global__ void k_tile_order(const int *__restrict__ flag, const int *__restrict__ scanv, int *__restrict__ order, int nt,
-                             int n_interior) {
+// class of a tile: 0 = has rows and stages no ghost (interior), 1 = has rows and stages ghosts (boundary); a tile without
+// interior locals (vacuum) is in neither class and appears in no launch
+__global__ void k_tile_class(const int *__restrict__ tile_nfw, const int *__restrict__ flag, int *__restrict__ cls_in,
+                             int *__restrict__ cls_bd, int nt) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nt) return;
-  const int nb = scanv[t];  // boundary tiles before t
-  if (flag[t]) order[n_interior + nb] = t;
-  else order[t - nb] = t;
+  const bool rows = tile_nfw[t] > 0;
+  cls_in[t] = (rows && !flag[t]) ? 1 : 0;
+  cls_bd[t] = (rows && flag[t]) ? 1 : 0;
+}
+__global__ void k_tile_order(const int *__restrict__ cls_in, const int *__restrict__ cls_bd, const int *__restrict__ scan_in,
+                             const int *__restrict__ scan_bd, int *__restrict__ order, int nt, int n_interior) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nt) return;
+  if (cls_in[t]) order[scan_in[t]] = t;
+  else if (cls_bd[t]) order[n_interior + scan_bd[t]] = t;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -89,7 +98,8 @@ struct SearchShared {
 template <int PASS>
 __global__ void __launch_bounds__(TPB, 3)
 k_tile_search(TileGrid g, Consts c, const double4 *__restrict__ q, const int *__restrict__ cell_start,
-              const int *__restrict__ gcell_start, const int *__restrict__ gitems, const int *__restrict__ tile_fw0,
+              const int *__restrict__ gcell_start, const int *__restrict__ gitems, const int *__restrict__ tile_order,
+              const int *__restrict__ tile_fw0,
               int *__restrict__ row_count, int *__restrict__ fw_len, int *__restrict__ fw_store, int *__restrict__ fw_sent,
               long long *__restrict__ fw_off, uint2 *__restrict__ list, int cap, int maxint, int cap_chunks, Ctrl *ctrl) {
   constexpr bool FILL = PASS != 0;
@@ -101,7 +111,7 @@ k_tile_search(TileGrid g, Consts c, const double4 *__restrict__ q, const int *__
   int *row_n = reinterpret_cast<int *>(sf + cap + 1);
   unsigned short *stg = reinterpret_cast<unsigned short *>(row_n + ((maxint + 8 + 7) & ~7));
   // a count pass may visit only every cap_chunks-th tile (the sample that sizes the first one-pass build)
-  const int tile = (PASS == 0 && cap_chunks > 1) ? (int)blockIdx.x * cap_chunks : (int)blockIdx.x;
+  const int tile = tile_order[(PASS == 0 && cap_chunks > 1) ? (int)blockIdx.x * cap_chunks : (int)blockIdx.x];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   tile_setup(ts, tile, g, c, cell_start, gcell_start);
   if (threadIdx.x == 0) ss.maxrel_bits = 0u;
@@ -384,6 +394,8 @@ int build_pair_list(Unit *u) {
   u->npairs = 0;
   u->nfw = 0;
   u->ntiles = 0;
+  u->n_active_tiles = 0;
+  u->n_interior_tiles = 0;
   u->inner_valid = false;
   u->outer_rainbow = false;
   u->inner_is_outer = false;
@@ -432,16 +444,26 @@ int build_pair_list(Unit *u) {
   if (getenv("MDB200_DEBUG"))
     fprintf(stderr, "[mdb200] tiles %d x %d x %d of %d x %d x %d cells, largest stages %d records (%d interior)\n", u->tnum[0],
             u->tnum[1], u->tnum[2], u->tdim[0], u->tdim[1], u->tdim[2], u->tile_cap, u->tile_maxint);
-  // ---- force-warps per tile -> first force-warp of every tile; interior tiles first
+  // ---- force-warps per tile -> first force-warp of every tile; the order of the launches: interior tiles with rows
+  //      first, then boundary tiles with rows; tiles without interior locals (vacuum) are left out
   MDB_TRY(exclusive_scan_i32(u->flags.ptr, u->tile_fw0.ptr, u->ntiles, u->scan_ws.ptr, u->stream, &u->launches));
-  MDB_TRY(exclusive_scan_i32(u->tile_flag.ptr, u->scan.ptr, u->ntiles, u->scan_ws.ptr, u->stream, &u->launches));
+  MDB_TRY(u->tile_tmp.ensure(3 * ((size_t)u->ntiles + 2)));
+  int *cls_in = u->tile_tmp.ptr, *cls_bd = cls_in + u->ntiles + 2, *scan_bd = cls_bd + u->ntiles + 2;
+  k_tile_class<<<nblk(u->ntiles), TPB, 0, u->stream>>>(u->flags.ptr, u->tile_flag.ptr, cls_in, cls_bd, u->ntiles);
+  u->launches++;
+  MDB_TRY(exclusive_scan_i32(cls_in, u->scan.ptr, u->ntiles, u->scan_ws.ptr, u->stream, &u->launches));
+  MDB_TRY(exclusive_scan_i32(cls_bd, scan_bd, u->ntiles, u->scan_ws.ptr, u->stream, &u->launches));
   MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->scratch[4], u->tile_fw0.ptr + u->ntiles, sizeof(int), cudaMemcpyDeviceToHost, u->stream));
   MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->scratch[5], u->scan.ptr + u->ntiles, sizeof(int), cudaMemcpyDeviceToHost, u->stream));
+  MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->scratch[6], scan_bd + u->ntiles, sizeof(int), cudaMemcpyDeviceToHost, u->stream));
   MDB_CUDA(cudaStreamSynchronize(u->stream));
   u->nfw = u->ctrl_host->scratch[4];
-  u->n_interior_tiles = u->ntiles - u->ctrl_host->scratch[5];
-  k_tile_order<<<nblk(u->ntiles), TPB, 0, u->stream>>>(u->tile_flag.ptr, u->scan.ptr, u->tile_order.ptr, u->ntiles, u->n_interior_tiles);
+  u->n_interior_tiles = u->ctrl_host->scratch[5];
+  u->n_active_tiles = u->n_interior_tiles + u->ctrl_host->scratch[6];
+  k_tile_order<<<nblk(u->ntiles), TPB, 0, u->stream>>>(cls_in, cls_bd, u->scan.ptr, scan_bd, u->tile_order.ptr, u->ntiles, u->n_interior_tiles);
   u->launches++;
+  if (getenv("MDB200_DEBUG") && u->n_active_tiles != u->ntiles)
+    fprintf(stderr, "[mdb200] %d of %d tiles hold particles of their own\n", u->n_active_tiles, u->ntiles);
   const long long nfw = u->nfw;
   MDB_TRY(u->row_count.ensure((size_t)pn + 32));
   MDB_TRY(u->fw_len.ensure((size_t)nfw + 2));
@@ -454,7 +476,8 @@ int build_pair_list(Unit *u) {
   MDB_CUDA(cudaFuncSetAttribute(k_tile_search<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
   MDB_CUDA(cudaFuncSetAttribute(k_tile_search<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
   MDB_CUDA(cudaFuncSetAttribute(k_tile_search<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
-#define SEARCH_ARGS(CAPCH) tile_grid(u), u->c, u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr, u->gcell_items.ptr, u->tile_fw0.ptr, \
+#define SEARCH_ARGS(CAPCH) tile_grid(u), u->c, u->q.ptr, u->cell_start.ptr, u->gcell_start.ptr, u->gcell_items.ptr, u->tile_order.ptr, \
+                           u->tile_fw0.ptr,                                                                                         \
                            u->row_count.ptr, u->fw_len.ptr, u->scan.ptr, u->fw_sent.ptr, u->fw_off.ptr, u->list.ptr, u->tile_cap,   \
                            u->tile_maxint, CAPCH, u->ctrl
   bool built = false;
@@ -467,8 +490,8 @@ int build_pair_list(Unit *u) {
     const char *e = getenv("MDB200_SAMPLE_TILES");
     const int min_tiles = e ? atoi(e) : 1024;
     const int stride = 8;
-    if (u->max_row_exact == 0 && !no_onepass && min_tiles > 0 && u->ntiles >= min_tiles) {
-      k_tile_search<0><<<(u->ntiles + stride - 1) / stride, TPB, sm1, u->stream>>>(SEARCH_ARGS(stride));
+    if (u->max_row_exact == 0 && !no_onepass && min_tiles > 0 && u->n_active_tiles >= min_tiles) {
+      k_tile_search<0><<<(u->n_active_tiles + stride - 1) / stride, TPB, sm1, u->stream>>>(SEARCH_ARGS(stride));
       u->launches++;
       MDB_CUDA(cudaGetLastError());
       MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->max_row, &u->ctrl->max_row, sizeof(int), cudaMemcpyDeviceToHost, u->stream));
@@ -493,7 +516,7 @@ int build_pair_list(Unit *u) {
       }
       MDB_TRY(u->list_in.ensure(u->list.cap));
       MDB_CUDA(cudaMemsetAsync(&u->ctrl->scratch[6], 0, sizeof(int), u->stream));
-      k_tile_search<2><<<u->ntiles, TPB, sm2, u->stream>>>(SEARCH_ARGS(cap_chunks));
+      k_tile_search<2><<<u->n_active_tiles, TPB, sm2, u->stream>>>(SEARCH_ARGS(cap_chunks));
       u->launches++;
       MDB_CUDA(cudaGetLastError());
       MDB_CUDA(cudaMemcpyAsync(&u->ctrl_host->scratch[6], &u->ctrl->scratch[6], sizeof(int), cudaMemcpyDeviceToHost, u->stream));
@@ -514,7 +537,7 @@ int build_pair_list(Unit *u) {
   }
   if (!built) {
     // ---- pass 1: row lengths
-    k_tile_search<0><<<u->ntiles, TPB, sm1, u->stream>>>(SEARCH_ARGS(0));
+    k_tile_search<0><<<u->n_active_tiles, TPB, sm1, u->stream>>>(SEARCH_ARGS(0));
     u->launches++;
     MDB_CUDA(cudaGetLastError());
     MDB_TRY(exclusive_scan_i32_to_i64(u->scan.ptr, u->fw_off.ptr, nfw, u->scan_ws64.ptr, u->stream, &u->launches, 1));
@@ -539,7 +562,7 @@ int build_pair_list(Unit *u) {
     }
     MDB_TRY(u->list_in.ensure(u->list.cap));
     // ---- pass 2: rows
-    k_tile_search<1><<<u->ntiles, TPB, sm2, u->stream>>>(SEARCH_ARGS(0));
+    k_tile_search<1><<<u->n_active_tiles, TPB, sm2, u->stream>>>(SEARCH_ARGS(0));
     u->launches++;
     MDB_CUDA(cudaGetLastError());
   }

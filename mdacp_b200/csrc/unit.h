@@ -177,8 +177,11 @@ struct Unit {
   int tile_maxint = 0;            // interior locals of the largest tile
   DevBuf<int> tile_fw0;           // first force-warp of tile t (ntiles + 1 entries)
   DevBuf<int> tile_flag;          // 1 = the tile stages ghosts (boundary tile)
-  DevBuf<int> tile_order;         // interior tiles first, then boundary tiles (overlapped exchange, api.cu)
-  int n_interior_tiles = 0;
+  DevBuf<int> tile_order;         // the tiles every launch goes through: those with interior locals ("active"), the ones
+                                  // that stage no ghost first, then the boundary tiles (overlapped exchange, api.cu)
+  DevBuf<int> tile_tmp;           // rebuild scratch of the ordering
+  int n_interior_tiles = 0;       // active tiles that stage no ghost
+  int n_active_tiles = 0;         // tiles with rows (a droplet in vacuum: a few per cent of ntiles)
   // FULL neighbour lists (every local's row holds all its partners), kG = 4 lanes per local: force-warp w of
   // a tile owns the tile's interior locals with staged index [8 w', 8 w' + 8); entry e of the local in group m
   // is handled by lane 4 m + (e & 3) at step e >> 2.  Storage: 16-bit entries, four steps of a lane in one
