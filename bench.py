@@ -554,7 +554,7 @@ def run_ours(args):
     unit.synchronize()
     barrier()
     te0 = time.time()
-    unit.upload4(qh[:n_now], ph[:n_now])           # H2D inside the timed region
+    unit.upload4_begin(qh[:n_now], ph[:n_now])     # H2D inside the timed region (momenta travel during the first build)
     for i in range(K):
         mdm.Calculate()                            # first call rebuilds the list (pairlist.cc:27-29)
         if i % OBSERVE_LOOP == 0:

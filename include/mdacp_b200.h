@@ -90,6 +90,13 @@ int mdb200_get_rect(mdb200_unit *u, double s[3], double e[3]);
  * uninitialised (pairlist.h:25), so the next mdb200_step rebuilds first, as collision.cc relies on. */
 int mdb200_upload(mdb200_unit *u, const double (*q)[4], const double (*p)[4], const int *type,
                   long long pn);
+/* As mdb200_upload, but returns as soon as the POSITIONS have arrived: the momenta keep travelling (second stream)
+ * while the caller's next mdb200_make_pairlist / mdb200_step builds the pair list, which needs positions only
+ * (mdmanager.cc:262-280 reads q alone until the first kick).  Any other entry waits for them first, so results never
+ * differ from mdb200_upload; what changes is the contract on the host arrays: `p` must stay valid and unmodified until
+ * the next call on this unit has returned.  Worth it for page-locked host arrays only. */
+int mdb200_upload_begin(mdb200_unit *u, const double (*q)[4], const double (*p)[4], const int *type,
+                        long long pn);
 /* Device -> host Variables, in REFERENCE INDEX ORDER: exactly the order the reference's arrays
  * would hold after the same history of migrations (mdunit.cc:78-122).  q receives min(tn, cap_rows)
  * rows (locals, then as many ghosts as fit), p and type receive pn rows.  Any of q/p/type may be

@@ -27,7 +27,7 @@ SYMBOLS = [
     "mdb200_synchronize", "mdb200_event_record", "mdb200_event_elapsed_ms", "mdb200_list_stats",
     "mdb200_snapshot_begin", "mdb200_snapshot_wait", "mdb200_change_scale", "mdb200_measure_fp64_peak",
     "mdb200_clear", "mdb200_generate_benchmark", "mdb200_generate_lattice", "mdb200_generate_ball",
-    "mdb200_generate_initial_velocity",
+    "mdb200_generate_initial_velocity", "mdb200_upload_begin",
 ]
 
 
@@ -64,6 +64,7 @@ def lib():
         L.mdb200_destroy.argtypes = [vp]
         L.mdb200_get_rect.argtypes = [vp, dp, dp]
         L.mdb200_upload.argtypes = [vp, vp, vp, vp, C.c_longlong]
+        L.mdb200_upload_begin.argtypes = [vp, vp, vp, vp, C.c_longlong]
         L.mdb200_clear.argtypes = [vp]
         L.mdb200_generate_benchmark.argtypes = [vp, C.c_double, llp]
         L.mdb200_generate_lattice.argtypes = [vp, C.c_double, C.c_double, llp]
@@ -191,6 +192,13 @@ class Unit:
 
     def generate_initial_velocity(self, v0, seed):
         check(lib().mdb200_generate_initial_velocity(self.handle, v0, int(seed)))
+
+    def upload4_begin(self, q4, p4, type_=None):
+        """mdb200_upload_begin: returns once the positions are on the device; p4 (page-locked) must stay untouched
+        until the next call on this unit has returned."""
+        assert q4.dtype == np.float64 and p4.dtype == np.float64 and q4.shape[1] == 4 and p4.shape[1] == 4
+        self._pending_upload = (q4, p4, type_)   # keep the host arrays alive
+        check(lib().mdb200_upload_begin(self.handle, _ptr(q4), _ptr(p4), _ptr(type_), q4.shape[0]))
 
     def counts(self):
         a, b, c, d = C.c_longlong(), C.c_longlong(), C.c_longlong(), C.c_longlong()

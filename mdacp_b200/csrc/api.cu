@@ -173,8 +173,17 @@ static int stage_barrier(Unit **us, int n) {
   return MDB200_OK;
 }
 
+// momenta queued by mdb200_upload_begin: everything that reads p on the unit's stream comes after their arrival
+static int settle_upload(Unit *u) {
+  if (!u->p_pending) return MDB200_OK;
+  MDB_CUDA(cudaStreamWaitEvent(u->stream, u->ev_p_up, 0));
+  u->p_pending = false;
+  return MDB200_OK;
+}
+
 // Undo the speculative pre-drift (unit.h, force.cu MODE 3): afterwards q holds the end-of-step positions.
-static int materialize(Unit *u) {
+static int materialize(Unit *u, bool settle = true) {
+  if (settle) MDB_TRY(settle_upload(u));  // (the first build after mdb200_upload_begin passes false: it needs no momenta)
   if (!u->predrifted) return MDB200_OK;
   DeviceGuard g(u->device);
   // NVE: last half-step positions + p dt/2, bit-identical to the plain path; Langevin: they are the end-of-step
@@ -250,6 +259,11 @@ static int reset_ctrl(Unit *u, bool keep_zeta) {
   return MDB200_OK;
 }
 
+// late momenta (unit.h): slot s takes the momentum of upload row psrc[s]
+__global__ void k_gather_momenta(const double4 *__restrict__ p_up, const int *__restrict__ psrc, double4 *__restrict__ p, int pn) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < pn) p[s] = p_up[psrc[s]];
+}
 __global__ void k_iota(int *a, int *b, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { a[i] = i; b[i] = i; }
@@ -303,6 +317,28 @@ struct DebugClock {
 
 static int make_pairlist(Unit **us, int n) {
   std::vector<long long> cnt(n);
+  // Momenta still on their way (mdb200_upload_begin).  One unit in one process: the build below needs positions only,
+  // so it carries the upload row of every local through migration and cell sort and the momenta are gathered into slot
+  // order on the upload stream when they are there (MDB200_LATE_P=0: wait for them first, like everybody else).
+  {
+    static const bool no_late = getenv("MDB200_LATE_P") && atoi(getenv("MDB200_LATE_P")) == 0;
+    const bool late = n == 1 && !comm_multi_process() && us[0]->p_pending && !us[0]->list_initialized && !no_late;
+    for (int i = 0; i < n; i++) {
+      DeviceGuard g(us[i]->device);
+      us[i]->late_p = late;
+      if (!late) MDB_TRY(settle_upload(us[i]));
+    }
+  }
+  struct LateScope {   // whatever happens below, nobody is left reading momenta that have not arrived
+    Unit *u;
+    ~LateScope() {
+      if (u->late_p) {
+        cudaStreamSynchronize(u->ustream);
+        u->late_p = false;
+        u->p_pending = false;
+      }
+    }
+  } late_scope{us[0]};
   for (int i = 0; i < n; i++) us[i]->vmax_ready = false;  // migration changes the set of locals
   for (int i = 0; i < n; i++) us[i]->inner_valid = false;  // the inner list is derived from the list being replaced
   DebugClock dbg(us[0]->stream);
@@ -338,6 +374,18 @@ static int make_pairlist(Unit **us, int n) {
     MDB_TRY(wrap_periodic(us[i]));
     // --- MeshList cell sort: locals become cell-ordered; tn := pn (mdmanager.cc:264-268)
     MDB_TRY(cell_sort_locals(us[i]));
+    if (us[i]->late_p) {
+      // p (before the sort's swap: now p_alt) receives the upload rows; slot s wants row psrc[s]
+      Unit *u = us[i];
+      MDB_CUDA(cudaEventRecord(u->ev_perm, u->stream));
+      MDB_CUDA(cudaStreamWaitEvent(u->ustream, u->ev_perm, 0));
+      if (u->pn > 0) {
+        k_gather_momenta<<<(unsigned)((u->pn + 255) / 256), 256, 0, u->ustream>>>(u->p_alt.ptr, u->psrc.ptr, u->p.ptr, (int)u->pn);
+        u->launches++;
+        MDB_CUDA(cudaGetLastError());
+      }
+      MDB_CUDA(cudaEventRecord(u->ev_p_ready, u->ustream));
+    }
   }
   dbg.lap("wrap + cell sort");
   // --- border lists + first ghost exchange (mdmanager.cc:269-275)
@@ -378,6 +426,11 @@ static int make_pairlist(Unit **us, int n) {
     if (rc != MDB200_OK && lerr == MDB200_OK) lerr = rc;
   }
   dbg.lap("ghost bins + snapshot + search");
+  if (us[0]->late_p) {
+    MDB_CUDA(cudaStreamWaitEvent(us[0]->stream, us[0]->ev_p_ready, 0));
+    us[0]->late_p = false;
+    us[0]->p_pending = false;
+  }
   // a rank whose rebuild failed must not leave the others waiting in the next collective
   int gerr = lerr;
   MDB_TRY(comm_allreduce_or(us, n, &gerr));
@@ -486,7 +539,7 @@ static int calculate(Unit **us, int n) {
   const bool langevin = ct && us[0]->prm.heatbath_type != MDB200_HT_NOSEHOOVER;
   static const bool no_predrift = getenv("MDB200_NO_PREDRIFT") != nullptr;
   if (expired || (ct && !langevin) || no_predrift)
-    for (int i = 0; i < n; i++) MDB_TRY(materialize(us[i]));
+    for (int i = 0; i < n; i++) MDB_TRY(materialize(us[i], !expired));
   if (expired) MDB_TRY(make_pairlist(us, n));
   // The force kernel walks the INNER list (force.cu): the entries of the pair list within cutoff + delta when it
   // was derived.  A new one is due when there is none (rebuild, momenta or positions changed outside the step) or
@@ -777,6 +830,12 @@ int mdb200_destroy(mdb200_unit *h) {
   u->send_buf.release(); u->mig_send_q.release(); u->mig_send_p.release(); u->mig_recv_q.release();
   u->mig_recv_p.release(); u->mig_send_t.release(); u->mig_recv_t.release();
   u->row_count.release(); u->list_in.release(); u->fw_len_in.release(); u->tile_fw0.release(); u->tile_flag.release(); u->tile_order.release(); u->tile_tmp.release();
+  if (u->ustream) {
+    cudaStreamSynchronize(u->ustream);
+    cudaStreamDestroy(u->ustream);
+    cudaEventDestroy(u->ev_q_up); cudaEventDestroy(u->ev_p_up); cudaEventDestroy(u->ev_perm); cudaEventDestroy(u->ev_p_ready);
+  }
+  u->psrc.release(); u->psrc_alt.release(); u->mig_send_s.release();
   if (u->cstream) { cudaStreamDestroy(u->cstream); cudaEventDestroy(u->ev_drift); cudaEventDestroy(u->ev_ghost); }
   u->fw_len.release(); u->fw_off.release(); u->fw_sent.release(); u->list.release();
   u->disp.release(); u->cand.release(); u->partial.release();
@@ -799,19 +858,37 @@ int mdb200_get_rect(mdb200_unit *h, double s[3], double e[3]) {
   return MDB200_OK;
 }
 
-int mdb200_upload(mdb200_unit *h, const double (*q)[4], const double (*p)[4], const int *type, long long pn) {
+// async_p: the momenta travel on the upload stream straight into p (no lane to repair: Variables::p has lane 3 = 0)
+// and the call returns once the positions are there (mdb200_upload_begin)
+static int upload_impl(mdb200_unit *h, const double (*q)[4], const double (*p)[4], const int *type, long long pn, bool async_p) {
   if (!h || pn < 0 || (pn > 0 && (!q || !p))) { set_error("bad upload arguments"); return MDB200_EINVAL; }
   if (pn > 2000000000LL) { set_error("pn exceeds 32-bit index range"); return MDB200_ECAPACITY; }
   Unit *u = &h->u;
   DeviceGuard g(u->device);
+  MDB_TRY(settle_upload(u));  // an earlier mdb200_upload_begin whose momenta nobody has waited for
   MDB_TRY(reserve_store(u, pn));
+  if (async_p && !u->ustream) {
+    MDB_CUDA(cudaStreamCreateWithFlags(&u->ustream, cudaStreamNonBlocking));
+    MDB_CUDA(cudaEventCreateWithFlags(&u->ev_q_up, cudaEventDisableTiming));
+    MDB_CUDA(cudaEventCreateWithFlags(&u->ev_p_up, cudaEventDisableTiming));
+    MDB_CUDA(cudaEventCreateWithFlags(&u->ev_perm, cudaEventDisableTiming));
+    MDB_CUDA(cudaEventCreateWithFlags(&u->ev_p_ready, cudaEventDisableTiming));
+  }
   if (pn > 0) {
-    // stage through the alt buffers (device-side repack keeps lane 3 == 0)
+    // positions are staged through the alt buffer (the device-side repack sets lane 3 = y, tile.cuh)
     MDB_CUDA(cudaMemcpyAsync(u->q_alt.ptr, q, sizeof(double) * 4 * (size_t)pn, cudaMemcpyHostToDevice, u->stream));
-    MDB_CUDA(cudaMemcpyAsync(u->p_alt.ptr, p, sizeof(double) * 4 * (size_t)pn, cudaMemcpyHostToDevice, u->stream));
     const unsigned nb = (unsigned)((pn + 255) / 256);
+    if (async_p) {
+      // behind the positions on the link (and behind whatever the unit's stream did with p before)
+      MDB_CUDA(cudaEventRecord(u->ev_q_up, u->stream));
+      MDB_CUDA(cudaStreamWaitEvent(u->ustream, u->ev_q_up, 0));
+      MDB_CUDA(cudaMemcpyAsync(u->p.ptr, p, sizeof(double) * 4 * (size_t)pn, cudaMemcpyHostToDevice, u->ustream));
+      MDB_CUDA(cudaEventRecord(u->ev_p_up, u->ustream));
+    } else {
+      MDB_CUDA(cudaMemcpyAsync(u->p_alt.ptr, p, sizeof(double) * 4 * (size_t)pn, cudaMemcpyHostToDevice, u->stream));
+    }
     k_pack_host_rows<<<nb, 256, 0, u->stream>>>((const double *)u->q_alt.ptr, u->q.ptr, (int)pn, 1);
-    k_pack_host_rows<<<nb, 256, 0, u->stream>>>((const double *)u->p_alt.ptr, u->p.ptr, (int)pn, 0);
+    if (!async_p) k_pack_host_rows<<<nb, 256, 0, u->stream>>>((const double *)u->p_alt.ptr, u->p.ptr, (int)pn, 0);
     if (type)
       MDB_CUDA(cudaMemcpyAsync(u->type.ptr, type, sizeof(int) * (size_t)pn, cudaMemcpyHostToDevice, u->stream));
     else
@@ -821,14 +898,27 @@ int mdb200_upload(mdb200_unit *h, const double (*q)[4], const double (*p)[4], co
     MDB_CUDA(cudaGetLastError());
   }
   MDB_TRY(store_replaced(u, pn));
+  u->p_pending = async_p && pn > 0;
   MDB_CUDA(cudaStreamSynchronize(u->stream));
   return MDB200_OK;
+}
+
+int mdb200_upload(mdb200_unit *h, const double (*q)[4], const double (*p)[4], const int *type, long long pn) {
+  return upload_impl(h, q, p, type, pn, false);
+}
+int mdb200_upload_begin(mdb200_unit *h, const double (*q)[4], const double (*p)[4], const int *type, long long pn) {
+  static const bool off = getenv("MDB200_UPLOAD_ASYNC") && atoi(getenv("MDB200_UPLOAD_ASYNC")) == 0;
+  return upload_impl(h, q, p, type, pn, !off);
 }
 
 // On-device initial states (generate.cu).  The makers append to the particle store like MDUnit::AddParticle; a store
 // that has been stepped (slot order != reference order) must be cleared first.
 static int gen_guard(mdb200_unit *h) {
   if (!h) { set_error("null unit"); return MDB200_EINVAL; }
+  {
+    DeviceGuard g(h->u.device);
+    MDB_TRY(settle_upload(&h->u));
+  }
   if (h->u.list_initialized) {
     set_error("the generators append to a freshly uploaded / generated store: call mdb200_clear first");
     return MDB200_EINVAL;
@@ -838,6 +928,7 @@ static int gen_guard(mdb200_unit *h) {
 int mdb200_clear(mdb200_unit *h) {
   if (!h) return MDB200_EINVAL;
   DeviceGuard g(h->u.device);
+  MDB_TRY(settle_upload(&h->u));
   return store_replaced(&h->u, 0);
 }
 int mdb200_generate_benchmark(mdb200_unit *h, double density, long long *added) {
@@ -1015,7 +1106,7 @@ static int unpack_units(mdb200_unit **units, int n, std::vector<Unit *> &us) {
 int mdb200_make_pairlist(mdb200_unit **units, int n) {
   std::vector<Unit *> us;
   MDB_TRY(unpack_units(units, n, us));
-  for (int i = 0; i < n; i++) MDB_TRY(materialize(us[i]));
+  for (int i = 0; i < n; i++) MDB_TRY(materialize(us[i], false));
   return make_pairlist(us.data(), n);
 }
 
@@ -1311,6 +1402,7 @@ int mdb200_measure_fp64_peak(int device, double *tflops) {
 int mdb200_synchronize(mdb200_unit *h) {
   if (!h) return MDB200_EINVAL;
   DeviceGuard g(h->u.device);
+  MDB_TRY(settle_upload(&h->u));
   MDB_CUDA(cudaStreamSynchronize(h->u.stream));
   return MDB200_OK;
 }

@@ -33,9 +33,13 @@ static inline unsigned nblk(long long n, int tpb = TPB) { return (unsigned)((n +
 // ---------------------------------------------------------------------------------------------
 // migration
 // ---------------------------------------------------------------------------------------------
-__global__ void k_begin_order(const int *__restrict__ slot_of_ref, int *__restrict__ ord, int pn) {
+// psrc (late momenta, unit.h): upload row of the local in slot r -- straight after an upload slot = reference index = row
+__global__ void k_begin_order(const int *__restrict__ slot_of_ref, int *__restrict__ ord, int *__restrict__ psrc, int pn) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < pn) ord[r] = slot_of_ref[r];
+  if (r < pn) {
+    ord[r] = slot_of_ref[r];
+    if (psrc) psrc[r] = r;
+  }
 }
 
 __device__ __forceinline__ bool over_boundary(int dir, const double4 &q, const Consts &c) {
@@ -65,14 +69,15 @@ __global__ void k_mig_compact(const double4 *__restrict__ q, const double4 *__re
                               const int *__restrict__ type, const int *__restrict__ ord,
                               const int *__restrict__ flags, const int *__restrict__ scanv,
                               int *__restrict__ ord_new, double4 *__restrict__ sq, double4 *__restrict__ sp,
-                              int *__restrict__ st, int pn) {
+                              int *__restrict__ st, const int *__restrict__ psrc, int *__restrict__ ss, int pn) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= pn) return;
   int h = ord[k];
   int j = scanv[k];
   if (flags[k]) {
     sq[j] = q[h];
-    sp[j] = p[h];
+    if (psrc) ss[j] = psrc[h];  // late momenta: the upload row travels instead
+    else sp[j] = p[h];
     st[j] = type[h];
   } else {
     ord_new[k - j] = h;
@@ -81,12 +86,13 @@ __global__ void k_mig_compact(const double4 *__restrict__ q, const double4 *__re
 
 __global__ void k_mig_unpack(double4 *__restrict__ q, double4 *__restrict__ p, int *__restrict__ type,
                              int *__restrict__ ord, const double4 *__restrict__ rq,
-                             const double4 *__restrict__ rp, const int *__restrict__ rt, int n, int pn,
-                             int tail) {
+                             const double4 *__restrict__ rp, const int *__restrict__ rt, int *__restrict__ psrc,
+                             const int *__restrict__ rs, int n, int pn, int tail) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   q[tail + i] = rq[i];
-  p[tail + i] = rp[i];
+  if (psrc) psrc[tail + i] = rs[i];
+  else p[tail + i] = rp[i];
   type[tail + i] = rt[i];
   ord[pn + i] = tail + i;
 }
@@ -100,8 +106,13 @@ int rebuild_begin_order(Unit *u) {
     MDB_TRY(u->mig_send_q.ensure(m)); MDB_TRY(u->mig_send_p.ensure(m)); MDB_TRY(u->mig_send_t.ensure(m));
     MDB_TRY(u->mig_recv_q.ensure(m)); MDB_TRY(u->mig_recv_p.ensure(m)); MDB_TRY(u->mig_recv_t.ensure(m));
   }
+  if (u->late_p) {
+    MDB_TRY(u->psrc.ensure((size_t)u->cap_p + 1));
+    MDB_TRY(u->psrc_alt.ensure((size_t)u->cap_p + 1));
+    MDB_TRY(u->mig_send_s.ensure(u->mig_send_t.cap));
+  }
   if (u->pn > 0) {
-    k_begin_order<<<nblk(u->pn), TPB, 0, u->stream>>>(u->slot_of_ref.ptr, u->ord.ptr, (int)u->pn);
+    k_begin_order<<<nblk(u->pn), TPB, 0, u->stream>>>(u->slot_of_ref.ptr, u->ord.ptr, u->late_p ? u->psrc.ptr : nullptr, (int)u->pn);
     u->launches++;
   }
   MDB_CUDA(cudaGetLastError());
@@ -131,10 +142,12 @@ int migrate_compact_pack(Unit *u, int dir, long long n_leave) {
   MDB_TRY(u->mig_send_q.ensure((size_t)n_leave));
   MDB_TRY(u->mig_send_p.ensure((size_t)n_leave));
   MDB_TRY(u->mig_send_t.ensure((size_t)n_leave));
+  if (u->late_p) MDB_TRY(u->mig_send_s.ensure((size_t)n_leave));
   MDB_TRY(exclusive_scan_i32(u->flags.ptr, u->scan.ptr, u->pn, u->scan_ws.ptr, u->stream, &u->launches));
   k_mig_compact<<<nblk(u->pn), TPB, 0, u->stream>>>(u->q.ptr, u->p.ptr, u->type.ptr, u->ord.ptr, u->flags.ptr,
                                                      u->scan.ptr, u->ord_alt.ptr, u->mig_send_q.ptr,
-                                                     u->mig_send_p.ptr, u->mig_send_t.ptr, (int)u->pn);
+                                                     u->mig_send_p.ptr, u->mig_send_t.ptr,
+                                                     u->late_p ? u->psrc.ptr : nullptr, u->mig_send_s.ptr, (int)u->pn);
   u->launches++;
   MDB_CUDA(cudaGetLastError());
   std::swap(u->ord, u->ord_alt);
@@ -163,6 +176,8 @@ int ensure_capacity(Unit *u, long long need_p, long long need_t) {
     grow = true;
   }
   if (!grow) return MDB200_OK;
+  // momenta still travelling into p (mdb200_upload_begin): let them arrive before the buffer is replaced
+  if (u->p_pending && u->ustream) MDB_CUDA(cudaStreamSynchronize(u->ustream));
   cudaStream_t st = u->stream;
   MDB_TRY(u->q.ensure((size_t)nct + 1, true, st));
   MDB_TRY(u->q_alt.ensure((size_t)nct + 1, true, st));  // ghosts live in both position buffers
@@ -193,13 +208,15 @@ int ensure_capacity(Unit *u, long long need_p, long long need_t) {
   return MDB200_OK;
 }
 
-int migrate_unpack(Unit *d, const double4 *rq, const double4 *rp, const int *rt, long long n) {
+int migrate_unpack(Unit *d, const double4 *rq, const double4 *rp, const int *rt, long long n, const int *rs) {
   if (n == 0) return MDB200_OK;
+  if (d->late_p && !rs) { set_error("late momenta: a migration without upload rows"); return MDB200_EINVAL; }
   // arrivals go to fresh slots past everything in use; the cell sort compacts afterwards
   long long tail = d->scratch_tail;
   MDB_TRY(ensure_capacity(d, tail + n, tail + n));
-  k_mig_unpack<<<nblk(n), TPB, 0, d->stream>>>(d->q.ptr, d->p.ptr, d->type.ptr, d->ord.ptr, rq, rp, rt, (int)n,
-                                               (int)d->pn, (int)tail);
+  if (d->late_p) MDB_TRY(d->psrc.ensure((size_t)(tail + n) + 1, true, d->stream));
+  k_mig_unpack<<<nblk(n), TPB, 0, d->stream>>>(d->q.ptr, d->p.ptr, d->type.ptr, d->ord.ptr, rq, rp, rt,
+                                               d->late_p ? d->psrc.ptr : nullptr, rs, (int)n, (int)d->pn, (int)tail);
   d->launches++;
   MDB_CUDA(cudaGetLastError());
   d->pn += n;
@@ -302,7 +319,8 @@ __global__ void k_permute_locals(const double4 *__restrict__ q, const double4 *_
                                  const int *__restrict__ type, const int *__restrict__ ord,
                                  const int *__restrict__ items, double4 *__restrict__ q2,
                                  double4 *__restrict__ p2, int *__restrict__ type2,
-                                 int *__restrict__ ref_of_slot, int *__restrict__ slot_of_ref, int pn) {
+                                 int *__restrict__ ref_of_slot, int *__restrict__ slot_of_ref,
+                                 const int *__restrict__ psrc, int *__restrict__ psrc2, int pn) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= pn) return;
   int k = items[s];
@@ -310,7 +328,8 @@ __global__ void k_permute_locals(const double4 *__restrict__ q, const double4 *_
   double4 qq = q[h];
   qq.w = qq.y;  // lane 3 of a position record repeats y (tile.cuh)
   q2[s] = qq;
-  p2[s] = p[h];
+  if (psrc) psrc2[s] = psrc[h];  // late momenta: gathered from the upload rows once they have arrived (api.cu)
+  else p2[s] = p[h];
   type2[s] = type[h];
   ref_of_slot[s] = k;
   slot_of_ref[k] = s;
@@ -354,12 +373,13 @@ int cell_sort_locals(Unit *u) {
     k_permute_locals<<<nblk(u->pn), TPB, 0, u->stream>>>(u->q.ptr, u->p.ptr, u->type.ptr, u->ord.ptr,
                                                           u->cell_items.ptr, u->q_alt.ptr, u->p_alt.ptr,
                                                           u->type_alt.ptr, u->ref_of_slot.ptr, u->slot_of_ref.ptr,
-                                                          (int)u->pn);
+                                                          u->late_p ? u->psrc.ptr : nullptr, u->psrc_alt.ptr, (int)u->pn);
     u->launches++;
     MDB_CUDA(cudaGetLastError());
     std::swap(u->q, u->q_alt);
     std::swap(u->p, u->p_alt);
     std::swap(u->type, u->type_alt);
+    if (u->late_p) std::swap(u->psrc, u->psrc_alt);
   }
   u->tn = u->pn;
   u->scratch_tail = u->pn;

@@ -442,7 +442,7 @@ int comm_migrate(Unit **us, int n, int dir, const long long *n_leave) {
     if (!is_remote(u, dir)) {
       Unit *d = u->nbr[dir];
       cudaSetDevice(d->device);
-      MDB_TRY(migrate_unpack(d, u->mig_send_q.ptr, u->mig_send_p.ptr, u->mig_send_t.ptr, n_leave[i]));
+      MDB_TRY(migrate_unpack(d, u->mig_send_q.ptr, u->mig_send_p.ptr, u->mig_send_t.ptr, n_leave[i], u->late_p ? u->mig_send_s.ptr : nullptr));
       continue;
     }
     cudaSetDevice(u->device);

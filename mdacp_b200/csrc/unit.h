@@ -225,6 +225,15 @@ struct Unit {
   Unit *src[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // source when receiving in dir (neighbour in opposite dir)
   bool comm_ready = false;
   std::vector<void *> deferred_free;  // replaced q / q_alt allocations still mapped by neighbour processes
+  // Momenta still on their way from the host (mdb200_upload_begin): they travel on `ustream` into p while the first
+  // pair-list build -- which needs positions only -- runs on `stream`.  A single unit of a single process carries the
+  // upload row of every local through migration and cell sort (psrc) and gathers the momenta into slot order once
+  // they have arrived; everybody else just waits for the copy first (api.cu: settle_upload / make_pairlist).
+  cudaStream_t ustream = 0;
+  cudaEvent_t ev_q_up = 0, ev_p_up = 0, ev_perm = 0, ev_p_ready = 0;
+  bool p_pending = false;         // the copy of the momenta has been queued and nobody has waited for it yet
+  bool late_p = false;            // this rebuild carries psrc instead of p
+  DevBuf<int> psrc, psrc_alt, mig_send_s;
   cudaStream_t cstream = 0;       // second stream for the overlapped ghost exchange (created on demand)
   cudaEvent_t ev_drift = 0, ev_ghost = 0;
 
@@ -282,7 +291,7 @@ int generate_initial_velocity(Unit *u, double v0, int seed);
 int rebuild_begin_order(Unit *u);                                        // ord[r] = slot_of_ref[r]
 int migrate_flag_and_count(Unit *u, int dir, long long *n_leave);        // sync
 int migrate_compact_pack(Unit *u, int dir, long long n_leave);           // keepers compacted, leavers packed
-int migrate_unpack(Unit *dst, const double4 *rq, const double4 *rp, const int *rt, long long n);
+int migrate_unpack(Unit *dst, const double4 *rq, const double4 *rp, const int *rt, long long n, const int *rs = nullptr);
 int wrap_periodic(Unit *u);
 int cell_sort_locals(Unit *u);
 int ghost_compose(Unit *u);          // after the six border set-ups of a rebuild (one unit that is all its own neighbours)

@@ -12,6 +12,9 @@ sys.path.insert(0, ROOT)
 from mdacp_b200 import driver, hostlib  # noqa: E402
 
 
+BEGIN = os.environ.get("E2E_UPLOAD_BEGIN", "1") != "0"
+
+
 def main():
     UL = float(sys.argv[1]) if len(sys.argv) > 1 else 284.0
     K = int(sys.argv[2]) if len(sys.argv) > 2 else 20
@@ -36,7 +39,7 @@ def main():
     unit.synchronize()
     for rep in range(3):
         t = [time.time()]
-        unit.upload4(qh[:n], ph[:n]); unit.synchronize(); t.append(time.time())
+        (unit.upload4_begin if BEGIN else unit.upload4)(qh[:n], ph[:n]); t.append(time.time())   # no synchronize: it would wait for the momenta
         mdm.Calculate(); unit.synchronize(); t.append(time.time())
         obs = mdm.observables(); unit.synchronize(); t.append(time.time())
         for i in range(K - 1):
