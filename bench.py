@@ -609,7 +609,8 @@ def run_ours(args):
                        "timing": "CUDA events on the unit's stream, max over ranks; host wall %.3f s" % (tw1 - tw0)},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "seconds": e2e_s, "includes": "upload from pinned host, first pair-list build, K steps, "
+                    "seconds": e2e_s, "includes": "upload from pinned host (mdb200_upload_begin: the momenta travel during "
+                                                  "the first pair-list build), first pair-list build, K steps, "
                                                   "observations, download of q and p"},
             "gpu_launches": launches,
             "roofline": roofline,

@@ -703,7 +703,20 @@ int reserve_store(Unit *u, long long pn) {
   // position buffers -- the path that re-exports the peer-to-peer windows and parks replaced allocations
   static const bool small_cap = getenv("MDB200_DEBUG_SMALL_CAPACITY") != nullptr;
   if (small_cap) { need_p = pn + 64; need_t = pn + 64; }
-  return ensure_capacity(u, need_p, need_t);
+  MDB_TRY(ensure_capacity(u, need_p, need_t));
+  // what mdb200_upload_begin and the late-momenta build need, created with the store rather than inside somebody's
+  // timed first call (stream / event creation and cudaMalloc synchronise the device)
+  if (!u->ustream) {
+    MDB_CUDA(cudaStreamCreateWithFlags(&u->ustream, cudaStreamNonBlocking));
+    MDB_CUDA(cudaEventCreateWithFlags(&u->ev_q_up, cudaEventDisableTiming));
+    MDB_CUDA(cudaEventCreateWithFlags(&u->ev_p_up, cudaEventDisableTiming));
+    MDB_CUDA(cudaEventCreateWithFlags(&u->ev_perm, cudaEventDisableTiming));
+    MDB_CUDA(cudaEventCreateWithFlags(&u->ev_p_ready, cudaEventDisableTiming));
+  }
+  MDB_TRY(u->psrc.ensure((size_t)u->cap_p + 1));
+  MDB_TRY(u->psrc_alt.ensure((size_t)u->cap_p + 1));
+  MDB_TRY(u->mig_send_s.ensure((size_t)(need_p / 64) + 4096));
+  return MDB200_OK;
 }
 
 // the store now holds pn particles in reference order (slot = reference index), no ghosts, no pair list
@@ -867,13 +880,6 @@ static int upload_impl(mdb200_unit *h, const double (*q)[4], const double (*p)[4
   DeviceGuard g(u->device);
   MDB_TRY(settle_upload(u));  // an earlier mdb200_upload_begin whose momenta nobody has waited for
   MDB_TRY(reserve_store(u, pn));
-  if (async_p && !u->ustream) {
-    MDB_CUDA(cudaStreamCreateWithFlags(&u->ustream, cudaStreamNonBlocking));
-    MDB_CUDA(cudaEventCreateWithFlags(&u->ev_q_up, cudaEventDisableTiming));
-    MDB_CUDA(cudaEventCreateWithFlags(&u->ev_p_up, cudaEventDisableTiming));
-    MDB_CUDA(cudaEventCreateWithFlags(&u->ev_perm, cudaEventDisableTiming));
-    MDB_CUDA(cudaEventCreateWithFlags(&u->ev_p_ready, cudaEventDisableTiming));
-  }
   if (pn > 0) {
     // positions are staged through the alt buffer (the device-side repack sets lane 3 = y, tile.cuh)
     MDB_CUDA(cudaMemcpyAsync(u->q_alt.ptr, q, sizeof(double) * 4 * (size_t)pn, cudaMemcpyHostToDevice, u->stream));
