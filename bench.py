@@ -431,7 +431,7 @@ def run_ours(args):
         mdm.SetSeed(12345)
 
     # --- state resident in HBM: upload, first build, warm-up (untimed) ---
-    unit.upload4(qh[:n_local], ph[:n_local])
+    unit.upload4_begin(qh[:n_local], ph[:n_local])   # the same entry the timed e2e region uses below (warms it up)
     mdm.MakePairList()
     W, K = args.warmup, args.steps
     obs = None

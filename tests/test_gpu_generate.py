@@ -142,3 +142,30 @@ def test_device_generators_match_host_generators(L, nunits):
             unit.clear()
     finally:
         mdm.close()
+
+
+def test_device_generator_at_the_benchmark_size():
+    """BASELINE.json configs[1]: 16,034,412 particles (MDB200_TEST_UNIT_LENGTH shrinks it): the on-device maker gives the
+    host maker's positions bit for bit and its momenta to an ulp, and a step runs from the generated store."""
+    import os
+    UL = float(os.environ.get("MDB200_TEST_UNIT_LENGTH", "284"))
+    mdm = driver.MDManager({"Mode": "Benchmark", "UnitLength": repr(UL), "TimeStep": "0.001"}, cutoff=3.0)
+    try:
+        unit = mdm.GetMDUnit(0)
+        s, e = mdm.GetRect(0)
+        n = unit.generate_benchmark(0.7)
+        unit.generate_initial_velocity(1.0, 0)
+        if UL == 284.0:
+            assert n == 16034412
+        d = unit.download(want_type=False)
+        qh = hostlib.benchmark_config(s, e, 0.7, 0)
+        assert n == len(qh) and np.array_equal(d["q"], qh[:, :3])
+        del qh
+        ph = hostlib.initial_velocity(n, 1.0, 0)
+        assert np.max(np.abs(d["p"] - ph[:, :3])) <= 8 * ULP
+        del ph, d
+        mdm.Calculate(3)
+        o = mdm.observables()
+        assert o["N"] == n and abs(o["K"] - 0.5) < 1e-3   # |p| = 1 for every particle
+    finally:
+        mdm.close()
