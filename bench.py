@@ -410,11 +410,30 @@ def run_ours(args):
     elif wl == "langevin":
         cap = int(vol * 0.70 * 1.05) + 65536
     else:
-        cap = int(vol * 0.374 * 1.3) + 65536
+        # two balls of radius L_y / 4 at density 0.374 (collision.cc:54-61), wherever they fall among the units: a unit holds
+        # at most both of them (the box is mostly vacuum: sizing by its volume would pin 13 GB of host memory)
+        r_ball = 0.25 * 60.0 * float(args.collision_scale)
+        cap = min(int(vol * 0.374 * 1.3), int(2 * 4.19 * r_ball ** 3 * 0.374 * 1.15)) + 65536
     q_pin = torch.zeros((cap, 4), dtype=torch.float64).pin_memory()
     p_pin = torch.zeros((cap, 4), dtype=torch.float64).pin_memory()
     qh, ph = q_pin.numpy(), p_pin.numpy()
-    if wl in ("benchmark", "shipped"):
+    if args.device_init:
+        # the same makers on the device (generate.cu): positions bit-identical to the host makers', momenta
+        # to an ulp (CUDA's cos / sin) -- an alternative provenance of the initial state, hence a flag
+        if wl in ("benchmark", "shipped"):
+            n_local = unit.generate_benchmark(DENSITY)
+            unit.generate_initial_velocity(V0, rank)
+        elif wl == "langevin":
+            n_local = unit.generate_lattice(0.70)
+            unit.generate_initial_velocity(1.8, rank)
+        else:
+            L = mdm.sinfo.L
+            n_local = unit.generate_ball([L[0] * 0.25, L[1] * 0.5, L[2] * 0.5], L[1] * 0.25, 1.0, 0.374)
+            n_local += unit.generate_ball([L[0] * 0.75, L[1] * 0.5, L[2] * 0.5], L[1] * 0.25, -1.0, 0.374)
+        unit.synchronize()
+        if n_local > cap:
+            raise MemoryError("pinned host buffers too small for %d particles" % n_local)
+    elif wl in ("benchmark", "shipped"):
         n_local = hostlib.benchmark_config(s, e, DENSITY, rank, out=qh).shape[0]
         hostlib.initial_velocity(n_local, V0, rank, out=ph)
     elif wl == "langevin":
@@ -432,13 +451,15 @@ def run_ours(args):
     t_gen = time.time() - t0
     n_total = int(allsum(float(n_local)))
     n_max = int(allmax(float(n_local)))
-    log("[rank %d] %s unit grid %s box %s..%s  N_local=%d N_total=%d  (generated in %.1f s)" % (
-        rank, wl, grid, [round(x, 3) for x in s], [round(x, 3) for x in e], n_local, n_total, t_gen))
+    log("[rank %d] %s unit grid %s box %s..%s  N_local=%d N_total=%d  (generated %sin %.2f s)" % (
+        rank, wl, grid, [round(x, 3) for x in s], [round(x, 3) for x in e], n_local, n_total,
+        "on the device " if args.device_init else "", t_gen))
     if wl == "langevin":
         mdm.SetSeed(12345)
 
     # --- state resident in HBM: upload, first build, warm-up (untimed) ---
-    unit.upload4_begin(qh[:n_local], ph[:n_local])   # the same entry the timed e2e region uses below (warms it up)
+    if not args.device_init:
+        unit.upload4_begin(qh[:n_local], ph[:n_local])   # the same entry the timed e2e region uses below (warms it up)
     mdm.MakePairList()
     W, K = args.warmup, args.steps
     obs = None
@@ -597,7 +618,7 @@ def run_ours(args):
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": "f64", "data": "synthetic" + (" (initial state made on the device)" if args.device_init else ""),
             "config": {"workload": "%s; %d particles on rank 0, unit grid %dx%dx%d; BASELINE.json configs[%d]" % (
                            wl_text, n_local, grid[0], grid[1], grid[2],
                            {"benchmark": 1 if world == 1 else 2, "shipped": 0, "langevin": 3, "collision": 4}[wl]),
@@ -643,6 +664,7 @@ def main():
     ap.add_argument("--workload", default="benchmark", choices=["benchmark", "shipped", "langevin", "collision"])
     ap.add_argument("--collision-scale", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--device-init", action="store_true")    # initial state by the on-device makers (generate.cu)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
